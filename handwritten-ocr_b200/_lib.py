@@ -1,0 +1,104 @@
+"""ctypes binding of libocrb200.so (include/ocrb200.h).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_double, c_float, c_int32, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libocrb200.so")
+
+
+class OcrbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_P = c_void_p
+_I = c_int32
+_L = c_int64
+_F = c_float
+
+# name -> argtypes (all return int unless listed in _SPECIAL)
+_SIGS = {
+    "ocrb_levenshtein_batch": [_P, _P, _P, _P, _I, _I, _P, _P, _P],
+    "ocrb_lcs_align_batch": [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "ocrb_rgb2gray_u8": [_P, _P, _I, _I, _I, _P],
+    "ocrb_clahe_u8": [_P, _P, _I, _I, _I, _P, _P],
+    "ocrb_adaptive_gauss_thresh_u8": [_P, _P, _I, _I, _I, _P],
+    "ocrb_sharpen3x3_u8": [_P, _P, _I, _I, _I, _I, _P],
+    "ocrb_deskew_angle": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "ocrb_warp_affine_cubic_u8": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "ocrb_smart_resize_host": [_I, _I, _I, _L, _L, _P, _P],
+    "ocrb_resize_bicubic_aa_u8": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ocrb_normalize_patchify": [_P, _P, _I, _I, _I, _I, _P, _I, _P],
+    "ocrb_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P],
+    "ocrb_gemv_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P, _F, _P],
+    "ocrb_rmsnorm_bf16": [_P, _L, _P, _P, _L, _I, _I, _F, _P],
+    "ocrb_rope_vision": [_P, _I, _I, _I, _P, _P, _P],
+    "ocrb_rope_text": [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _P],
+    "ocrb_attention_varlen": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    "ocrb_kv_write_prefill": [_P, _L, _P, _L, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
+    "ocrb_decode_attention": [_P, _L, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _F, _P, _L, _P, _I, _P],
+    "ocrb_argmax_step": [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
+    "ocrb_embed_gather": [_P, _P, _P, _I, _I, _P],
+    "ocrb_rows_copy": [_P, _L, _P, _P, _L, _P, _I, _I, _P],
+    "ocrb_decode_rope_table": [_P, _P, _P, _I, _I, _P, _P, _P],
+}
+
+EXPORTS = ["ocrb_version", "ocrb_last_error", "ocrb_launch_count", "ocrb_launch_count_reset"] + list(_SIGS)
+
+
+def load():
+    """Load the library (once).  Raises OcrbError when it is missing: there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OcrbError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C handwritten-ocr_b200/csrc`). This package has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    L.ocrb_version.restype = c_int32
+    L.ocrb_last_error.restype = ctypes.c_char_p
+    L.ocrb_launch_count.restype = c_uint64
+    L.ocrb_launch_count_reset.restype = None
+    for name, args in _SIGS.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = c_int32
+    _lib = L
+    return L
+
+
+def call(name: str, *args):
+    L = load()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise OcrbError(f"{name} failed ({rc}): {L.ocrb_last_error().decode(errors='replace')}")
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / numpy array; None -> NULL."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().ocrb_launch_count())
+
+
+def launch_count_reset() -> None:
+    load().ocrb_launch_count_reset()

@@ -1,0 +1,435 @@
+// Batched greedy decode hot path (HF generation loop, utils.py:2743-2806, one token per sequence
+// per step): weight-streaming skinny GEMM ("GEMV", HBM-bound: every weight byte is read exactly once
+// per step for all B sequences) with HF's rounding points fused in, and split-KV paged attention.
+#include "common.cuh"
+#include <math.h>
+
+namespace ocrb {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int GV_WARPS = 8;       // warps per CTA
+constexpr int GV_ROWS = 2;        // weight rows per warp (a gate/up pair under SwiGLU)
+constexpr int GV_MAXB = 8;        // sequences per pass
+
+__device__ __forceinline__ uint4 ld_stream(const void *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void unpack8(const uint4 &raw, float *f) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f[2 * k] = __uint_as_float(w[k] << 16);
+    f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+  }
+}
+
+__device__ __forceinline__ float silu_bf16(float g) {
+  // torch silu on bf16: computed in fp32 as x / (1 + exp(-x)), rounded to bf16
+  return bf16_round(g / (1.0f + expf(-g)));
+}
+
+__device__ __forceinline__ float gelu_erf_bf16(float x) {
+  return bf16_round(0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)));
+}
+
+// D[b, n] = epilogue( sum_k X[b,k] * W[n,k] ).  One warp owns GV_ROWS consecutive weight rows (under
+// SwiGLU: rows n and n+64 of a 128-row [gate64|up64] tile) and streams them once with 16-byte loads;
+// X (optionally RMS-normalised on the fly, HF rounding) sits in shared memory as bf16.
+template <int NB, bool NORM>
+__global__ void __launch_bounds__(GV_WARPS * 32)
+gemv_kernel(const bf16 *__restrict__ X, long long ldx, const bf16 *__restrict__ W, long long ldw, bf16 *__restrict__ D,
+            long long ldd, int N, int K, const bf16 *__restrict__ bias, const bf16 *__restrict__ residual, long long ldr,
+            int epilogue, const bf16 *__restrict__ norm_w, float eps, bool x_in_smem) {
+  extern __shared__ __align__(16) uint8_t gv_smem[];
+  bf16 *xs = reinterpret_cast<bf16 *>(gv_smem);  // [NB][K] when x_in_smem
+  __shared__ float s_red[GV_WARPS][NB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kvec = K >> 3;
+
+  if (NORM) {
+    // HF RMSNorm prologue: rstd per sequence, then xs = bf16( w * bf16(x * rstd) )
+    float ss[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) ss[b] = 0.f;
+    for (int v = threadIdx.x; v < kvec; v += GV_WARPS * 32) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const uint4 raw = *reinterpret_cast<const uint4 *>(X + (size_t)b * ldx + v * 8);
+        float f[8];
+        unpack8(raw, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ss[b] = fmaf(f[k], f[k], ss[b]);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float v = ss[b];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_red[warp][b] = v;
+    }
+    __syncthreads();
+    float rstd[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < GV_WARPS; ++w) t += s_red[w][b];
+      rstd[b] = rsqrtf(t / (float)K + eps);
+    }
+    for (int v = threadIdx.x; v < kvec; v += GV_WARPS * 32) {
+      const uint4 wraw = *reinterpret_cast<const uint4 *>(norm_w + v * 8);
+      float wf[8];
+      unpack8(wraw, wf);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const uint4 raw = *reinterpret_cast<const uint4 *>(X + (size_t)b * ldx + v * 8);
+        float f[8];
+        unpack8(raw, f);
+        uint4 o;
+        bf16 *oe = reinterpret_cast<bf16 *>(&o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) oe[k] = __float2bfloat16_rn(wf[k] * bf16_round(f[k] * rstd[b]));
+        *reinterpret_cast<uint4 *>(xs + (size_t)b * K + v * 8) = o;
+      }
+    }
+    __syncthreads();
+  } else if (x_in_smem) {
+    for (int v = threadIdx.x; v < kvec; v += GV_WARPS * 32)
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        *reinterpret_cast<uint4 *>(xs + (size_t)b * K + v * 8) =
+            *reinterpret_cast<const uint4 *>(X + (size_t)b * ldx + v * 8);
+    __syncthreads();
+  }
+  const bf16 *xsrc = (NORM || x_in_smem) ? xs : X;
+  const long long xstride = (NORM || x_in_smem) ? (long long)K : ldx;
+
+  // rows of this warp
+  const int pair = blockIdx.x * GV_WARPS + warp;
+  int n0, n1, out_col;
+  if (epilogue == OCRB_EPI_SWIGLU) {
+    const int tile = pair >> 6, j = pair & 63;
+    n0 = tile * 128 + j;       // gate row
+    n1 = n0 + 64;              // up row
+    out_col = tile * 64 + j;
+    if (n1 >= N) return;
+  } else {
+    n0 = pair * 2;
+    n1 = n0 + 1;
+    out_col = n0;
+    if (n0 >= N) return;
+  }
+  const bool has1 = n1 < N;
+  const bf16 *w0 = W + (size_t)n0 * ldw;
+  const bf16 *w1 = W + (size_t)(has1 ? n1 : n0) * ldw;
+
+  float acc0[NB], acc1[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) acc0[b] = acc1[b] = 0.f;
+
+  int v = lane;
+  // main loop, 2x unrolled: 4 independent 16-byte weight loads in flight per lane
+  for (; v + 32 < kvec; v += 64) {
+    const uint4 a0 = ld_stream(w0 + v * 8), a1 = ld_stream(w1 + v * 8);
+    const uint4 c0 = ld_stream(w0 + (v + 32) * 8), c1 = ld_stream(w1 + (v + 32) * 8);
+    float fa0[8], fa1[8], fc0[8], fc1[8];
+    unpack8(a0, fa0); unpack8(a1, fa1); unpack8(c0, fc0); unpack8(c1, fc1);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float x[8];
+      unpack8(*reinterpret_cast<const uint4 *>(xsrc + (size_t)b * xstride + v * 8), x);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc0[b] = fmaf(fa0[k], x[k], acc0[b]); acc1[b] = fmaf(fa1[k], x[k], acc1[b]); }
+      unpack8(*reinterpret_cast<const uint4 *>(xsrc + (size_t)b * xstride + (v + 32) * 8), x);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc0[b] = fmaf(fc0[k], x[k], acc0[b]); acc1[b] = fmaf(fc1[k], x[k], acc1[b]); }
+    }
+  }
+  for (; v < kvec; v += 32) {
+    const uint4 a0 = ld_stream(w0 + v * 8), a1 = ld_stream(w1 + v * 8);
+    float fa0[8], fa1[8];
+    unpack8(a0, fa0); unpack8(a1, fa1);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float x[8];
+      unpack8(*reinterpret_cast<const uint4 *>(xsrc + (size_t)b * xstride + v * 8), x);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc0[b] = fmaf(fa0[k], x[k], acc0[b]); acc1[b] = fmaf(fa1[k], x[k], acc1[b]); }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc0[b] += __shfl_xor_sync(0xffffffffu, acc0[b], o);
+      acc1[b] += __shfl_xor_sync(0xffffffffu, acc1[b], o);
+    }
+  }
+  // epilogue: lane b finishes sequence b
+  if (lane < NB) {
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      if (lane == b) { r0 = acc0[b]; r1 = acc1[b]; }
+    if (bias) {
+      r0 += __bfloat162float(bias[n0]);
+      if (has1) r1 += __bfloat162float(bias[n1]);
+    }
+    r0 = bf16_round(r0);
+    r1 = bf16_round(r1);
+    bf16 *drow = D + (size_t)lane * ldd;
+    if (epilogue == OCRB_EPI_SWIGLU) {
+      drow[out_col] = __float2bfloat16_rn(silu_bf16(r0) * r1);
+    } else {
+      if (epilogue == OCRB_EPI_RESIDUAL) {
+        const bf16 *rr = residual + (size_t)lane * ldr;
+        r0 += __bfloat162float(rr[n0]);
+        if (has1) r1 += __bfloat162float(rr[n1]);
+      } else if (epilogue == OCRB_EPI_GELU) {
+        r0 = gelu_erf_bf16(r0);
+        r1 = gelu_erf_bf16(r1);
+      }
+      if (has1) {
+        __nv_bfloat162 o2 = __floats2bfloat162_rn(r0, r1);
+        *reinterpret_cast<__nv_bfloat162 *>(drow + n0) = o2;
+      } else {
+        drow[n0] = __float2bfloat16_rn(r0);
+      }
+    }
+  }
+}
+
+// ───────────── paged decode attention, split over the KV length ─────────────
+// grid = (n_splits, n_kv, B), 128 threads.  Each CTA serves all G = n_q/n_kv query heads of one KV
+// head over one chunk of the context.  Phase 1: lane-per-key dot products (q in shared memory, fp32).
+// Phase 2: chunk max / exp / sum.  Phase 3: thread-per-dim P.V.  Partial (m, l, acc) go to split_ws;
+// a second kernel merges the splits.  The CTA with split 0 also applies mRoPE to the new token's
+// q,k (bf16 arithmetic, as HF) and appends k,v to the cache; every CTA re-derives the roped q,k it
+// needs from qkv, so there is no inter-CTA dependency.
+constexpr int DA_MAXG = 8;
+constexpr int DA_THREADS = 128;
+
+__device__ __forceinline__ float rope_elem_bf16(const bf16 *vec, int i, int hd, const bf16 *c, const bf16 *s) {
+  const int half = hd >> 1;
+  const float x = __bfloat162float(vec[i]);
+  const float other = (i < half) ? -__bfloat162float(vec[i + half]) : __bfloat162float(vec[i - half]);
+  const float t = bf16_round(x * __bfloat162float(c[i]));
+  const float u = bf16_round(other * __bfloat162float(s[i]));
+  return bf16_round(t + u);
+}
+
+__global__ void __launch_bounds__(DA_THREADS)
+decode_attn_partial_kernel(const bf16 *__restrict__ qkv, long long ldqkv, bf16 *__restrict__ k_cache,
+                           bf16 *__restrict__ v_cache, const int32_t *__restrict__ block_table, int max_pages,
+                           const int32_t *__restrict__ ctx_len, int page_size, int n_q, int n_kv, int hd,
+                           const bf16 *__restrict__ cosT, const bf16 *__restrict__ sinT, float scale,
+                           float *__restrict__ split_ws, int n_splits, int chunk) {
+  extern __shared__ __align__(16) uint8_t da_smem[];
+  const int G = n_q / n_kv;
+  float *s_q = reinterpret_cast<float *>(da_smem);   // [G][hd]
+  float *s_knew = s_q + G * hd;                      // [hd] roped new key
+  float *s_p = s_knew + hd;                          // [G][chunk]
+  __shared__ float s_m[DA_MAXG], s_l[DA_MAXG];
+  const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ctx = ctx_len[b];          // tokens already cached; the new token sits at position ctx
+  const int total = ctx + 1;
+  const bf16 *row = qkv + (size_t)b * ldqkv;
+  const bf16 *c = cosT + (size_t)b * hd, *s = sinT + (size_t)b * hd;
+  const bf16 *knew = row + (size_t)n_q * hd + (size_t)kvh * hd;
+  const bf16 *vnew = row + (size_t)(n_q + n_kv) * hd + (size_t)kvh * hd;
+  for (int i = tid; i < G * hd; i += DA_THREADS) {
+    const int g = i / hd, d = i - g * hd;
+    s_q[i] = rope_elem_bf16(row + (size_t)(kvh * G + g) * hd, d, hd, c, s);
+  }
+  for (int d = tid; d < hd; d += DA_THREADS) s_knew[d] = rope_elem_bf16(knew, d, hd, c, s);
+  __syncthreads();
+  const size_t tok_stride = (size_t)n_kv * hd;
+  if (split == 0) {
+    // append the new token's k (roped) and v
+    const int page = block_table[(size_t)b * max_pages + ctx / page_size];
+    const size_t dst = ((size_t)page * page_size + ctx % page_size) * tok_stride + (size_t)kvh * hd;
+    for (int d = tid; d < hd; d += DA_THREADS) {
+      k_cache[dst + d] = __float2bfloat16_rn(s_knew[d]);
+      v_cache[dst + d] = vnew[d];
+    }
+  }
+  const int k0 = split * chunk;
+  const int k1 = min(total, k0 + chunk);
+  float *ws = split_ws + (((size_t)b * n_q + (size_t)kvh * G) * n_splits + split) * (hd + 2);
+  const size_t ws_head = (size_t)n_splits * (hd + 2);
+  if (k0 >= k1) {
+    for (int g = tid; g < G; g += DA_THREADS) { ws[g * ws_head] = -INFINITY; ws[g * ws_head + 1] = 0.f; }
+    return;
+  }
+  // phase 1: scores
+  for (int key = k0 + tid; key < k1; key += DA_THREADS) {
+    float sc[DA_MAXG];
+#pragma unroll
+    for (int g = 0; g < DA_MAXG; ++g) sc[g] = 0.f;
+    if (key == ctx) {
+      for (int d = 0; d < hd; ++d) {
+        const float kv = s_knew[d];
+#pragma unroll
+        for (int g = 0; g < DA_MAXG; ++g)
+          if (g < G) sc[g] = fmaf(s_q[g * hd + d], kv, sc[g]);
+      }
+    } else {
+      const int page = block_table[(size_t)b * max_pages + key / page_size];
+      const bf16 *kr = k_cache + ((size_t)page * page_size + key % page_size) * tok_stride + (size_t)kvh * hd;
+      for (int d8 = 0; d8 < hd; d8 += 8) {
+        float kf[8];
+        unpack8(*reinterpret_cast<const uint4 *>(kr + d8), kf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+#pragma unroll
+          for (int g = 0; g < DA_MAXG; ++g)
+            if (g < G) sc[g] = fmaf(s_q[g * hd + d8 + e], kf[e], sc[g]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < DA_MAXG; ++g)
+      if (g < G) s_p[g * chunk + (key - k0)] = sc[g] * scale;
+  }
+  __syncthreads();
+  // phase 2: per-head max / exp / sum (warp w handles heads w, w+4, ...)
+  const int nk = k1 - k0;
+  for (int g = warp; g < G; g += DA_THREADS / 32) {
+    float m = -INFINITY;
+    for (int i = lane; i < nk; i += 32) m = fmaxf(m, s_p[g * chunk + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float l = 0.f;
+    for (int i = lane; i < nk; i += 32) {
+      const float p = __expf(s_p[g * chunk + i] - m);
+      s_p[g * chunk + i] = p;
+      l += p;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (lane == 0) { s_m[g] = m; s_l[g] = l; }
+  }
+  __syncthreads();
+  // phase 3: P.V, thread per output dim
+  for (int d = tid; d < hd; d += DA_THREADS) {
+    float acc[DA_MAXG];
+#pragma unroll
+    for (int g = 0; g < DA_MAXG; ++g) acc[g] = 0.f;
+    for (int key = k0; key < k1; ++key) {
+      float vv;
+      if (key == ctx) vv = __bfloat162float(vnew[d]);
+      else {
+        const int page = block_table[(size_t)b * max_pages + key / page_size];
+        vv = __bfloat162float(v_cache[((size_t)page * page_size + key % page_size) * tok_stride + (size_t)kvh * hd + d]);
+      }
+#pragma unroll
+      for (int g = 0; g < DA_MAXG; ++g)
+        if (g < G) acc[g] = fmaf(s_p[g * chunk + (key - k0)], vv, acc[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < DA_MAXG; ++g)
+      if (g < G) ws[g * ws_head + 2 + d] = acc[g];
+  }
+  for (int g = tid; g < G; g += DA_THREADS) { ws[g * ws_head] = s_m[g]; ws[g * ws_head + 1] = s_l[g]; }
+}
+
+// grid = (n_q, B), hd threads
+__global__ void decode_attn_combine_kernel(const float *__restrict__ split_ws, int n_q, int n_splits, int hd,
+                                           bf16 *__restrict__ out, long long ldo) {
+  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  const float *ws = split_ws + ((size_t)b * n_q + h) * n_splits * (hd + 2);
+  float M = -INFINITY;
+  for (int s = 0; s < n_splits; ++s) M = fmaxf(M, ws[(size_t)s * (hd + 2)]);
+  float L = 0.f, acc = 0.f;
+  for (int s = 0; s < n_splits; ++s) {
+    const float m = ws[(size_t)s * (hd + 2)];
+    if (m == -INFINITY) continue;
+    const float f = __expf(m - M);
+    L += ws[(size_t)s * (hd + 2) + 1] * f;
+    acc += ws[(size_t)s * (hd + 2) + 2 + d] * f;
+  }
+  out[(size_t)b * ldo + (size_t)h * hd + d] = __float2bfloat16_rn(acc / L);
+}
+
+template <int NB>
+static int launch_gemv(const bf16 *X, long long ldx, const bf16 *W, long long ldw, bf16 *D, long long ldd, int N, int K,
+                       const bf16 *bias, const bf16 *residual, long long ldr, int epilogue, const bf16 *norm_w, float eps,
+                       cudaStream_t st) {
+  const int pairs = (epilogue == OCRB_EPI_SWIGLU) ? N / 2 : (N + 1) / 2;
+  const int blocks = cdiv(pairs, GV_WARPS);
+  const size_t xbytes = (size_t)NB * K * sizeof(bf16);
+  const bool norm = norm_w != nullptr;
+  const bool x_in_smem = norm || xbytes <= 48 * 1024;
+  OCRB_REQUIRE(!norm || xbytes <= 200 * 1024, "gemv_bf16: fused RMSNorm needs B*K*2 <= 200 KiB of shared memory");
+  const size_t smem = x_in_smem ? xbytes : 0;
+  if (norm) {
+    if (smem > 48 * 1024)
+      OCRB_CUDA(cudaFuncSetAttribute(gemv_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemv_kernel<NB, true><<<blocks, GV_WARPS * 32, smem, st>>>(X, ldx, W, ldw, D, ldd, N, K, bias, residual, ldr, epilogue,
+                                                                norm_w, eps, true);
+  } else {
+    gemv_kernel<NB, false><<<blocks, GV_WARPS * 32, smem, st>>>(X, ldx, W, ldw, D, ldd, N, K, bias, residual, ldr, epilogue,
+                                                                 nullptr, eps, x_in_smem);
+  }
+  return check_launch("gemv_kernel");
+}
+
+}  // namespace ocrb
+
+using namespace ocrb;
+
+extern "C" int ocrb_gemv_bf16(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd, int32_t B,
+                              int32_t N, int32_t K, const void *bias, const void *residual, int64_t ldr, int32_t epilogue,
+                              const void *norm_w, float eps, void *stream) {
+  OCRB_REQUIRE(A && W && D, "gemv_bf16: null pointer");
+  OCRB_REQUIRE(B >= 1 && B <= GV_MAXB, "gemv_bf16: B must be in 1..8 (use ocrb_gemm_bf16 for larger batches)");
+  OCRB_REQUIRE(N > 0 && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemv_bf16: K and strides must be multiples of 8");
+  OCRB_REQUIRE(epilogue >= 0 && epilogue <= 3, "gemv_bf16: bad epilogue");
+  OCRB_REQUIRE(epilogue != OCRB_EPI_RESIDUAL || residual, "gemv_bf16: residual epilogue without residual");
+  OCRB_REQUIRE(epilogue != OCRB_EPI_SWIGLU || N % 128 == 0, "gemv_bf16: SwiGLU needs N (packed gate|up rows) % 128 == 0");
+  OCRB_REQUIRE(epilogue == OCRB_EPI_SWIGLU || ldd % 2 == 0, "gemv_bf16: ldd must be even");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bf16 *X = (const bf16 *)A, *Wp = (const bf16 *)W, *bp = (const bf16 *)bias, *rp = (const bf16 *)residual,
+             *nw = (const bf16 *)norm_w;
+  bf16 *Dp = (bf16 *)D;
+#define GV_CASE(nb) \
+  case nb: return launch_gemv<nb>(X, lda, Wp, ldw, Dp, ldd, N, K, bp, rp, ldr, epilogue, nw, eps, st);
+  switch (B) {
+    GV_CASE(1) GV_CASE(2) GV_CASE(3) GV_CASE(4) GV_CASE(5) GV_CASE(6) GV_CASE(7) GV_CASE(8)
+  }
+#undef GV_CASE
+  return OCRB_EINVAL;
+}
+
+extern "C" int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cache, void *v_cache,
+                                     const int32_t *block_table, int32_t max_pages, const int32_t *ctx_len, int32_t B,
+                                     int32_t page_size, int32_t n_q, int32_t n_kv, int32_t hd, const void *cosT,
+                                     const void *sinT, float scale, void *out, int64_t ldo, float *split_ws,
+                                     int32_t n_splits, void *stream) {
+  OCRB_REQUIRE(qkv && k_cache && v_cache && block_table && ctx_len && cosT && sinT && out && split_ws,
+               "decode_attention: null pointer");
+  OCRB_REQUIRE(B > 0 && n_kv > 0 && n_q % n_kv == 0 && n_q / n_kv <= DA_MAXG && hd % 8 == 0 && hd <= 256 && n_splits > 0,
+               "decode_attention: bad sizes");
+  const int max_ctx = max_pages * page_size;
+  const int chunk = cdiv(max_ctx, n_splits);
+  const int G = n_q / n_kv;
+  const size_t smem = ((size_t)G * hd + hd + (size_t)G * chunk) * sizeof(float);
+  OCRB_REQUIRE(smem <= 200 * 1024, "decode_attention: chunk too large, raise n_splits");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (smem > 48 * 1024)
+    OCRB_CUDA(cudaFuncSetAttribute(decode_attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  decode_attn_partial_kernel<<<dim3(n_splits, n_kv, B), DA_THREADS, smem, st>>>(
+      (const bf16 *)qkv, ldqkv, (bf16 *)k_cache, (bf16 *)v_cache, block_table, max_pages, ctx_len, page_size, n_q, n_kv, hd,
+      (const bf16 *)cosT, (const bf16 *)sinT, scale, split_ws, n_splits, chunk);
+  int rc = check_launch("decode_attn_partial_kernel");
+  if (rc) return rc;
+  decode_attn_combine_kernel<<<dim3(n_q, B), hd, 0, st>>>(split_ws, n_q, n_splits, hd, (bf16 *)out, ldo);
+  return check_launch("decode_attn_combine_kernel");
+}

@@ -1,0 +1,284 @@
+// Small bandwidth-bound ops of the VLM (HF modeling_qwen2_5_vl.py): RMSNorm, vision RoPE, text mRoPE,
+// embedding / row gathers, paged-KV prefill write, greedy argmax + step bookkeeping.  All mirror HF's
+// rounding points (fp32 math, bf16 stores where HF materialises bf16 tensors).
+#include "common.cuh"
+#include <math.h>
+
+namespace ocrb {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ───────────── RMSNorm: one CTA per row ─────────────
+__global__ void __launch_bounds__(256)
+rmsnorm_kernel(const bf16 *__restrict__ x, long long ldx, const bf16 *__restrict__ w, bf16 *__restrict__ y,
+               long long ldy, int dim, float eps) {
+  __shared__ float s_part[8];
+  const bf16 *xr = x + (size_t)blockIdx.x * ldx;
+  bf16 *yr = y + (size_t)blockIdx.x * ldy;
+  float ss = 0.f;
+  const int nvec = dim >> 3;
+  for (int v = threadIdx.x; v < nvec; v += 256) {
+    const uint4 raw = *reinterpret_cast<const uint4 *>(xr + v * 8);
+    const bf16 *e = reinterpret_cast<const bf16 *>(&raw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float f = __bfloat162float(e[k]);
+      ss = fmaf(f, f, ss);
+    }
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += s_part[k];
+  const float rstd = rsqrtf(tot / (float)dim + eps);
+  for (int v = threadIdx.x; v < nvec; v += 256) {
+    const uint4 raw = *reinterpret_cast<const uint4 *>(xr + v * 8);
+    const uint4 wraw = *reinterpret_cast<const uint4 *>(w + v * 8);
+    const bf16 *e = reinterpret_cast<const bf16 *>(&raw);
+    const bf16 *we = reinterpret_cast<const bf16 *>(&wraw);
+    uint4 o;
+    bf16 *oe = reinterpret_cast<bf16 *>(&o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float n = bf16_round(__bfloat162float(e[k]) * rstd);
+      oe[k] = __float2bfloat16_rn(__bfloat162float(we[k]) * n);
+    }
+    *reinterpret_cast<uint4 *>(yr + v * 8) = o;
+  }
+}
+
+// ───────────── vision RoPE (fp32 math, unfused like eager torch) ─────────────
+// qkv: [S, 3, heads, hd]; rotates q (slot 0) and k (slot 1) in place.
+__global__ void __launch_bounds__(256)
+rope_vision_kernel(bf16 *__restrict__ qkv, int S, int heads, int hd, const float *__restrict__ cosT,
+                   const float *__restrict__ sinT) {
+  const int half = hd >> 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)S * 2 * heads * half;
+  if (idx >= total) return;
+  const int i = (int)(idx % half);
+  long long r = idx / half;
+  const int h = (int)(r % heads);
+  r /= heads;
+  const int which = (int)(r % 2);
+  const int s = (int)(r / 2);
+  bf16 *p = qkv + ((size_t)s * 3 + which) * heads * hd + (size_t)h * hd;
+  const float x1 = __bfloat162float(p[i]), x2 = __bfloat162float(p[i + half]);
+  const float c1 = cosT[(size_t)s * hd + i], c2 = cosT[(size_t)s * hd + i + half];
+  const float s1 = sinT[(size_t)s * hd + i], s2 = sinT[(size_t)s * hd + i + half];
+  const float o1 = __fadd_rn(__fmul_rn(x1, c1), __fmul_rn(-x2, s1));
+  const float o2 = __fadd_rn(__fmul_rn(x2, c2), __fmul_rn(x1, s2));
+  p[i] = __float2bfloat16_rn(o1);
+  p[i + half] = __float2bfloat16_rn(o2);
+}
+
+// ───────────── text mRoPE in bf16 arithmetic (every op rounds to bf16 as eager torch does) ─────────────
+__device__ __forceinline__ void rope_bf16_pair(bf16 &a, bf16 &b, bf16 c1, bf16 s1, bf16 c2, bf16 s2) {
+  const float x1 = __bfloat162float(a), x2 = __bfloat162float(b);
+  const float t1 = bf16_round(x1 * __bfloat162float(c1));
+  const float u1 = bf16_round(-x2 * __bfloat162float(s1));
+  const float t2 = bf16_round(x2 * __bfloat162float(c2));
+  const float u2 = bf16_round(x1 * __bfloat162float(s2));
+  a = __float2bfloat16_rn(t1 + u1);
+  b = __float2bfloat16_rn(t2 + u2);
+}
+
+__global__ void __launch_bounds__(256)
+rope_text_kernel(bf16 *__restrict__ q, long long ldq, bf16 *__restrict__ k, long long ldk, int T, int n_q, int n_kv,
+                 int hd, const bf16 *__restrict__ cosT, const bf16 *__restrict__ sinT) {
+  const int half = hd >> 1;
+  const int heads = n_q + n_kv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)T * heads * half;
+  if (idx >= total) return;
+  const int i = (int)(idx % half);
+  long long r = idx / half;
+  const int h = (int)(r % heads);
+  const int t = (int)(r / heads);
+  bf16 *p = (h < n_q) ? q + (size_t)t * ldq + (size_t)h * hd : k + (size_t)t * ldk + (size_t)(h - n_q) * hd;
+  const bf16 *c = cosT + (size_t)t * hd, *s = sinT + (size_t)t * hd;
+  rope_bf16_pair(p[i], p[i + half], c[i], s[i], c[i + half], s[i + half]);
+}
+
+// cos/sin for one decode step: pos[b] = ctx_len[b] + rope_delta[b] (text tokens: t = h = w = pos).
+__global__ void decode_rope_table_kernel(const int32_t *__restrict__ ctx_len, const int32_t *__restrict__ rope_delta,
+                                         const float *__restrict__ inv_freq, int B, int hd, bf16 *__restrict__ cosT,
+                                         bf16 *__restrict__ sinT) {
+  const int half = hd >> 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * half) return;
+  const int b = idx / half, i = idx - b * half;
+  const float pos = (float)(ctx_len[b] + rope_delta[b]);
+  const float f = __fmul_rn(inv_freq[i], pos);
+  const bf16 c = __float2bfloat16_rn(cosf(f)), s = __float2bfloat16_rn(sinf(f));
+  cosT[(size_t)b * hd + i] = c;
+  cosT[(size_t)b * hd + i + half] = c;
+  sinT[(size_t)b * hd + i] = s;
+  sinT[(size_t)b * hd + i + half] = s;
+}
+
+// ───────────── row gathers ─────────────
+__global__ void __launch_bounds__(256)
+rows_copy_kernel(const bf16 *__restrict__ src, long long lds, const int32_t *__restrict__ src_idx, bf16 *__restrict__ dst,
+                 long long ldd, const int32_t *__restrict__ dst_idx, int n_rows, int nvec) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_rows * nvec) return;
+  const int row = (int)(idx / nvec), v = (int)(idx - (long long)row * nvec);
+  const long long sr = src_idx ? src_idx[row] : row;
+  const long long dr = dst_idx ? dst_idx[row] : row;
+  const uint4 val = *reinterpret_cast<const uint4 *>(src + sr * lds + v * 8);
+  *reinterpret_cast<uint4 *>(dst + dr * ldd + v * 8) = val;
+}
+
+// ───────────── paged KV: prefill write ─────────────
+__global__ void __launch_bounds__(256)
+kv_write_prefill_kernel(const bf16 *__restrict__ k, long long ldk, const bf16 *__restrict__ v, long long ldv,
+                        bf16 *__restrict__ k_cache, bf16 *__restrict__ v_cache, const int32_t *__restrict__ block_table,
+                        int max_pages, const int32_t *__restrict__ cu_seqlens, int n_seq, int T, int page_size,
+                        int row_vec /* n_kv*hd/8 */) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * row_vec) return;
+  const int t = (int)(idx / row_vec), vv = (int)(idx - (long long)t * row_vec);
+  int s = 0;
+  while (s + 1 < n_seq && t >= cu_seqlens[s + 1]) ++s;
+  const int pos = t - cu_seqlens[s];
+  const int page = block_table[(size_t)s * max_pages + pos / page_size];
+  const size_t dst = ((size_t)page * page_size + pos % page_size) * row_vec * 8 + (size_t)vv * 8;
+  *reinterpret_cast<uint4 *>(k_cache + dst) = *reinterpret_cast<const uint4 *>(k + (size_t)t * ldk + vv * 8);
+  *reinterpret_cast<uint4 *>(v_cache + dst) = *reinterpret_cast<const uint4 *>(v + (size_t)t * ldv + vv * 8);
+}
+
+// ───────────── greedy argmax + per-step bookkeeping: one CTA per sequence ─────────────
+__global__ void __launch_bounds__(512)
+argmax_step_kernel(const bf16 *__restrict__ logits, long long ldl, int V, int eos, int pad, int max_new,
+                   int32_t *__restrict__ out_tokens, int32_t *__restrict__ next_ids, int32_t *__restrict__ finished,
+                   int32_t *__restrict__ ctx_len, int32_t *__restrict__ step, int advance_ctx) {
+  __shared__ float s_val[16];
+  __shared__ int s_idx[16];
+  const int b = blockIdx.x;
+  const bf16 *row = logits + (size_t)b * ldl;
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  const int nvec = V >> 3;
+  for (int v = threadIdx.x; v < nvec; v += 512) {
+    const uint4 raw = *reinterpret_cast<const uint4 *>(row + v * 8);
+    const bf16 *e = reinterpret_cast<const bf16 *>(&raw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float f = __bfloat162float(e[k]);
+      if (f > best) { best = f; best_i = v * 8 + k; }  // ascending index within a thread: first max kept
+    }
+  }
+  for (int i = (nvec << 3) + threadIdx.x; i < V; i += 512) {
+    const float f = __bfloat162float(row[i]);
+    if (f > best || (f == best && i < best_i)) { best = f; best_i = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = best_i; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 16; ++k)
+      if (s_val[k] > best || (s_val[k] == best && s_idx[k] < best_i)) { best = s_val[k]; best_i = s_idx[k]; }
+    int tok = best_i;
+    const int st = step[0];
+    if (finished[b]) tok = pad;
+    if (st < max_new) out_tokens[(size_t)b * max_new + st] = tok;
+    if (tok == eos) finished[b] = 1;
+    next_ids[b] = tok;
+    if (advance_ctx) ctx_len[b] += 1;
+  }
+}
+
+__global__ void step_increment_kernel(int32_t *step) { step[0] += 1; }
+
+}  // namespace ocrb
+
+using namespace ocrb;
+
+extern "C" int ocrb_rmsnorm_bf16(const void *x, int64_t ldx, const void *w, void *y, int64_t ldy, int32_t rows,
+                                 int32_t dim, float eps, void *stream) {
+  OCRB_REQUIRE(x && w && y && rows > 0 && dim > 0 && dim % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0,
+               "rmsnorm_bf16: bad arguments (dim and strides must be multiples of 8)");
+  rmsnorm_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, ldx, (const bf16 *)w, (bf16 *)y, ldy, dim, eps);
+  return check_launch("rmsnorm_kernel");
+}
+
+extern "C" int ocrb_rope_vision(void *qkv, int32_t S, int32_t heads, int32_t hd, const float *cosT, const float *sinT,
+                                void *stream) {
+  OCRB_REQUIRE(qkv && cosT && sinT && S > 0 && heads > 0 && hd > 0 && hd % 2 == 0, "rope_vision: bad arguments");
+  const long long total = (long long)S * 2 * heads * (hd / 2);
+  rope_vision_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((bf16 *)qkv, S, heads, hd, cosT, sinT);
+  return check_launch("rope_vision_kernel");
+}
+
+extern "C" int ocrb_rope_text(void *q, int64_t ldq, void *k, int64_t ldk, int32_t T, int32_t n_q, int32_t n_kv,
+                              int32_t hd, const void *cosT, const void *sinT, void *stream) {
+  OCRB_REQUIRE(q && k && cosT && sinT && T > 0 && n_q > 0 && n_kv > 0 && hd % 2 == 0, "rope_text: bad arguments");
+  const long long total = (long long)T * (n_q + n_kv) * (hd / 2);
+  rope_text_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((bf16 *)q, ldq, (bf16 *)k, ldk, T, n_q, n_kv, hd,
+                                                                      (const bf16 *)cosT, (const bf16 *)sinT);
+  return check_launch("rope_text_kernel");
+}
+
+extern "C" int ocrb_decode_rope_table(const int32_t *ctx_len, const int32_t *rope_delta, const float *inv_freq, int32_t B,
+                                      int32_t hd, void *cosT, void *sinT, void *stream) {
+  OCRB_REQUIRE(ctx_len && rope_delta && inv_freq && cosT && sinT && B > 0 && hd % 2 == 0, "decode_rope_table: bad arguments");
+  decode_rope_table_kernel<<<cdiv(B * (hd / 2), 128), 128, 0, (cudaStream_t)stream>>>(ctx_len, rope_delta, inv_freq, B, hd,
+                                                                                   (bf16 *)cosT, (bf16 *)sinT);
+  return check_launch("decode_rope_table_kernel");
+}
+
+extern "C" int ocrb_rows_copy(const void *src, int64_t lds, const int32_t *src_idx, void *dst, int64_t ldd,
+                              const int32_t *dst_idx, int32_t n_rows, int32_t dim, void *stream) {
+  if (n_rows == 0) return OCRB_OK;
+  OCRB_REQUIRE(src && dst && n_rows > 0 && dim > 0 && dim % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0,
+               "rows_copy: bad arguments");
+  const long long total = (long long)n_rows * (dim / 8);
+  rows_copy_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16 *)src, lds, src_idx, (bf16 *)dst, ldd,
+                                                                      dst_idx, n_rows, dim / 8);
+  return check_launch("rows_copy_kernel");
+}
+
+extern "C" int ocrb_embed_gather(const void *table, const int32_t *ids, void *out, int32_t T, int32_t dim, void *stream) {
+  OCRB_REQUIRE(ids, "embed_gather: null ids");
+  return ocrb_rows_copy(table, dim, ids, out, dim, nullptr, T, dim, stream);
+}
+
+extern "C" int ocrb_kv_write_prefill(const void *k, int64_t ldk, const void *v, int64_t ldv, void *k_cache, void *v_cache,
+                                     const int32_t *block_table, int32_t max_pages, const int32_t *cu_seqlens,
+                                     int32_t n_seq, int32_t T, int32_t page_size, int32_t n_kv, int32_t hd, void *stream) {
+  OCRB_REQUIRE(k && v && k_cache && v_cache && block_table && cu_seqlens, "kv_write_prefill: null pointer");
+  OCRB_REQUIRE(T > 0 && n_seq > 0 && page_size > 0 && (n_kv * hd) % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0,
+               "kv_write_prefill: bad sizes");
+  const int row_vec = n_kv * hd / 8;
+  kv_write_prefill_kernel<<<cdiv((long long)T * row_vec, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16 *)k, ldk, (const bf16 *)v, ldv, (bf16 *)k_cache, (bf16 *)v_cache, block_table, max_pages, cu_seqlens,
+      n_seq, T, page_size, row_vec);
+  return check_launch("kv_write_prefill_kernel");
+}
+
+extern "C" int ocrb_argmax_step(const void *logits, int64_t ldl, int32_t B, int32_t V, int32_t eos, int32_t pad,
+                                int32_t max_new, int32_t *out_tokens, int32_t *next_ids, int32_t *finished,
+                                int32_t *ctx_len, int32_t *step, int32_t advance_ctx, void *stream) {
+  OCRB_REQUIRE(logits && out_tokens && next_ids && finished && ctx_len && step, "argmax_step: null pointer");
+  OCRB_REQUIRE(B > 0 && V > 0 && ldl % 8 == 0 && max_new > 0, "argmax_step: bad sizes");
+  argmax_step_kernel<<<B, 512, 0, (cudaStream_t)stream>>>((const bf16 *)logits, ldl, V, eos, pad, max_new, out_tokens,
+                                                          next_ids, finished, ctx_len, step, advance_ctx);
+  int rc = check_launch("argmax_step_kernel");
+  if (rc) return rc;
+  step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+  return check_launch("step_increment_kernel");
+}

@@ -1,0 +1,358 @@
+// Dense GEMM of the VLM on 5th-generation tensor cores: D[M,N'] = epilogue(A[M,K] . W[N,K]^T).
+// Every nn.Linear / Conv3d-as-GEMM of the vision tower and of decoder prefill goes through here
+// (HF modeling_qwen2_5_vl.py: patch_embed :99-111, qkv/proj :214-283, MLPs :76-88 / :607-622,
+// merger :133-146, q/k/v/o :704-760).
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 128x64 (A) and BNx64 (W) bf16 boxes, 128B swizzle,
+//              into a 4-stage shared-memory ring, completion on mbarriers (expect_tx)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32 in TMEM),
+//              tcgen05.commit frees ring slots / signals the accumulator
+//   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns -> registers -> bias / residual / SwiGLU / GELU with
+//              HF's bf16 rounding points -> 16-byte global stores
+// M/N/K tails are handled by TMA zero fill on loads and predicated stores.
+#include "common.cuh"
+#include <cuda.h>
+#include <math.h>
+#include <mutex>
+
+namespace ocrb {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int GM_BM = 128;
+constexpr int GM_BK = 64;          // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int GM_STAGES = 4;
+constexpr int GM_THREADS = 192;
+constexpr int UMMA_K = 16;
+
+// ───────────── PTX wrappers ─────────────
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must fail fast (trap) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("ocrb gemm: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);   // start address
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ float silu_bf16r(float g) { return bf16_round(g / (1.0f + expf(-g))); }
+__device__ __forceinline__ float gelu_bf16r(float x) { return bf16_round(0.5f * x * (1.0f + erff(x * 0.70710678118654752440f))); }
+
+struct GemmParams {
+  bf16 *D;
+  long long ldd;
+  const bf16 *bias;
+  const bf16 *residual;
+  long long ldr;
+  int M, N, K;
+  int epilogue;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, GemmParams p) {
+  constexpr uint32_t A_BYTES = GM_BM * GM_BK * 2;   // 16 KiB
+  constexpr uint32_t B_BYTES = BN * GM_BK * 2;      // 16 / 32 KiB
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t gm_smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(gm_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + GM_STAGES * STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + GM_STAGES;
+  uint64_t *accum_bar = empty_bar + GM_STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM_BM;
+  const int num_kb = (p.K + GM_BK - 1) / GM_BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < GM_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % GM_STAGES;
+        const uint32_t ph = (kb / GM_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        uint8_t *sa = smem + s * STAGE_BYTES;
+        tma_load_2d(sa, &map_a, &full_bar[s], kb * GM_BK, m0);
+        tma_load_2d(sa + A_BYTES, &map_w, &full_bar[s], kb * GM_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % GM_STAGES;
+        const uint32_t ph = (kb / GM_STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc(sa);
+        const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < GM_BK / UMMA_K; ++k) {
+          // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
+      }
+      umma_commit(accum_bar);        // accumulator complete
+    }
+  } else {
+    // ───────────── epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) ─────────────
+    const int quad = warp & 3;
+    const int row = m0 + quad * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tcgen05_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const bool row_ok = row < p.M;
+    if (p.epilogue == OCRB_EPI_SWIGLU) {
+      // weight rows are packed per 128 as [gate 64 | up 64]; output column block = n0/2
+#pragma unroll 1
+      for (int blk = 0; blk < BN / 128; ++blk) {
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t g[32], u[32];
+          tmem_ld32(lane_addr + blk * 128 + c, g);
+          tmem_ld32(lane_addr + blk * 128 + 64 + c, u);
+          tmem_ld_wait();
+          const int ng = n0 + blk * 128 + c;        // packed row index of the gate columns
+          const int out_col = (n0 >> 1) + blk * 64 + c;
+          if (row_ok && ng < p.N) {
+            bf16 *drow = p.D + (size_t)row * p.ldd + out_col;
+#pragma unroll
+            for (int v8 = 0; v8 < 4; ++v8) {
+              uint4 pk;
+              bf16 *pe = reinterpret_cast<bf16 *>(&pk);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int i = v8 * 8 + e;
+                float gv = __uint_as_float(g[i]), uv = __uint_as_float(u[i]);
+                if (p.bias) {
+                  gv += __bfloat162float(p.bias[ng + i]);
+                  uv += __bfloat162float(p.bias[ng + 64 + i]);
+                }
+                pe[e] = __float2bfloat16_rn(silu_bf16r(bf16_round(gv)) * bf16_round(uv));
+              }
+              *reinterpret_cast<uint4 *>(drow + v8 * 8) = pk;
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + c, r);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        if (row_ok && n < p.N) {
+          bf16 *drow = p.D + (size_t)row * p.ldd + n;
+          const bf16 *rrow = p.residual ? p.residual + (size_t)row * p.ldr + n : nullptr;
+#pragma unroll
+          for (int v8 = 0; v8 < 4; ++v8) {
+            if (n + v8 * 8 >= p.N) break;
+            uint4 pk, rk = make_uint4(0, 0, 0, 0);
+            bf16 *pe = reinterpret_cast<bf16 *>(&pk);
+            if (p.epilogue == OCRB_EPI_RESIDUAL) rk = *reinterpret_cast<const uint4 *>(rrow + v8 * 8);
+            const bf16 *re = reinterpret_cast<const bf16 *>(&rk);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int i = v8 * 8 + e;
+              float v = __uint_as_float(r[i]);
+              if (p.bias) v += __bfloat162float(p.bias[n + i]);
+              v = bf16_round(v);
+              if (p.epilogue == OCRB_EPI_RESIDUAL) v += __bfloat162float(re[e]);
+              else if (p.epilogue == OCRB_EPI_GELU) v = gelu_bf16r(v);
+              pe[e] = __float2bfloat16_rn(v);
+            }
+            *reinterpret_cast<uint4 *>(drow + v8 * 8) = pk;
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// ───────────── host: tensor maps ─────────────
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle.
+static int make_map(CUtensorMap *m, const void *ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("gemm_bf16: cuTensorMapEncodeTiled not available from the driver");
+    return OCRB_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)GM_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_bf16: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+    return OCRB_ECUDA;
+  }
+  return OCRB_OK;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, const GemmParams &p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)GM_STAGES * (GM_BM * GM_BK * 2 + BN * GM_BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OCRB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(p.N, BN), cdiv(p.M, GM_BM));
+  gemm_tcgen05_kernel<BN><<<grid, GM_THREADS, smem, st>>>(ma, mw, p);
+  return check_launch("gemm_tcgen05_kernel");
+}
+
+}  // namespace ocrb
+
+using namespace ocrb;
+
+extern "C" int ocrb_gemm_bf16(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd, int32_t M,
+                              int32_t N, int32_t K, const void *bias, const void *residual, int64_t ldr, int32_t epilogue,
+                              void *stream) {
+  OCRB_REQUIRE(A && W && D, "gemm_bf16: null pointer");
+  OCRB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: bad sizes");
+  OCRB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldd % 8 == 0 && N % 8 == 0,
+               "gemm_bf16: K, N and row strides must be multiples of 8 (16-byte TMA / store granularity)");
+  OCRB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)D & 15) == 0,
+               "gemm_bf16: pointers must be 16-byte aligned");
+  OCRB_REQUIRE(epilogue >= 0 && epilogue <= 3, "gemm_bf16: bad epilogue");
+  OCRB_REQUIRE(epilogue != OCRB_EPI_RESIDUAL || (residual && ldr % 8 == 0 && ((uintptr_t)residual & 15) == 0),
+               "gemm_bf16: residual epilogue needs a 16-byte aligned residual with ldr % 8 == 0");
+  OCRB_REQUIRE(epilogue != OCRB_EPI_SWIGLU || N % 128 == 0, "gemm_bf16: SwiGLU needs packed N % 128 == 0");
+  OCRB_REQUIRE(epilogue != OCRB_EPI_GELU || bias, "gemm_bf16: GELU epilogue expects a bias");
+  GemmParams p;
+  p.D = (bf16 *)D;
+  p.ldd = ldd;
+  p.bias = (const bf16 *)bias;
+  p.residual = (epilogue == OCRB_EPI_RESIDUAL) ? (const bf16 *)residual : nullptr;
+  p.ldr = ldr;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epilogue = epilogue;
+  // Tile width: 256 when it divides evenly and the grid still fills the machine, else 128.
+  const bool wide = (N % 256 == 0) && ((long long)cdiv(N, 256) * cdiv(M, GM_BM) >= 148);
+  const int BN = wide ? 256 : 128;
+  CUtensorMap ma, mw;
+  int rc = make_map(&ma, A, M, K, lda, GM_BM);
+  if (rc) return rc;
+  rc = make_map(&mw, W, N, K, ldw, BN);
+  if (rc) return rc;
+  if (wide) return launch_gemm<256>(ma, mw, p, (cudaStream_t)stream);
+  return launch_gemm<128>(ma, mw, p, (cudaStream_t)stream);
+}

@@ -1,0 +1,554 @@
+// uint8 image kernels of the preprocessing strategies (tools.py:503-573), bit-exact against
+// OpenCV 4.13.0.92 semantics.  Compiled with -fmad=false; every
+// floating-point operation whose rounding matters is additionally written with an explicit
+// _rn intrinsic so that nothing is contracted or reassociated.
+#include "common.cuh"
+#include <math.h>
+
+namespace ocrb {
+
+// ───────────────────────── A.1 RGB -> gray ─────────────────────────
+__device__ __forceinline__ uint32_t gray_px(uint32_t r, uint32_t g, uint32_t b) {
+  return (9798u * r + 19235u * g + 3735u * b + 16384u) >> 15;
+}
+
+// 16 pixels per thread: three 16-byte loads, one 16-byte store.
+__global__ void __launch_bounds__(256)
+rgb2gray_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t npix) {
+  const size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (base >= npix) return;
+  if (base + 16 <= npix) {
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + base * 3);
+    union { uint4 v[3]; uint8_t b[48]; } in;
+    in.v[0] = __ldg(s4);
+    in.v[1] = __ldg(s4 + 1);
+    in.v[2] = __ldg(s4 + 2);
+    union { uint4 v; uint8_t b[16]; } o;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o.b[k] = (uint8_t)gray_px(in.b[3 * k], in.b[3 * k + 1], in.b[3 * k + 2]);
+    *reinterpret_cast<uint4 *>(dst + base) = o.v;
+  } else {
+    for (size_t p = base; p < npix; ++p) dst[p] = (uint8_t)gray_px(src[3 * p], src[3 * p + 1], src[3 * p + 2]);
+  }
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// ───────────────────────── A.2 CLAHE ─────────────────────────
+// Pass 1: one CTA per (tile, image): 256-bin shared histogram -> clip -> redistribute -> LUT.
+__global__ void __launch_bounds__(256)
+clahe_lut_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ lut, int H, int W, int tw, int th,
+                 int clip, float lut_scale) {
+  __shared__ int hist[256];
+  __shared__ int scan[256];
+  __shared__ int s_clipped;
+  const int tile = blockIdx.x, img = blockIdx.y;
+  const int ty = tile >> 3, tx = tile & 7;
+  const uint8_t *im = src + (size_t)img * H * W;
+  hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_clipped = 0;
+  __syncthreads();
+  const int x0 = tx * tw, y0 = ty * th;
+  for (int p = threadIdx.x; p < tw * th; p += 256) {
+    const int yy = reflect101(y0 + p / tw, H);
+    const int xx = reflect101(x0 + p % tw, W);
+    atomicAdd(&hist[im[(size_t)yy * W + xx]], 1);
+  }
+  __syncthreads();
+  int h = hist[threadIdx.x];
+  const int excess = max(h - clip, 0);
+  // block sum of the excess
+  int e = excess;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_clipped, e);
+  __syncthreads();
+  const int clipped = s_clipped;
+  h = min(h, clip);
+  const int batch = clipped / 256;
+  const int resid = clipped - batch * 256;
+  h += batch;
+  if (resid) {
+    const int step = max(256 / resid, 1);
+    const int i = threadIdx.x;
+    if (i % step == 0 && i / step < resid) h += 1;
+  }
+  // inclusive scan over 256 bins (Hillis-Steele in shared memory)
+  scan[threadIdx.x] = h;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    int v = scan[threadIdx.x];
+    if ((int)threadIdx.x >= o) v += scan[threadIdx.x - o];
+    __syncthreads();
+    scan[threadIdx.x] = v;
+    __syncthreads();
+  }
+  const float f = __fmul_rn((float)scan[threadIdx.x], lut_scale);
+  int q = __float2int_rn(f);
+  q = min(max(q, 0), 255);
+  lut[((size_t)img * 64 + tile) * 256 + threadIdx.x] = (uint8_t)q;
+}
+
+// Pass 2: bilinear blend of the four neighbouring tile LUTs; unfused fp32 mul/add in OpenCV's order.
+__global__ void __launch_bounds__(256)
+clahe_apply_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const uint8_t *__restrict__ lut,
+                   int H, int W, float inv_tw, float inv_th) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int img = blockIdx.z;
+  if (x >= W) return;
+  const float xf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
+  const float yf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+  int tx1 = (int)floorf(xf), ty1 = (int)floorf(yf);
+  int tx2 = tx1 + 1, ty2 = ty1 + 1;
+  const float xa = __fsub_rn(xf, (float)tx1), ya = __fsub_rn(yf, (float)ty1);
+  const float xa1 = __fsub_rn(1.0f, xa), ya1 = __fsub_rn(1.0f, ya);
+  tx1 = max(tx1, 0);
+  tx2 = min(tx2, 7);
+  ty1 = max(ty1, 0);
+  ty2 = min(ty2, 7);
+  const size_t p = ((size_t)img * H + y) * W + x;
+  const int v = src[p];
+  const uint8_t *L = lut + (size_t)img * 64 * 256;
+  const float l11 = (float)L[(ty1 * 8 + tx1) * 256 + v];
+  const float l12 = (float)L[(ty1 * 8 + tx2) * 256 + v];
+  const float l21 = (float)L[(ty2 * 8 + tx1) * 256 + v];
+  const float l22 = (float)L[(ty2 * 8 + tx2) * 256 + v];
+  const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+  const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+  const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+  int q = __float2int_rn(res);
+  q = min(max(q, 0), 255);
+  dst[p] = (uint8_t)q;
+}
+
+// ───────────────────────── A.3 adaptive Gaussian threshold ─────────────────────────
+// cv2.getGaussianKernel(21, 0, CV_32F) bit patterns (sigma = 3.5).
+__constant__ uint32_t c_gauss21[21] = {
+    0x3afcd8aau, 0x3b8946cfu, 0x3c09607cu, 0x3c7d66a6u, 0x3cd7632bu, 0x3d28b99eu, 0x3d739f36u,
+    0x3da21867u, 0x3dc6cb1eu, 0x3de0b045u, 0x3dea0c9bu, 0x3de0b045u, 0x3dc6cb1eu, 0x3da21867u,
+    0x3d739f36u, 0x3d28b99eu, 0x3cd7632bu, 0x3c7d66a6u, 0x3c09607cu, 0x3b8946cfu, 0x3afcd8aau};
+
+constexpr int AT_TW = 64, AT_TH = 32, AT_R = 10;
+constexpr int AT_SW = AT_TW + 2 * AT_R;  // 84
+constexpr int AT_SH = AT_TH + 2 * AT_R;  // 52
+
+// One CTA = one 64x32 output tile.  Source tile (+10 halo, replicate border) staged in shared
+// memory; the fp32 row pass (sequential FMA) is kept in shared memory for the column pass
+// (symmetric FMA), then round-half-even and compare: one HBM read + one HBM write per pixel.
+__global__ void __launch_bounds__(256)
+adaptive_thresh_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H, int W) {
+  __shared__ uint8_t s_src[AT_SH][AT_SW + 4];
+  __shared__ float s_row[AT_SH][AT_TW + 1];
+  const int img = blockIdx.z;
+  const int x0 = blockIdx.x * AT_TW, y0 = blockIdx.y * AT_TH;
+  const uint8_t *im = src + (size_t)img * H * W;
+  for (int p = threadIdx.x; p < AT_SH * AT_SW; p += 256) {
+    const int r = p / AT_SW, c = p % AT_SW;
+    const int yy = min(max(y0 + r - AT_R, 0), H - 1);
+    const int xx = min(max(x0 + c - AT_R, 0), W - 1);
+    s_src[r][c] = im[(size_t)yy * W + xx];
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < AT_SH * AT_TW; p += 256) {
+    const int r = p / AT_TW, c = p % AT_TW;
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 21; ++j) acc = __fmaf_rn((float)s_src[r][c + j], __uint_as_float(c_gauss21[j]), acc);
+    s_row[r][c] = acc;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < AT_TH * AT_TW; p += 256) {
+    const int r = p / AT_TW, c = p % AT_TW;
+    const int y = y0 + r, x = x0 + c;
+    if (y >= H || x >= W) continue;
+    float acc = __fmaf_rn(s_row[r + AT_R][c], __uint_as_float(c_gauss21[10]), 0.0f);
+#pragma unroll
+    for (int i = 1; i <= 10; ++i)
+      acc = __fmaf_rn(__fadd_rn(s_row[r + AT_R + i][c], s_row[r + AT_R - i][c]), __uint_as_float(c_gauss21[10 + i]), acc);
+    int mean = __float2int_rn(acc);
+    mean = min(max(mean, 0), 255);
+    const int s = s_src[r + AT_R][c + AT_R];
+    dst[((size_t)img * H + y) * W + x] = (s - mean > -10) ? 255 : 0;
+  }
+}
+
+// ───────────────────────── A.4 sharpen ─────────────────────────
+__global__ void __launch_bounds__(256)
+sharpen_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H, int W, int C) {
+  const int xb = blockIdx.x * blockDim.x + threadIdx.x;  // byte index within the row
+  const int y = blockIdx.y;
+  const int img = blockIdx.z;
+  const int rowb = W * C;
+  if (xb >= rowb) return;
+  const int x = xb / C, c = xb - x * C;
+  const uint8_t *im = src + (size_t)img * H * rowb;
+  const int yu = reflect101(y - 1, H), yd = reflect101(y + 1, H);
+  const int xl = reflect101(x - 1, W), xr = reflect101(x + 1, W);
+  const int ctr = im[(size_t)y * rowb + xb];
+  int v = 5 * ctr - im[(size_t)yu * rowb + xb] - im[(size_t)yd * rowb + xb] - im[(size_t)y * rowb + xl * C + c] -
+          im[(size_t)y * rowb + xr * C + c];
+  v = min(max(v, 0), 255);
+  dst[((size_t)img * H + y) * rowb + xb] = (uint8_t)v;
+}
+
+// ───────────────────────── A.5 deskew ─────────────────────────
+// (a) per-row extents of dark (<128) pixels: one warp per row.
+__global__ void __launch_bounds__(256)
+dark_extents_kernel(const uint8_t *__restrict__ src, int32_t *__restrict__ ext, int H, int W, int C, int n_rows_total) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows_total) return;
+  const uint8_t *r = src + (size_t)row * W * C;
+  int cnt = 0, mn = W, mx = -1;
+  for (int x = lane; x < W; x += 32) {
+    uint32_t g;
+    if (C == 3) g = gray_px(r[3 * x], r[3 * x + 1], r[3 * x + 2]);
+    else g = r[x];
+    if (g < 128) {
+      ++cnt;
+      mn = min(mn, x);
+      mx = max(mx, x);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) {
+    ext[(size_t)row * 3 + 0] = cnt;
+    ext[(size_t)row * 3 + 1] = mn;
+    ext[(size_t)row * 3 + 2] = mx;
+  }
+}
+
+__device__ __forceinline__ long long cross3(int ox, int oy, int ax, int ay, int bx, int by) {
+  return (long long)(ax - ox) * (by - oy) - (long long)(ay - oy) * (bx - ox);
+}
+
+// (b) one CTA per image: monotone-chain hull of the <= 2H extent points (thread 0; the points are
+// already sorted: x = row ascending, y = min col then max col), then every hull edge in parallel:
+// fp32 projections in the pinned order, first-minimum area, angle by atan2 in double, rotation matrix.
+// The reference hands (row, col) to minAreaRect as (x, y) (tools.py:557-560).
+__global__ void __launch_bounds__(256)
+deskew_angle_kernel(const int32_t *__restrict__ ext, int H, int W, double *__restrict__ out_angle,
+                    double *__restrict__ out_M, int32_t *__restrict__ hull_ws) {
+  const int img = blockIdx.x;
+  const int32_t *e = ext + (size_t)img * H * 3;
+  int32_t *pts = hull_ws + (size_t)img * (4 * H + 8) * 2;  // [2H+4][2] candidate points
+  int32_t *hull = pts + (2 * H + 4) * 2;                   // [2H+4][2] hull
+  __shared__ int s_np, s_nh, s_total;
+  __shared__ float s_area[256];
+  __shared__ int s_idx[256];
+  if (threadIdx.x == 0) {
+    int total = 0, np = 0;
+    for (int y = 0; y < H; ++y) {
+      const int c = e[y * 3];
+      total += c;
+      if (c > 0) {
+        const int mn = e[y * 3 + 1], mx = e[y * 3 + 2];
+        pts[2 * np] = y; pts[2 * np + 1] = mn; ++np;
+        if (mx != mn) { pts[2 * np] = y; pts[2 * np + 1] = mx; ++np; }
+      }
+    }
+    s_total = total;
+    s_np = np;
+    int k = 0;
+    if (total > 100 && np >= 3) {
+      // lower hull
+      for (int i = 0; i < np; ++i) {
+        const int qx = pts[2 * i], qy = pts[2 * i + 1];
+        while (k >= 2 && cross3(hull[2 * (k - 2)], hull[2 * (k - 2) + 1], hull[2 * (k - 1)], hull[2 * (k - 1) + 1], qx, qy) <= 0) --k;
+        hull[2 * k] = qx; hull[2 * k + 1] = qy; ++k;
+      }
+      // upper hull
+      const int lo = k + 1;
+      for (int i = np - 2; i >= 0; --i) {
+        const int qx = pts[2 * i], qy = pts[2 * i + 1];
+        while (k >= lo && cross3(hull[2 * (k - 2)], hull[2 * (k - 2) + 1], hull[2 * (k - 1)], hull[2 * (k - 1) + 1], qx, qy) <= 0) --k;
+        hull[2 * k] = qx; hull[2 * k + 1] = qy; ++k;
+      }
+      --k;  // last point equals the first
+    }
+    s_nh = k;
+  }
+  __syncthreads();
+  const int nh = s_nh;
+  if (s_total <= 100 || nh < 3) {
+    if (threadIdx.x == 0) {
+      // <= 100 dark pixels: unchanged image (tools.py:558-559).  Degenerate hulls (all dark pixels
+      // collinear) are reported as unsupported by NaN as well.
+      out_angle[img] = nan("");
+      for (int q = 0; q < 6; ++q) out_M[img * 6 + q] = nan("");
+    }
+    return;
+  }
+  float best_area = INFINITY;
+  int best_i = 0x7fffffff;
+  for (int i = threadIdx.x; i < nh; i += 256) {
+    const int j = (i + 1 == nh) ? 0 : i + 1;
+    const float vx = __fsub_rn((float)hull[2 * j], (float)hull[2 * i]);
+    const float vy = __fsub_rn((float)hull[2 * j + 1], (float)hull[2 * i + 1]);
+    const double nrm = sqrt(__dadd_rn(__dmul_rn((double)vx, (double)vx), __dmul_rn((double)vy, (double)vy)));
+    const float inv = (float)(1.0 / nrm);
+    const float lx = __fmul_rn(vx, inv), ly = __fmul_rn(vy, inv);
+    float amin = INFINITY, amax = -INFINITY, bmin = INFINITY, bmax = -INFINITY;
+    for (int q = 0; q < nh; ++q) {
+      const float px = (float)hull[2 * q], py = (float)hull[2 * q + 1];
+      const float a = __fadd_rn(__fmul_rn(px, lx), __fmul_rn(py, ly));
+      const float b = __fadd_rn(-__fmul_rn(px, ly), __fmul_rn(py, lx));
+      amin = fminf(amin, a); amax = fmaxf(amax, a);
+      bmin = fminf(bmin, b); bmax = fmaxf(bmax, b);
+    }
+    const float w = __fsub_rn(amax, amin), h = __fsub_rn(bmax, bmin);
+    const float area = __fmul_rn(w, h);
+    if (area < best_area) { best_area = area; best_i = i; }
+  }
+  s_area[threadIdx.x] = best_area;
+  s_idx[threadIdx.x] = best_i;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ba = INFINITY; int bi = 0x7fffffff;
+    for (int t = 0; t < 256; ++t)
+      if (s_area[t] < ba || (s_area[t] == ba && s_idx[t] < bi)) { ba = s_area[t]; bi = s_idx[t]; }
+    // recompute the winning edge's frame
+    const int i = bi, j = (i + 1 == nh) ? 0 : i + 1;
+    const float vx = __fsub_rn((float)hull[2 * j], (float)hull[2 * i]);
+    const float vy = __fsub_rn((float)hull[2 * j + 1], (float)hull[2 * i + 1]);
+    const double nrm = sqrt(__dadd_rn(__dmul_rn((double)vx, (double)vx), __dmul_rn((double)vy, (double)vy)));
+    const float inv = (float)(1.0 / nrm);
+    const float lx = __fmul_rn(vx, inv), ly = __fmul_rn(vy, inv);
+    float amin = INFINITY, amax = -INFINITY, bmin = INFINITY, bmax = -INFINITY;
+    for (int q = 0; q < nh; ++q) {
+      const float px = (float)hull[2 * q], py = (float)hull[2 * q + 1];
+      const float a = __fadd_rn(__fmul_rn(px, lx), __fmul_rn(py, ly));
+      const float b = __fadd_rn(-__fmul_rn(px, ly), __fmul_rn(py, lx));
+      amin = fminf(amin, a); amax = fmaxf(amax, a);
+      bmin = fminf(bmin, b); bmax = fmaxf(bmax, b);
+    }
+    const float w = __fsub_rn(amax, amin), h = __fsub_rn(bmax, bmin);
+    float cx[4], cy[4];
+    cx[0] = __fmul_rn(lx, w);  cy[0] = __fmul_rn(ly, w);
+    cx[1] = __fmul_rn(-ly, h); cy[1] = __fmul_rn(lx, h);
+    cx[2] = -cx[0]; cy[2] = -cy[0];
+    cx[3] = -cx[1]; cy[3] = -cy[1];
+    const double PI = 3.14159265358979323846;
+    float ang = -90.0f;
+    for (int q = 0; q < 4; ++q) {
+      const double a = atan2((double)cy[q], (double)cx[q]);
+      if (a >= -PI / 2 && a < 0.0) { ang = (float)(a * 180.0 / PI); break; }
+    }
+    double angle = (double)ang;
+    if (angle < -45.0) angle = -(90.0 + angle);
+    else angle = -angle;
+    out_angle[img] = angle;
+    const double th = angle * (PI / 180.0);
+    const double al = cos(th), be = sin(th);
+    const double ccx = (double)(W / 2), ccy = (double)(H / 2);
+    double *M = out_M + img * 6;
+    M[0] = al;
+    M[1] = be;
+    M[2] = __dsub_rn(__dmul_rn(__dsub_rn(1.0, al), ccx), __dmul_rn(be, ccy));
+    M[3] = -be;
+    M[4] = al;
+    M[5] = __dadd_rn(__dmul_rn(be, ccx), __dmul_rn(__dsub_rn(1.0, al), ccy));
+  }
+}
+
+// OpenCV fixed-point bicubic table: int16 [1024][16], index (fy*32 + fx), built on the host.
+__device__ int16_t g_cubic_itab[1024 * 16];
+
+__global__ void __launch_bounds__(256)
+warp_affine_cubic_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H, int W, int C,
+                         const double *__restrict__ Mall) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int img = blockIdx.z;
+  if (x >= W) return;
+  const size_t img_off = (size_t)img * H * W * C;
+  const uint8_t *im = src + img_off;
+  uint8_t *o = dst + img_off + ((size_t)y * W + x) * C;
+  const double *Mf = Mall + img * 6;
+  double m0 = Mf[0], m1 = Mf[1], m2 = Mf[2], m3 = Mf[3], m4 = Mf[4], m5 = Mf[5];
+  if (m0 != m0) {  // NaN: leave the image unchanged
+    for (int c = 0; c < C; ++c) o[c] = im[((size_t)y * W + x) * C + c];
+    return;
+  }
+  // invertAffineTransform as in cv::warpAffine
+  double D = __dsub_rn(__dmul_rn(m0, m4), __dmul_rn(m1, m3));
+  D = (D != 0.0) ? 1.0 / D : 0.0;
+  const double A11 = __dmul_rn(m4, D), A22 = __dmul_rn(m0, D);
+  m0 = A11;
+  m1 = __dmul_rn(m1, -D);
+  m3 = __dmul_rn(m3, -D);
+  m4 = A22;
+  const double b1 = __dsub_rn(__dmul_rn(-m0, m2), __dmul_rn(m1, m5));
+  const double b2 = __dsub_rn(__dmul_rn(-m3, m2), __dmul_rn(m4, m5));
+  m2 = b1;
+  m5 = b2;
+  const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(m0, (double)x), 1024.0));
+  const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(m3, (double)x), 1024.0));
+  const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)y), m2), 1024.0)) + 16;
+  const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)y), m5), 1024.0)) + 16;
+  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+  int sx = X >> 5, sy = Y >> 5;
+  sx = min(max(sx, -32768), 32767);
+  sy = min(max(sy, -32768), 32767);
+  const int16_t *wt = g_cubic_itab + (((Y & 31) * 32 + (X & 31)) << 4);
+  int xs[4], ys[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    xs[k] = min(max(sx - 1 + k, 0), W - 1);
+    ys[k] = min(max(sy - 1 + k, 0), H - 1);
+  }
+  for (int c = 0; c < C; ++c) {
+    int acc = 0;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx)
+        acc += (int)wt[ky * 4 + kx] * (int)im[((size_t)ys[ky] * W + xs[kx]) * C + c];
+    int v = (acc + 16384) >> 15;
+    o[c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+// Host: OpenCV's interpolateCubic + initInterTab2D (fp32, unfused), incl. the ksize/2 quirk.
+static void build_cubic_itab(int16_t *out) {
+  const float A = -0.75f;
+  float tab[32][4];
+  for (int i = 0; i < 32; ++i) {
+    volatile float t = (float)i / 32.0f;
+    volatile float x1 = t + 1.0f;
+    volatile float c0 = A * x1;
+    c0 = c0 - 5.0f * A; c0 = c0 * x1; c0 = c0 + 8.0f * A; c0 = c0 * x1; c0 = c0 - 4.0f * A;
+    volatile float c1 = (A + 2.0f) * t;
+    c1 = c1 - (A + 3.0f); c1 = c1 * t; c1 = c1 * t; c1 = c1 + 1.0f;
+    volatile float u = 1.0f - t;
+    volatile float c2 = (A + 2.0f) * u;
+    c2 = c2 - (A + 3.0f); c2 = c2 * u; c2 = c2 * u; c2 = c2 + 1.0f;
+    volatile float c3 = 1.0f - c0;
+    c3 = c3 - c1; c3 = c3 - c2;
+    tab[i][0] = c0; tab[i][1] = c1; tab[i][2] = c2; tab[i][3] = c3;
+  }
+  for (int fy = 0; fy < 32; ++fy)
+    for (int fx = 0; fx < 32; ++fx) {
+      int iw[4][4];
+      int sum = 0;
+      for (int ky = 0; ky < 4; ++ky)
+        for (int kx = 0; kx < 4; ++kx) {
+          volatile float v = tab[fy][ky] * tab[fx][kx];
+          volatile float sc = v * 32768.0f;
+          long r = lrintf(sc);
+          if (r > 32767) r = 32767;
+          if (r < -32768) r = -32768;
+          iw[ky][kx] = (int)r;
+          sum += (int)r;
+        }
+      if (sum != 32768) {
+        const int diff = sum - 32768;
+        int mk1 = 2, mk2 = 2, Mk1 = 2, Mk2 = 2;
+        for (int k1 = 2; k1 < 4; ++k1)
+          for (int k2 = 2; k2 < 4; ++k2) {
+            if (iw[k1][k2] < iw[mk1][mk2]) { mk1 = k1; mk2 = k2; }
+            else if (iw[k1][k2] > iw[Mk1][Mk2]) { Mk1 = k1; Mk2 = k2; }
+          }
+        if (diff < 0) iw[Mk1][Mk2] = (int16_t)(iw[Mk1][Mk2] - diff);
+        else iw[mk1][mk2] = (int16_t)(iw[mk1][mk2] - diff);
+      }
+      for (int ky = 0; ky < 4; ++ky)
+        for (int kx = 0; kx < 4; ++kx) out[(fy * 32 + fx) * 16 + ky * 4 + kx] = (int16_t)iw[ky][kx];
+    }
+}
+
+static int ensure_itab() {
+  static int state = 0;  // per process; tables are tiny
+  static int dev_done[64] = {0};
+  int dev = 0;
+  OCRB_CUDA(cudaGetDevice(&dev));
+  (void)state;
+  if (dev < 64 && dev_done[dev]) return OCRB_OK;
+  static int16_t host_tab[1024 * 16];
+  build_cubic_itab(host_tab);
+  OCRB_CUDA(cudaMemcpyToSymbol(g_cubic_itab, host_tab, sizeof(host_tab)));
+  if (dev < 64) dev_done[dev] = 1;
+  return OCRB_OK;
+}
+
+}  // namespace ocrb
+
+using namespace ocrb;
+
+extern "C" int ocrb_rgb2gray_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t H, int32_t W, void *stream) {
+  OCRB_REQUIRE(src && dst && n_img > 0 && H > 0 && W > 0, "rgb2gray_u8: bad arguments");
+  OCRB_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "rgb2gray_u8: pointers must be 16-byte aligned");
+  const size_t npix = (size_t)n_img * H * W;
+  const int threads = 256;
+  const long long nthr = (long long)((npix + 15) / 16);
+  rgb2gray_kernel<<<cdiv(nthr, threads), threads, 0, (cudaStream_t)stream>>>(src, dst, npix);
+  return check_launch("rgb2gray_kernel");
+}
+
+extern "C" int ocrb_clahe_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t H, int32_t W, uint8_t *lut_ws,
+                             void *stream) {
+  OCRB_REQUIRE(src && dst && lut_ws && n_img > 0 && H > 0 && W > 0, "clahe_u8: bad arguments");
+  int We = W, He = H;
+  if (!(W % 8 == 0 && H % 8 == 0)) {
+    We = W + (8 - W % 8);
+    He = H + (8 - H % 8);
+  }
+  const int tw = We / 8, th = He / 8;
+  OCRB_REQUIRE(tw >= 1 && th >= 1 && tw <= W && th <= H, "clahe_u8: image too small for an 8x8 tile grid");
+  const int area = tw * th;
+  int clip = (int)(3.0 * area / 256.0);
+  if (clip < 1) clip = 1;
+  volatile float lut_scale = 255.0f / (float)area;
+  clahe_lut_kernel<<<dim3(64, n_img), 256, 0, (cudaStream_t)stream>>>(src, lut_ws, H, W, tw, th, clip, lut_scale);
+  int rc = check_launch("clahe_lut_kernel");
+  if (rc) return rc;
+  volatile float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+  clahe_apply_kernel<<<dim3(cdiv(W, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, lut_ws, H, W, inv_tw, inv_th);
+  return check_launch("clahe_apply_kernel");
+}
+
+extern "C" int ocrb_adaptive_gauss_thresh_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t H, int32_t W,
+                                             void *stream) {
+  OCRB_REQUIRE(src && dst && n_img > 0 && H > 0 && W > 0, "adaptive_gauss_thresh_u8: bad arguments");
+  adaptive_thresh_kernel<<<dim3(cdiv(W, AT_TW), cdiv(H, AT_TH), n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W);
+  return check_launch("adaptive_thresh_kernel");
+}
+
+extern "C" int ocrb_sharpen3x3_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                                  void *stream) {
+  OCRB_REQUIRE(src && dst && n_img > 0 && H > 1 && W > 1 && (C == 1 || C == 3), "sharpen3x3_u8: bad arguments");
+  sharpen_kernel<<<dim3(cdiv((long long)W * C, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, C);
+  return check_launch("sharpen_kernel");
+}
+
+extern "C" int ocrb_deskew_angle(const uint8_t *src, int32_t n_img, int32_t H, int32_t W, int32_t C, double *out_angle,
+                                 double *out_M, int32_t *ext_ws, int32_t *hull_ws, void *stream) {
+  OCRB_REQUIRE(src && out_angle && out_M && ext_ws && hull_ws, "deskew_angle: null pointer");
+  OCRB_REQUIRE(n_img > 0 && H > 0 && W > 0 && (C == 1 || C == 3), "deskew_angle: bad sizes");
+  const int rows = n_img * H;
+  dark_extents_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(src, ext_ws, H, W, C, rows);
+  int rc = check_launch("dark_extents_kernel");
+  if (rc) return rc;
+  deskew_angle_kernel<<<n_img, 256, 0, (cudaStream_t)stream>>>(ext_ws, H, W, out_angle, out_M, hull_ws);
+  return check_launch("deskew_angle_kernel");
+}
+
+extern "C" int ocrb_warp_affine_cubic_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t H, int32_t W,
+                                         int32_t C, const double *M, void *stream) {
+  OCRB_REQUIRE(src && dst && M && n_img > 0 && H > 0 && W > 0 && (C == 1 || C == 3), "warp_affine_cubic_u8: bad arguments");
+  OCRB_REQUIRE(src != dst, "warp_affine_cubic_u8: in-place not supported");
+  int rc = ensure_itab();
+  if (rc) return rc;
+  warp_affine_cubic_kernel<<<dim3(cdiv(W, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, C, M);
+  return check_launch("warp_affine_cubic_kernel");
+}

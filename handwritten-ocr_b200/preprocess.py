@@ -1,0 +1,175 @@
+"""Preprocessing strategies of the read path on the GPU (reference: ocr_agent/tools.py:496-673).
+
+Pages live in HBM as uint8 tensors [n, H, W, 3] (RGB) or [n, H, W] (gray, PIL mode "L"); every
+transform is one or two hand-written kernels called through the C ABI and is bit-exact against the
+reference's OpenCV result.  A whole batch of same-sized pages goes through each kernel in one launch.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# name -> implemented on the GPU?  (tools.py:623-630 registers these six)
+TRANSFORMS = ("high_contrast", "binarize", "sharpen", "deskew", "denoise", "remove_lines")
+_NOT_YET = {"denoise": "fastNlMeansDenoising", "remove_lines": "Telea inpaint"}
+
+
+def _check(x: torch.Tensor):
+    if not (x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous()):
+        raise ValueError("expected a contiguous CUDA uint8 tensor [n,H,W,3] or [n,H,W]")
+    if x.dim() == 4 and x.shape[-1] != 3:
+        raise ValueError("only RGB (3 channels) or gray pages are supported (reference: tools.py:656 keeps the file's mode)")
+    if x.dim() not in (3, 4):
+        raise ValueError("expected [n,H,W,3] or [n,H,W]")
+
+
+def to_gray(x: torch.Tensor) -> torch.Tensor:
+    """cv2.cvtColor(RGB2GRAY) when 3-D, identity when already gray (tools.py:510)."""
+    _check(x)
+    if x.dim() == 3:
+        return x
+    n, H, W, _ = x.shape
+    out = torch.empty((n, H, W), dtype=torch.uint8, device=x.device)
+    _lib.call("ocrb_rgb2gray_u8", _lib.ptr(x), _lib.ptr(out), n, H, W, _lib.stream_ptr())
+    return out
+
+
+def high_contrast(x: torch.Tensor) -> torch.Tensor:
+    """tools._apply_high_contrast (tools.py:503-516): gray + CLAHE(3.0, 8x8) -> "L"."""
+    g = to_gray(x)
+    n, H, W = g.shape
+    out = torch.empty_like(g)
+    lut = torch.empty((n, 64, 256), dtype=torch.uint8, device=g.device)
+    _lib.call("ocrb_clahe_u8", _lib.ptr(g), _lib.ptr(out), n, H, W, _lib.ptr(lut), _lib.stream_ptr())
+    return out
+
+
+def binarize(x: torch.Tensor) -> torch.Tensor:
+    """tools._apply_binarize (tools.py:519-531): gray + adaptive Gaussian threshold 21/10 -> "L"."""
+    g = to_gray(x)
+    n, H, W = g.shape
+    out = torch.empty_like(g)
+    _lib.call("ocrb_adaptive_gauss_thresh_u8", _lib.ptr(g), _lib.ptr(out), n, H, W, _lib.stream_ptr())
+    return out
+
+
+def sharpen(x: torch.Tensor) -> torch.Tensor:
+    """tools._apply_sharpen (tools.py:534-546): 3x3 [0,-1,0;-1,5,-1;0,-1,0] on every channel."""
+    _check(x)
+    n, H, W = x.shape[:3]
+    C = 3 if x.dim() == 4 else 1
+    out = torch.empty_like(x)
+    _lib.call("ocrb_sharpen3x3_u8", _lib.ptr(x), _lib.ptr(out), n, H, W, C, _lib.stream_ptr())
+    return out
+
+
+def deskew_angle(x: torch.Tensor):
+    """Rotation angle (degrees, NaN = leave unchanged) and forward matrix per page (tools.py:556-567)."""
+    _check(x)
+    n, H, W = x.shape[:3]
+    C = 3 if x.dim() == 4 else 1
+    dev = x.device
+    angle = torch.empty(n, dtype=torch.float64, device=dev)
+    M = torch.empty((n, 6), dtype=torch.float64, device=dev)
+    ext = torch.empty((n, H, 3), dtype=torch.int32, device=dev)
+    hull = torch.empty((n, (4 * H + 8) * 2), dtype=torch.int32, device=dev)
+    _lib.call("ocrb_deskew_angle", _lib.ptr(x), n, H, W, C, _lib.ptr(angle), _lib.ptr(M), _lib.ptr(ext),
+              _lib.ptr(hull), _lib.stream_ptr())
+    return angle, M
+
+
+def warp_affine(x: torch.Tensor, M: torch.Tensor) -> torch.Tensor:
+    """cv2.warpAffine(INTER_CUBIC, BORDER_REPLICATE) with per-page forward matrices M [n,6] float64."""
+    _check(x)
+    n, H, W = x.shape[:3]
+    C = 3 if x.dim() == 4 else 1
+    M = M.to(device=x.device, dtype=torch.float64).contiguous()
+    out = torch.empty_like(x)
+    _lib.call("ocrb_warp_affine_cubic_u8", _lib.ptr(x), _lib.ptr(out), n, H, W, C, _lib.ptr(M), _lib.stream_ptr())
+    return out
+
+
+def deskew(x: torch.Tensor, M: torch.Tensor | None = None) -> torch.Tensor:
+    """tools._apply_deskew (tools.py:549-573); same mode/shape as the input."""
+    if M is None:
+        _, M = deskew_angle(x)
+    return warp_affine(x, M)
+
+
+def apply_transform(x: torch.Tensor, name: str) -> torch.Tensor:
+    if name == "high_contrast":
+        return high_contrast(x)
+    if name == "binarize":
+        return binarize(x)
+    if name == "sharpen":
+        return sharpen(x)
+    if name == "deskew":
+        return deskew(x)
+    if name in _NOT_YET:
+        raise NotImplementedError(
+            f"transform '{name}' ({_NOT_YET[name]}) has no GPU kernel yet (SURVEY §8 f3) and this "
+            "package has no CPU fallback")
+    raise KeyError(name)
+
+
+def apply_strategy(x: torch.Tensor, strategy) -> torch.Tensor:
+    """Chain of transforms, left to right (tools.py:645-665). Unknown names are skipped with the
+    reference's message; "original" is a no-op."""
+    steps = [strategy] if isinstance(strategy, str) else list(strategy)
+    for step in steps:
+        if step == "original":
+            continue
+        if step not in TRANSFORMS:
+            print(f"  [preprocess] Unknown transform '{step}', skipping")
+            continue
+        x = apply_transform(x, step)
+    return x
+
+
+# ───────────── HF image-processor stage (run_ocr side) ─────────────
+def smart_resize(H: int, W: int, factor: int = 28, min_pixels: int = 256 * 256, max_pixels: int = 1024 * 1024):
+    import ctypes
+    oh, ow = ctypes.c_int32(), ctypes.c_int32()
+    _lib.call("ocrb_smart_resize_host", H, W, factor, min_pixels, max_pixels, ctypes.byref(oh), ctypes.byref(ow))
+    return oh.value, ow.value
+
+
+def resize(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """torchvision uint8 bicubic-antialias resize semantics (HF image_processing_backends.py:200-251)."""
+    _check(x)
+    n, H, W = x.shape[:3]
+    C = 3 if x.dim() == 4 else 1
+    shape = (n, out_h, out_w, 3) if C == 3 else (n, out_h, out_w)
+    out = torch.empty(shape, dtype=torch.uint8, device=x.device)
+    tmp = torch.empty((n * H * out_w * C,), dtype=torch.uint8, device=x.device)
+    _lib.call("ocrb_resize_bicubic_aa_u8", _lib.ptr(x), _lib.ptr(out), _lib.ptr(tmp), n, H, W, C, out_h, out_w,
+              _lib.stream_ptr())
+    return out
+
+
+def pixel_values(x: torch.Tensor, *, dtype=torch.bfloat16, group_perm: torch.Tensor | None = None,
+                 min_pixels: int = 256 * 256, max_pixels: int = 1024 * 1024):
+    """HF Qwen2VLImageProcessor on device pages: smart_resize -> resize -> normalize -> patchify.
+    Gray pages are replicated to three channels (PIL convert("RGB"), HF image_utils.py:462-501).
+    Returns (pixel_values [n*gh*gw, 1176], (gh, gw))."""
+    _check(x)
+    n, H, W = x.shape[:3]
+    C = 3 if x.dim() == 4 else 1
+    rh, rw = smart_resize(H, W, 28, min_pixels, max_pixels)
+    r = x if (rh, rw) == (H, W) else resize(x, rh, rw)
+    gh, gw = rh // 14, rw // 14
+    out = torch.empty((n * gh * gw, 1176), dtype=dtype, device=x.device)
+    code = {torch.float32: 0, torch.bfloat16: 1}[dtype]
+    _lib.call("ocrb_normalize_patchify", _lib.ptr(r), _lib.ptr(out), n, rh, rw, C, _lib.ptr(group_perm), code,
+              _lib.stream_ptr())
+    return out, (gh, gw)
+
+
+def to_device(pages) -> torch.Tensor:
+    """numpy page(s) [H,W,3]/[H,W] or a list of same-sized pages -> CUDA uint8 batch."""
+    if isinstance(pages, np.ndarray):
+        pages = [pages]
+    arr = np.stack([np.ascontiguousarray(p) for p in pages], 0)
+    return torch.from_numpy(arr).pin_memory().cuda(non_blocking=True)

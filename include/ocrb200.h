@@ -1,0 +1,193 @@
+/* libocrb200 -- C ABI of the B200-native OCR read path.
+ *
+ * This is the drop-in boundary for the reference's `ocr_agent.tools` hot functions
+ * (/root/reference/ocr_agent/tools.py).  The reference is pure Python; its "FFI" for
+ * this path would be a ctypes binding, shown in INTEGRATION.md.  Every entry point:
+ *   - is `extern "C"`, takes plain pointers / sizes (no torch types);
+ *   - returns 0 on success, a negative OCRB_E* code on failure (text via ocrb_last_error());
+ *   - takes DEVICE pointers unless the parameter name ends in `_host`;
+ *   - launches on the given `stream` (a cudaStream_t passed as void*) and does not synchronise
+ *     unless stated.
+ * sm_100a only.  There is no CPU fallback anywhere in this library.
+ */
+#ifndef OCRB200_H
+#define OCRB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCRB_OK 0
+#define OCRB_EINVAL (-1)
+#define OCRB_ECUDA (-2)
+#define OCRB_EUNSUPPORTED (-3)
+
+/* ───────────── library ───────────── */
+int ocrb_version(void);              /* 100*major + minor */
+const char *ocrb_last_error(void);   /* thread-local text of the last failure */
+/* Number of kernel launches this library has issued in this process (bench `gpu_launches`). */
+uint64_t ocrb_launch_count(void);
+void ocrb_launch_count_reset(void);
+
+/* ───────────── text ops: tools.py:69-100 (levenshtein, _levenshtein_words) ─────────────
+ * One warp per pair, anti-diagonal wavefront.  seq*: concatenated int32 symbols (code points or
+ * word ids); off*: n_pairs+1 int32 offsets.  out[p] = unit-cost edit distance of pair p.
+ * workspace: int32[n_pairs * (max_len_b + 1)]. */
+int ocrb_levenshtein_batch(const int32_t *seq_a, const int32_t *off_a, const int32_t *seq_b,
+                           const int32_t *off_b, int32_t n_pairs, int32_t max_len_b,
+                           int32_t *out, int32_t *workspace, void *stream);
+
+/* tools.py:465-493 (_align_to_backbone): LCS table + backtrack with the reference tie rule
+ * (`dp[i-1][j] >= dp[i][j-1]` -> up).  Symbols are ids of LOWER-CASED words.  One CTA per pair.
+ * aligned: int32[total backbone symbols] (same offsets as off_bb): index into the pair's word
+ * list, or -1.  workspace: uint8[sum_p n_p*m_p] direction table; ws_off: int64[n_pairs] offsets
+ * into it.  max_len_bb bounds the shared-memory diagonals (<= 16000). */
+int ocrb_lcs_align_batch(const int32_t *seq_bb, const int32_t *off_bb, const int32_t *seq_w,
+                         const int32_t *off_w, int32_t n_pairs, int32_t max_len_bb,
+                         int32_t *aligned, uint8_t *workspace, const int64_t *ws_off, void *stream);
+
+/* ───────────── image ops: tools.py:503-573 via OpenCV 4.13 semantics ─────────────
+ * Images are uint8, HWC (C = 1 or 3), n_img images of identical H x W, contiguous. */
+
+/* tools.py:510 cv2.cvtColor(RGB2GRAY): Y = (9798R + 19235G + 3735B + 16384) >> 15 */
+int ocrb_rgb2gray_u8(const uint8_t *src_rgb, uint8_t *dst_gray, int32_t n_img, int32_t H,
+                     int32_t W, void *stream);
+
+/* tools.py:511-512 cv2.createCLAHE(3.0,(8,8)).apply(gray).  lut_ws: uint8[n_img*64*256]. */
+int ocrb_clahe_u8(const uint8_t *src_gray, uint8_t *dst_gray, int32_t n_img, int32_t H, int32_t W,
+                  uint8_t *lut_ws, void *stream);
+
+/* tools.py:527-529 cv2.adaptiveThreshold(gray,255,GAUSSIAN_C,BINARY,21,10) */
+int ocrb_adaptive_gauss_thresh_u8(const uint8_t *src_gray, uint8_t *dst_gray, int32_t n_img,
+                                  int32_t H, int32_t W, void *stream);
+
+/* tools.py:541-542 cv2.filter2D(img,-1,[[0,-1,0],[-1,5,-1],[0,-1,0]]), reflect-101 */
+int ocrb_sharpen3x3_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t H, int32_t W,
+                       int32_t C, void *stream);
+
+/* tools.py:556-564: dark-pixel (<128) row extents -> convex hull -> min-area-rect angle ->
+ * rotation matrix about (W//2, H//2).  src has C channels (gray computed on the fly for C=3).
+ * out_angle: double[n_img] (NaN when <= 100 dark pixels: image must be left unchanged),
+ * out_M: double[n_img*6] forward matrix of cv2.getRotationMatrix2D.
+ * ext_ws: int32[n_img*H*3].  hull_ws: int32[n_img*(4*H+8)*2]. */
+int ocrb_deskew_angle(const uint8_t *src, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                      double *out_angle, double *out_M, int32_t *ext_ws, int32_t *hull_ws,
+                      void *stream);
+
+/* tools.py:568-570 cv2.warpAffine(img, M, (W,H), INTER_CUBIC, BORDER_REPLICATE).  M: double[n_img*6]
+ * on the device (forward matrix; inverted in-kernel as OpenCV does).  An image whose M[0] is NaN
+ * is copied unchanged (the `<= 100 dark pixels` early return). */
+int ocrb_warp_affine_cubic_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t H,
+                              int32_t W, int32_t C, const double *M, void *stream);
+
+/* HF image_processing_qwen2_vl.py:62-88 smart_resize (host arithmetic, no device work). */
+int ocrb_smart_resize_host(int32_t H, int32_t W, int32_t factor, int64_t min_pixels,
+                           int64_t max_pixels, int32_t *out_H, int32_t *out_W);
+
+/* torchvision uint8 bicubic-antialias resize (horizontal pass, uint8 intermediate, vertical pass).
+ * tmp: uint8[n_img*H*outW*C]. */
+int ocrb_resize_bicubic_aa_u8(const uint8_t *src, uint8_t *dst, uint8_t *tmp, int32_t n_img,
+                              int32_t H, int32_t W, int32_t C, int32_t out_H, int32_t out_W,
+                              void *stream);
+
+/* HF rescale+normalize+patchify: y=(float(x)-mean*255)/(std*255), frame duplicated x2, written as
+ * [n_img*gh*gw, 1176] in 2x2 merge-group order.  src: HWC with C in {1,3} (C=1 is replicated,
+ * = PIL convert("RGB") of an "L" image).  group_perm: optional int32[n_img*gh*gw/4] gather map
+ * (output group g reads source group group_perm[g], global index) or NULL.
+ * out_dtype: 0 = fp32 (HF `pixel_values`), 1 = bf16 (what the vision tower consumes). */
+int ocrb_normalize_patchify(const uint8_t *src, void *dst, int32_t n_img, int32_t H, int32_t W,
+                            int32_t C, const int32_t *group_perm, int32_t out_dtype, void *stream);
+
+/* ───────────── dense ops of the VLM (HF modeling_qwen2_5_vl.py) ───────────── */
+
+/* Epilogues of ocrb_gemm_bf16 */
+#define OCRB_EPI_NONE 0      /* D = bf16(acc [+ bias]) */
+#define OCRB_EPI_RESIDUAL 1  /* D = bf16( bf16(acc [+ bias]) + residual ) */
+#define OCRB_EPI_SWIGLU 2    /* weight rows interleaved per 64: [gate64|up64]; D[:, n/2] =
+                                bf16( bf16(silu(bf16(g))) * bf16(u) ), g/u = acc [+ bias] */
+#define OCRB_EPI_GELU 3      /* D = bf16(gelu_erf(bf16(acc + bias))) */
+
+/* D[M,N'] = epilogue(A[M,K] * W[N,K]^T).  A, W, D, residual: bf16 row-major with row strides
+ * lda/ldw/ldd/ldr (elements, multiples of 8).  bias: bf16[N] or NULL.  tcgen05 + TMEM + TMA. */
+int ocrb_gemm_bf16(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd,
+                   int32_t M, int32_t N, int32_t K, const void *bias, const void *residual,
+                   int64_t ldr, int32_t epilogue, void *stream);
+
+/* Skinny GEMM for decode (M = B <= 16 rows): weight-streaming, HBM-bound.  Same epilogues.
+ * Optional fused RMSNorm prologue: if norm_w != NULL, A is first normalised row-wise the HF way
+ * (fp32 normalise -> bf16 -> * weight in bf16) with `eps`.  out_f32 != NULL additionally stores
+ * fp32(bf16(acc)) (used for lm_head logits). */
+int ocrb_gemv_bf16(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd,
+                   int32_t B, int32_t N, int32_t K, const void *bias, const void *residual,
+                   int64_t ldr, int32_t epilogue, const void *norm_w, float eps, void *stream);
+
+/* HF Qwen2_5_VLRMSNorm (modeling:66-71): y = w * bf16( x_f32 * rsqrt(mean(x^2)+eps) ) */
+int ocrb_rmsnorm_bf16(const void *x, int64_t ldx, const void *w, void *y, int64_t ldy, int32_t rows,
+                      int32_t dim, float eps, void *stream);
+
+/* Vision 2-D RoPE (modeling:156-167) applied in place to q and k inside a fused qkv buffer
+ * [S, 3*heads*hd]: fp32 math, bf16 out.  cos/sin: fp32 [S, hd]. */
+int ocrb_rope_vision(void *qkv, int32_t S, int32_t heads, int32_t hd, const float *cos,
+                     const float *sin, void *stream);
+
+/* Text mRoPE (modeling:659-669) in bf16 arithmetic as HF does (cos/sin already bf16, already
+ * section-mixed per token: [T, hd]).  q: [T, n_q*hd] (stride ldq), k: [T, n_kv*hd] (stride ldk). */
+int ocrb_rope_text(void *q, int64_t ldq, void *k, int64_t ldk, int32_t T, int32_t n_q, int32_t n_kv,
+                   int32_t hd, const void *cos, const void *sin, void *stream);
+
+/* Variable-length flash attention (non-causal or causal), bf16 in/out, fp32 softmax.
+ * q: [T, n_q, hd] strides (ldq per token), k/v: [T, n_kv, hd]; cu_seqlens: int32[n_seq+1];
+ * n_q % n_kv == 0 (GQA).  hd in {80, 128}.  out: [T, n_q*hd] stride ldo. */
+int ocrb_attention_varlen(const void *q, int64_t ldq, const void *k, int64_t ldk, const void *v,
+                          int64_t ldv, void *out, int64_t ldo, const int32_t *cu_seqlens,
+                          int32_t n_seq, int32_t max_seqlen, int32_t n_q, int32_t n_kv, int32_t hd,
+                          float scale, int32_t causal, void *stream);
+
+/* Paged KV cache: pages of `page_size` tokens; k_cache/v_cache: bf16 [n_pages, page_size, n_kv, hd].
+ * block_table: int32[B, max_pages_per_seq].  ctx_len: int32[B] on the device (tokens already cached). */
+
+/* Scatter T tokens of k/v (prefill) into the paged cache: token t of sequence s goes to
+ * position pos0[s] + (t - cu_seqlens[s]). */
+int ocrb_kv_write_prefill(const void *k, int64_t ldk, const void *v, int64_t ldv, void *k_cache,
+                          void *v_cache, const int32_t *block_table, int32_t max_pages,
+                          const int32_t *cu_seqlens, int32_t n_seq, int32_t T, int32_t page_size,
+                          int32_t n_kv, int32_t hd, void *stream);
+
+/* One decode step of attention for B sequences: applies mRoPE (bf16) to q,k of the new token,
+ * appends k,v at position ctx_len[b], attends over ctx_len[b]+1 tokens.  qkv: [B, (n_q+2*n_kv)*hd].
+ * cos/sin: bf16 [B, hd] for this step.  out: [B, n_q*hd]. */
+int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cache, void *v_cache,
+                          const int32_t *block_table, int32_t max_pages, const int32_t *ctx_len,
+                          int32_t B, int32_t page_size, int32_t n_q, int32_t n_kv, int32_t hd,
+                          const void *cos, const void *sin, float scale, void *out, int64_t ldo,
+                          float *split_ws, int32_t n_splits, void *stream);
+
+/* Greedy pick (HF generation/utils.py:2793 argmax over fp32 logits, lowest index on ties) +
+ * sequence bookkeeping for one decode step, all on the device:
+ *   tok = argmax(logits[b]); if finished[b] tok = pad; out_tokens[b*max_new + step[0]] = tok;
+ *   finished[b] |= tok == eos; ctx_len[b] += 1; next_ids[b] = tok; (step[0] += 1 by block 0)
+ * logits: bf16 [B, V] (stride ldl). */
+int ocrb_argmax_step(const void *logits, int64_t ldl, int32_t B, int32_t V, int32_t eos,
+                     int32_t pad, int32_t max_new, int32_t *out_tokens, int32_t *next_ids,
+                     int32_t *finished, int32_t *ctx_len, int32_t *step, int32_t advance_ctx,
+                     void *stream);
+
+/* Embedding gather: out[t] = table[ids[t]] (bf16 rows of `dim`). */
+int ocrb_embed_gather(const void *table, const int32_t *ids, void *out, int32_t T, int32_t dim,
+                      void *stream);
+
+/* Row gather/scatter of bf16 rows: dst[dst_idx[i]] = src[src_idx[i]] (NULL index = identity). */
+int ocrb_rows_copy(const void *src, int64_t lds, const int32_t *src_idx, void *dst, int64_t ldd,
+                   const int32_t *dst_idx, int32_t n_rows, int32_t dim, void *stream);
+
+/* Per-step mRoPE tables for decode: pos[b] = ctx_len[b] + rope_delta[b]; writes bf16 cos/sin [B, hd]
+ * (all three mrope sections share the position for text tokens). inv_freq: fp32[hd/2]. */
+int ocrb_decode_rope_table(const int32_t *ctx_len, const int32_t *rope_delta, const float *inv_freq,
+                           int32_t B, int32_t hd, void *cos, void *sin, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCRB200_H */

@@ -1,0 +1,304 @@
+"""GPU numerics of the dense VLM kernels through the C ABI vs plain PyTorch references that mirror
+HF's rounding points (bf16 tensors between ops, fp32 accumulation inside them)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def L(pkg):
+    from handwritten_ocr_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+def sp():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(BF)
+
+
+def ref_linear(A, W, bias=None):
+    out = A.float() @ W.float().t()
+    if bias is not None:
+        out = out + bias.float()
+    return out.to(BF)
+
+
+def pack_swiglu(Wg, Wu):
+    """[gate64|up64] row interleave expected by OCRB_EPI_SWIGLU."""
+    I = Wg.shape[0]
+    assert I % 64 == 0
+    return torch.stack([Wg.view(I // 64, 64, -1), Wu.view(I // 64, 64, -1)], 1).reshape(2 * I, -1).contiguous()
+
+
+def close_bf16(got, want, what, ulps=2.0, frac_exact=0.97):
+    g, w = got.float(), want.float()
+    tol = ulps * 2.0 ** -8 * w.abs().clamp_min(1e-2)
+    bad = (g - w).abs() > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.numel()} beyond {ulps} bf16 ulp; max err {(g - w).abs().max().item()}"
+    ex = (g == w).float().mean().item()
+    assert ex >= frac_exact, f"{what}: only {ex:.4f} bit-equal"
+
+
+GEMM_SHAPES = [(128, 128, 64), (256, 256, 128), (300, 384, 1176), (130, 200, 72), (1000, 1280, 1280),
+               (4096, 3584, 512), (3108, 4608, 3584), (999, 5120, 5120)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain_and_bias(L, M, N, K):
+    A, W, b = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2), rnd(N, seed=3)
+    for bias in (None, b):
+        D = torch.full((M, N), float("nan"), device="cuda", dtype=BF)
+        L.call("ocrb_gemm_bf16", A.data_ptr(), K, W.data_ptr(), K, D.data_ptr(), N, M, N, K,
+               L.ptr(bias), None, 0, 0, sp())
+        torch.cuda.synchronize()
+        close_bf16(D, ref_linear(A, W, bias), f"gemm {M}x{N}x{K} bias={bias is not None}")
+
+
+def test_gemm_strided_operands(L):
+    M, N, K = 333, 256, 320
+    Abig, Wbig = rnd(M, K + 64, seed=4), rnd(N, K + 128, scale=K ** -0.5, seed=5)
+    A, W = Abig[:, 8:8 + K], Wbig[:, 16:16 + K]
+    Dbig = torch.zeros((M, N + 40), device="cuda", dtype=BF)
+    L.call("ocrb_gemm_bf16", A.data_ptr(), Abig.stride(0), W.data_ptr(), Wbig.stride(0), Dbig[:, 8:].data_ptr(),
+           Dbig.stride(0), M, N, K, None, None, 0, 0, sp())
+    torch.cuda.synchronize()
+    close_bf16(Dbig[:, 8:8 + N], ref_linear(A, W), "strided gemm")
+    assert (Dbig[:, :8] == 0).all() and (Dbig[:, 8 + N:] == 0).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 384, 256), (3108, 3584, 1024)])
+def test_gemm_residual(L, M, N, K):
+    A, W, R = rnd(M, K, seed=6), rnd(N, K, scale=K ** -0.5, seed=7), rnd(M, N, seed=8)
+    D = torch.empty((M, N), device="cuda", dtype=BF)
+    L.call("ocrb_gemm_bf16", A.data_ptr(), K, W.data_ptr(), K, D.data_ptr(), N, M, N, K, None, R.data_ptr(), N, 1, sp())
+    torch.cuda.synchronize()
+    close_bf16(D, (ref_linear(A, W).float() + R.float()).to(BF), "gemm+residual")
+
+
+@pytest.mark.parametrize("M,I,K,bias", [(200, 128, 256, False), (1000, 3456, 1280, True), (700, 2048, 512, False)])
+def test_gemm_swiglu(L, M, I, K, bias):
+    A = rnd(M, K, seed=9)
+    Wg, Wu = rnd(I, K, scale=K ** -0.5, seed=10), rnd(I, K, scale=K ** -0.5, seed=11)
+    bg, bu = rnd(I, seed=12), rnd(I, seed=13)
+    Wp = pack_swiglu(Wg, Wu)
+    bp = pack_swiglu(bg.view(-1, 1), bu.view(-1, 1)).view(-1).contiguous() if bias else None
+    D = torch.empty((M, I), device="cuda", dtype=BF)
+    L.call("ocrb_gemm_bf16", A.data_ptr(), K, Wp.data_ptr(), K, D.data_ptr(), I, M, 2 * I, K, L.ptr(bp), None, 0, 2, sp())
+    torch.cuda.synchronize()
+    g = ref_linear(A, Wg, bg if bias else None)
+    u = ref_linear(A, Wu, bu if bias else None)
+    want = torch.nn.functional.silu(g) * u
+    close_bf16(D, want, "gemm+swiglu", ulps=3.0, frac_exact=0.9)
+
+
+def test_gemm_gelu(L):
+    M, N, K = 999, 512, 640
+    A, W, b = rnd(M, K, seed=14), rnd(N, K, scale=K ** -0.5, seed=15), rnd(N, seed=16)
+    D = torch.empty((M, N), device="cuda", dtype=BF)
+    L.call("ocrb_gemm_bf16", A.data_ptr(), K, W.data_ptr(), K, D.data_ptr(), N, M, N, K, b.data_ptr(), None, 0, 3, sp())
+    torch.cuda.synchronize()
+    close_bf16(D, torch.nn.functional.gelu(ref_linear(A, W, b)), "gemm+gelu", ulps=3.0, frac_exact=0.9)
+
+
+@pytest.mark.parametrize("B", [1, 3, 5, 8])
+@pytest.mark.parametrize("N,K", [(512, 256), (4608, 3584), (3584, 18944), (1000, 328)])
+def test_gemv_plain_bias_residual(L, B, N, K):
+    X, W, b, R = rnd(B, K, seed=20), rnd(N, K, scale=K ** -0.5, seed=21), rnd(N, seed=22), rnd(B, N, seed=23)
+    for epi, bias in [(0, None), (0, b), (1, None)]:
+        D = torch.empty((B, N), device="cuda", dtype=BF)
+        L.call("ocrb_gemv_bf16", X.data_ptr(), K, W.data_ptr(), K, D.data_ptr(), N, B, N, K, L.ptr(bias),
+               R.data_ptr() if epi == 1 else None, N, epi, None, 0.0, sp())
+        torch.cuda.synchronize()
+        want = ref_linear(X, W, bias)
+        if epi == 1:
+            want = (want.float() + R.float()).to(BF)
+        close_bf16(D, want, f"gemv B={B} {N}x{K} epi={epi}")
+
+
+def hf_rmsnorm(x, w, eps):
+    xf = x.float()
+    var = xf.pow(2).mean(-1, keepdim=True)
+    return w * (xf * torch.rsqrt(var + eps)).to(x.dtype)
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_gemv_fused_norm_and_swiglu(L, B):
+    K, I = 3584, 1024
+    X, nw = rnd(B, K, seed=30), (1 + 0.1 * rnd(K, seed=31).float()).to(BF)
+    Wg, Wu = rnd(I, K, scale=K ** -0.5, seed=32), rnd(I, K, scale=K ** -0.5, seed=33)
+    Wp = pack_swiglu(Wg, Wu)
+    D = torch.empty((B, I), device="cuda", dtype=BF)
+    L.call("ocrb_gemv_bf16", X.data_ptr(), K, Wp.data_ptr(), K, D.data_ptr(), I, B, 2 * I, K, None, None, 0, 2,
+           nw.data_ptr(), 1e-6, sp())
+    torch.cuda.synchronize()
+    xn = hf_rmsnorm(X, nw, 1e-6)
+    want = torch.nn.functional.silu(ref_linear(xn, Wg)) * ref_linear(xn, Wu)
+    close_bf16(D, want, "gemv norm+swiglu", ulps=3.0, frac_exact=0.9)
+
+
+def test_gemv_batch_invariance(L):
+    """A sequence decoded in a batch must produce the bits it produces alone (SURVEY §7 hard part 1 iv)."""
+    N, K = 2048, 3584
+    X, W = rnd(5, K, seed=40), rnd(N, K, scale=K ** -0.5, seed=41)
+    D5 = torch.empty((5, N), device="cuda", dtype=BF)
+    L.call("ocrb_gemv_bf16", X.data_ptr(), K, W.data_ptr(), K, D5.data_ptr(), N, 5, N, K, None, None, 0, 0, None, 0.0, sp())
+    for b in range(5):
+        D1 = torch.empty((1, N), device="cuda", dtype=BF)
+        L.call("ocrb_gemv_bf16", X[b:b + 1].data_ptr(), K, W.data_ptr(), K, D1.data_ptr(), N, 1, N, K, None, None, 0, 0,
+               None, 0.0, sp())
+        assert torch.equal(D1[0], D5[b])
+
+
+@pytest.mark.parametrize("rows,dim", [(7, 1280), (3, 3584), (999, 5120)])
+def test_rmsnorm(L, rows, dim):
+    x, w = rnd(rows, dim, seed=50), (1 + 0.1 * rnd(dim, seed=51).float()).to(BF)
+    y = torch.empty_like(x)
+    L.call("ocrb_rmsnorm_bf16", x.data_ptr(), dim, w.data_ptr(), y.data_ptr(), dim, rows, dim, 1e-6, sp())
+    close_bf16(y, hf_rmsnorm(x, w, 1e-6), "rmsnorm", ulps=1.0, frac_exact=0.995)
+
+
+def rotate_half(x):
+    h = x.shape[-1] // 2
+    return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+
+
+def test_rope_vision(L):
+    S, H, hd = 500, 16, 80
+    qkv = rnd(S, 3 * H * hd, seed=60)
+    ang = torch.rand(S, hd // 2, device="cuda") * 50
+    emb = torch.cat((ang, ang), -1)
+    cos, sin = emb.cos().contiguous(), emb.sin().contiguous()
+    q, k, v = qkv.view(S, 3, H, hd).unbind(1)
+    qf, kf = q.float(), k.float()
+    c, s = cos.unsqueeze(-2), sin.unsqueeze(-2)
+    wq = (qf * c + rotate_half(qf) * s).to(BF)
+    wk = (kf * c + rotate_half(kf) * s).to(BF)
+    out = qkv.clone()
+    L.call("ocrb_rope_vision", out.data_ptr(), S, H, hd, cos.data_ptr(), sin.data_ptr(), sp())
+    o = out.view(S, 3, H, hd)
+    assert torch.equal(o[:, 0], wq) and torch.equal(o[:, 1], wk) and torch.equal(o[:, 2], v)
+
+
+def test_rope_text_bf16(L):
+    T, nq, nkv, hd = 77, 28, 4, 128
+    q, k = rnd(T, nq * hd, seed=61), rnd(T, nkv * hd, seed=62)
+    ang = torch.rand(T, hd // 2, device="cuda") * 100
+    emb = torch.cat((ang, ang), -1)
+    cos, sin = emb.cos().to(BF).contiguous(), emb.sin().to(BF).contiguous()
+    wq = (q.view(T, nq, hd) * cos[:, None]) + (rotate_half(q.view(T, nq, hd)) * sin[:, None])
+    wk = (k.view(T, nkv, hd) * cos[:, None]) + (rotate_half(k.view(T, nkv, hd)) * sin[:, None])
+    q2, k2 = q.clone(), k.clone()
+    L.call("ocrb_rope_text", q2.data_ptr(), nq * hd, k2.data_ptr(), nkv * hd, T, nq, nkv, hd, cos.data_ptr(),
+           sin.data_ptr(), sp())
+    assert torch.equal(q2.view(T, nq, hd), wq) and torch.equal(k2.view(T, nkv, hd), wk)
+
+
+def sdpa_ref(q, k, v, causal, scale):
+    # q: [T, H, hd] one sequence, fp32 reference
+    qf, kf, vf = (t.float().transpose(0, 1) for t in (q, k, v))
+    if kf.shape[0] != qf.shape[0]:
+        rep = qf.shape[0] // kf.shape[0]
+        kf, vf = kf.repeat_interleave(rep, 0), vf.repeat_interleave(rep, 0)
+    s = (qf @ kf.transpose(1, 2)) * scale
+    if causal:
+        T = s.shape[-1]
+        s = s.masked_fill(torch.triu(torch.ones(T, T, device=s.device, dtype=torch.bool), 1), float("-inf"))
+    return (torch.softmax(s, -1) @ vf).transpose(0, 1)
+
+
+@pytest.mark.parametrize("hd,nq,nkv,causal,lens", [
+    (80, 16, 16, 0, [64, 48, 16, 12, 64, 1]),
+    (80, 16, 16, 0, [700]),
+    (128, 28, 4, 1, [300, 65, 1]),
+    (128, 8, 8, 1, [1036]),
+    (64, 4, 2, 1, [130]),
+])
+def test_attention_varlen(L, hd, nq, nkv, causal, lens):
+    T = sum(lens)
+    q, k, v = rnd(T, nq * hd, seed=70), rnd(T, nkv * hd, seed=71), rnd(T, nkv * hd, seed=72)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    out = torch.full((T, nq * hd), float("nan"), device="cuda", dtype=BF)
+    scale = hd ** -0.5
+    L.call("ocrb_attention_varlen", q.data_ptr(), nq * hd, k.data_ptr(), nkv * hd, v.data_ptr(), nkv * hd,
+           out.data_ptr(), nq * hd, cu.data_ptr(), len(lens), max(lens), nq, nkv, hd, scale, causal, sp())
+    torch.cuda.synchronize()
+    off = 0
+    for n in lens:
+        want = sdpa_ref(q[off:off + n].view(n, nq, hd), k[off:off + n].view(n, nkv, hd), v[off:off + n].view(n, nkv, hd),
+                        bool(causal), scale)
+        got = out[off:off + n].view(n, nq, hd).float()
+        err = (got - want).abs().max().item()
+        assert err < 2e-2, f"attention len {n}: max err {err}"
+        off += n
+
+
+def test_decode_attention_paged(L):
+    B, nq, nkv, hd, page = 3, 28, 4, 128, 16
+    ctx = [100, 37, 250]
+    max_pages = 20
+    n_pages = B * max_pages
+    kc = rnd(n_pages, page, nkv, hd, seed=80)
+    vc = rnd(n_pages, page, nkv, hd, seed=81)
+    perm = torch.randperm(n_pages, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    bt = perm.view(B, max_pages).to(torch.int32).contiguous()
+    qkv = rnd(B, (nq + 2 * nkv) * hd, seed=82)
+    ang = torch.rand(B, hd // 2, device="cuda") * 100
+    emb = torch.cat((ang, ang), -1)
+    cos, sin = emb.cos().to(BF).contiguous(), emb.sin().to(BF).contiguous()
+    ctx_d = torch.tensor(ctx, dtype=torch.int32, device="cuda")
+    n_splits = 6
+    ws = torch.empty(B * nq * n_splits * (hd + 2), device="cuda", dtype=torch.float32)
+    out = torch.empty(B, nq * hd, device="cuda", dtype=BF)
+    kc0, vc0 = kc.clone(), vc.clone()
+    L.call("ocrb_decode_attention", qkv.data_ptr(), qkv.stride(0), kc.data_ptr(), vc.data_ptr(), bt.data_ptr(), max_pages,
+           ctx_d.data_ptr(), B, page, nq, nkv, hd, cos.data_ptr(), sin.data_ptr(), hd ** -0.5, out.data_ptr(), nq * hd,
+           ws.data_ptr(), n_splits, sp())
+    torch.cuda.synchronize()
+    for b in range(B):
+        q = qkv[b, :nq * hd].view(nq, hd)
+        kn = qkv[b, nq * hd:(nq + nkv) * hd].view(nkv, hd)
+        vn = qkv[b, (nq + nkv) * hd:].view(nkv, hd)
+        qr = q * cos[b] + rotate_half(q) * sin[b]
+        kr = kn * cos[b] + rotate_half(kn) * sin[b]
+        pos = torch.arange(ctx[b], device="cuda")
+        pg = bt[b, pos // page].long()
+        K = torch.cat([kc0[pg, pos % page], kr[None]], 0)   # [ctx+1, nkv, hd]
+        V = torch.cat([vc0[pg, pos % page], vn[None]], 0)
+        want = sdpa_ref(qr[None], K, V, False, hd ** -0.5)[0]
+        err = (out[b].view(nq, hd).float() - want).abs().max().item()
+        assert err < 2e-2, f"decode attention b={b}: {err}"
+        # the new token was appended at position ctx[b]
+        p_new = bt[b, ctx[b] // page].long()
+        assert torch.equal(kc[p_new, ctx[b] % page], kr)
+        assert torch.equal(vc[p_new, ctx[b] % page], vn)
+
+
+def test_argmax_step_first_index_and_eos(L):
+    B, V, max_new = 4, 152064, 8
+    logits = rnd(B, V, seed=90)
+    logits[0, 777] = 50.0
+    logits[0, 90000] = 50.0          # tie -> lowest index
+    logits[1, 151645] = 60.0         # eos
+    logits[2, V - 1] = 70.0
+    out = torch.full((B, max_new), -1, dtype=torch.int32, device="cuda")
+    nxt = torch.zeros(B, dtype=torch.int32, device="cuda")
+    fin = torch.tensor([0, 0, 0, 1], dtype=torch.int32, device="cuda")
+    ctx = torch.tensor([10, 20, 30, 40], dtype=torch.int32, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.call("ocrb_argmax_step", logits.data_ptr(), V, B, V, 151645, 151645, max_new, out.data_ptr(), nxt.data_ptr(),
+           fin.data_ptr(), ctx.data_ptr(), step.data_ptr(), 1, sp())
+    torch.cuda.synchronize()
+    assert nxt.tolist() == [777, 151645, V - 1, 151645]
+    assert out[:, 0].tolist() == nxt.tolist() and fin.tolist() == [0, 1, 0, 1]
+    assert ctx.tolist() == [11, 21, 31, 41] and step.item() == 1
+    assert nxt[0].item() == int(torch.argmax(logits[0].float()))
