@@ -370,8 +370,11 @@ static int launch_gemv(const bf16 *X, long long ldx, const bf16 *W, long long ld
   OCRB_REQUIRE(!norm || xbytes <= 200 * 1024, "gemv_bf16: fused RMSNorm needs B*K*2 <= 200 KiB of shared memory");
   const size_t smem = x_in_smem ? xbytes : 0;
   if (norm) {
-    if (smem > 48 * 1024)
+    static size_t attr_smem = 48 * 1024;  // raise the dynamic shared-memory limit once per size class
+    if (smem > attr_smem) {
       OCRB_CUDA(cudaFuncSetAttribute(gemv_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
+    }
     gemv_kernel<NB, true><<<blocks, GV_WARPS * 32, smem, st>>>(X, ldx, W, ldw, D, ldd, N, K, bias, residual, ldr, epilogue,
                                                                 norm_w, eps, true);
   } else {
@@ -423,8 +426,11 @@ extern "C" int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cac
   const size_t smem = ((size_t)G * hd + hd + (size_t)G * chunk) * sizeof(float);
   OCRB_REQUIRE(smem <= 200 * 1024, "decode_attention: chunk too large, raise n_splits");
   cudaStream_t st = (cudaStream_t)stream;
-  if (smem > 48 * 1024)
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
     OCRB_CUDA(cudaFuncSetAttribute(decode_attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
   decode_attn_partial_kernel<<<dim3(n_splits, n_kv, B), DA_THREADS, smem, st>>>(
       (const bf16 *)qkv, ldqkv, (bf16 *)k_cache, (bf16 *)v_cache, block_table, max_pages, ctx_len, page_size, n_q, n_kv, hd,
       (const bf16 *)cosT, (const bf16 *)sinT, scale, split_ws, n_splits, chunk);

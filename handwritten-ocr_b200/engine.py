@@ -1,0 +1,148 @@
+"""Batched OCR read engine: preprocessed pages in HBM -> token ids.
+
+One `read_batch` call serves every (page, strategy) candidate it is given -- the 2 initial reads and
+the tiebreaker of a page (nodes.py:86-110), or all strategies of a reocr sweep (nodes.py:239-302) --
+in ONE vision-tower pass, ONE prefill and ONE batched greedy decode over the paged KV cache, where
+the reference runs them strictly one after another with batch 1 (tools.py:744-765).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, preprocess
+from .vlm import BF, Decoder, DecodeState, PagedKV, VisionPlan, VLMWeights, text_rope_tables, vision_forward
+from .vlm_config import EOS, IMAGE_PAD, SyntheticTokenizer, VLMConfig, build_prompt_ids, rope_index
+
+OCR_PROMPT = "Extract and return all the text from this handwritten document."
+
+
+class OcrEngine:
+    def __init__(self, weights: VLMWeights, *, max_batch: int = 8, max_new_tokens: int = 2048,
+                 max_prompt: int = 1600, page_size: int = 16, tokenizer=None, min_pixels: int = 256 * 256,
+                 max_pixels: int = 1024 * 1024):
+        self.w = weights
+        self.cfg: VLMConfig = weights.cfg
+        self.dev = weights.device
+        self.tok = tokenizer or SyntheticTokenizer()
+        self.max_batch, self.max_new, self.page = max_batch, max_new_tokens, page_size
+        self.min_pixels, self.max_pixels = min_pixels, max_pixels
+        self.pages_per_seq = math.ceil((max_prompt + max_new_tokens) / page_size)
+        self.kv = PagedKV(self.cfg, max_batch * self.pages_per_seq, page_size, self.dev)
+        self.dec = Decoder(weights, self.kv, max_batch, self.pages_per_seq * page_size)
+        self._plans = {}
+        self._states = {}
+        self.timings = {}
+
+    # ───────────── stages ─────────────
+    def _plan(self, grid_hw, n):
+        key = (grid_hw, n)
+        if key not in self._plans:
+            self._plans[key] = VisionPlan(self.cfg, grid_hw, n, self.dev)
+        return self._plans[key]
+
+    def encode_images(self, pages_u8: torch.Tensor):
+        """uint8 pages [n,H,W,3] / [n,H,W] on the device -> (merged embeddings in window order, plan)."""
+        n, H, W = pages_u8.shape[:3]
+        rh, rw = preprocess.smart_resize(H, W, 28, self.min_pixels, self.max_pixels)
+        plan = self._plan((rh // 14, rw // 14), n)
+        pv, _ = preprocess.pixel_values(pages_u8, dtype=BF, group_perm=plan.group_perm, min_pixels=self.min_pixels,
+                                        max_pixels=self.max_pixels)
+        return vision_forward(self.w, plan, pv), plan
+
+    def build_inputs(self, plan: VisionPlan, prompt: str):
+        """Token ids, 3-D positions and rope delta for ONE sequence of this grid (identical for all
+        candidates of a batch: same prompt, same grid)."""
+        n_img_tok = plan.G
+        ids = build_prompt_ids(self.tok, prompt, n_img_tok)
+        pos3, delta = rope_index(ids, plan.grid_hw, self.cfg.vision.merge, self.cfg.vision.tokens_per_second)
+        return ids, pos3, delta
+
+    def read_batch(self, pages_u8: torch.Tensor, *, prompt: str = OCR_PROMPT, max_new_tokens: int | None = None,
+                   use_graph: bool = True, return_debug: bool = False):
+        """Greedy transcription token ids for each page of the batch (HF `generate` semantics:
+        tools.py:764-765 with the default GenerationConfig: greedy, eos 151645, pad = eos)."""
+        max_new = self.max_new if max_new_tokens is None else int(max_new_tokens)
+        n = pages_u8.shape[0]
+        if n > self.max_batch:
+            raise ValueError(f"batch of {n} exceeds max_batch={self.max_batch}")
+        t = self.cfg.text
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        merged, plan = self.encode_images(pages_u8)
+        ev[1].record()
+        ids, pos3, delta = self.build_inputs(plan, prompt)
+        T = len(ids)
+        if T + max_new > self.pages_per_seq * self.page:
+            raise ValueError("prompt + max_new_tokens exceeds the KV capacity this engine was built with")
+        ids_d = torch.from_numpy(np.tile(ids, n)).to(self.dev)
+        h = torch.empty((n * T, t.hidden), dtype=BF, device=self.dev)
+        _lib.call("ocrb_embed_gather", self.w.embed.data_ptr(), ids_d.data_ptr(), h.data_ptr(), n * T, t.hidden,
+                  _lib.stream_ptr())
+        # scatter image embeddings: window-order row r of image i is source group plan.group_perm[r]
+        img_pos = np.nonzero(ids == IMAGE_PAD)[0]                       # positions of the G image tokens
+        gp = plan.group_perm.cpu().numpy()                              # global group index (i*G + g)
+        dst = (gp // plan.G) * T + img_pos[gp % plan.G]
+        dst_d = torch.from_numpy(dst.astype(np.int32)).to(self.dev)
+        _lib.call("ocrb_rows_copy", merged.data_ptr(), merged.stride(0), None, h.data_ptr(), h.stride(0),
+                  dst_d.data_ptr(), merged.shape[0], t.hidden, _lib.stream_ptr())
+        pos_d = torch.from_numpy(pos3).to(self.dev)
+        cos1, sin1, inv_freq = text_rope_tables(self.cfg, pos_d)
+        cos, sin = cos1.repeat(n, 1).contiguous(), sin1.repeat(n, 1).contiguous()
+        cu = torch.arange(0, (n + 1) * T, T, dtype=torch.int32, device=self.dev)
+        # paged KV: block table per sequence
+        need = math.ceil((T + max_new) / self.page)
+        pages = [self.kv.alloc(need) for _ in range(n)]
+        bt = torch.full((n, self.pages_per_seq), 0, dtype=torch.int32)
+        for i, pg in enumerate(pages):
+            bt[i, :need] = torch.tensor(pg, dtype=torch.int32)
+        bt = bt.to(self.dev)
+        try:
+            self.dec.prefill(h, cos, sin, cu, n, T, bt)
+            last = h[T - 1::T]                                          # [n, hidden] last prompt token of each sequence
+            key = (n, max_new)
+            st = self._states.get(key)
+            if st is None:
+                st = DecodeState(self.dec, n, max_new, bt, [T] * n, [delta] * n, inv_freq)
+                self._states[key] = st
+            else:
+                st.block_table.copy_(bt)
+                st.ctx_len.fill_(T)
+                st.rope_delta.fill_(delta)
+                st.finished.zero_()
+                st.step.zero_()
+                st.out_tokens.fill_(EOS)
+            last_c = last.contiguous()
+            self.dec.logits_last(last_c, st.logits)
+            prefill_logits = st.logits.clone() if return_debug else None
+            _lib.call("ocrb_argmax_step", st.logits.data_ptr(), st.logits.stride(0), n, t.vocab, EOS, EOS, max_new,
+                      st.out_tokens.data_ptr(), st.next_ids.data_ptr(), st.finished.data_ptr(), st.ctx_len.data_ptr(),
+                      st.step.data_ptr(), 0, _lib.stream_ptr())
+            ev[2].record()
+            self.dec.decode(st, max_new - 1, use_graph=use_graph)
+            ev[3].record()
+            toks = st.out_tokens.cpu().numpy()
+            n_steps = int(st.step.cpu())
+        finally:
+            for pg in pages:
+                self.kv.release(pg)
+        torch.cuda.synchronize()
+        self.timings = {"vision_ms": ev[0].elapsed_time(ev[1]), "prefill_ms": ev[1].elapsed_time(ev[2]),
+                        "decode_ms": ev[2].elapsed_time(ev[3]), "prompt_len": T, "steps": n_steps, "batch": n}
+        # HF stops appending once every sequence is finished (finished rows are padded with eos until
+        # then); the device loop only checks every 64 steps, so trim to HF's stopping point.
+        toks = toks[:, :n_steps]
+        is_eos = toks == EOS
+        first_eos = np.where(is_eos.any(1), is_eos.argmax(1), n_steps - 1)
+        keep = int(first_eos.max()) + 1 if n_steps > 0 else 0
+        out = [toks[i, :keep].tolist() for i in range(n)]
+        if return_debug:
+            return out, {"prefill_logits": prefill_logits, "merged": merged, "plan": plan, "ids": ids, "pos3": pos3,
+                         "delta": delta}
+        return out
+
+    def detokenize(self, ids) -> str:
+        return self.tok.decode(ids, skip_special_tokens=True)
