@@ -1,0 +1,250 @@
+"""Drop-in replacement for the hot functions of the reference's `ocr_agent.tools`
+(/root/reference/ocr_agent/tools.py): same names, arguments, return values, prints and error
+behaviour, so `ocr_agent/nodes.py` and `ocr_agent/graph.py` run unchanged on top (install with
+`handwritten_ocr_b200.install()` before `ocr_agent.nodes` is imported -- INTEGRATION.md).
+
+    preprocess_image(image_path, strategy) -> str          tools.py:633
+    run_ocr(image_path, params=None) -> str                tools.py:728
+    unload_ocr_model() -> None                             tools.py:714
+    compare_versions / merge_versions / evaluate / tier1_metrics / cer / wer / levenshtein /
+    normalize_text                                         tools.py:51-139,305-350,411-493
+    transcribe(image, strategy) -> str                     = run_ocr(preprocess_image(...))  (new)
+
+Everything numerical runs in libocrb200 on the GPU; there is no CPU fallback.  Because nodes.py
+asks for reads one at a time (preprocess S0, read, preprocess S1, read, compare, maybe S2 ...), the
+first `preprocess_image` of a page speculatively preprocesses all configured GPU strategies and the
+first `run_ocr` of that page reads ALL of them in one batch (one vision pass, one prefill, one
+paged-KV decode); later calls for the same page return the cached text.
+"""
+from __future__ import annotations
+
+import gc
+import os
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+from PIL import Image, ImageOps
+
+from . import _lib, preprocess
+from .textops import (_find_differing_segments, _levenshtein_words, cer, compare_versions, evaluate,  # noqa: F401
+                      levenshtein, merge_versions, normalize_text, tier1_metrics, wer)
+
+try:  # the reference's config module when it is importable (same names are read: tools.py:23)
+    from ocr_agent import config  # type: ignore
+except Exception:  # pragma: no cover - standalone use
+    from . import default_config as config
+
+_LOSSLESS = {".png", ".bmp", ".tif", ".tiff", ".ppm", ".pgm"}
+
+# module-level model cache (tools.py:679-680)
+_ocr_engine = None
+_options = {
+    "speculative": True,        # batch all strategies of a page into one read
+    "keep_resident": True,      # unload_ocr_model() keeps the 16.6 GB of weights in the 180 GB of HBM
+    "checkpoint": os.environ.get("OCRB_CHECKPOINT"),   # dir with HF safetensors; None -> random init
+    "vlm_config": None,         # VLMConfig override (tests use the tiny config)
+    "max_batch": 8,
+    "seed": 0,
+}
+# processed path -> (device tensor [1,H,W(,3)], original path, label)
+_processed: dict = {}
+# original path -> {label: text}
+_texts: dict = {}
+# original path -> {label: processed path}
+_by_original: dict = {}
+
+
+def configure(**kw) -> None:
+    """Set engine options (see _options) before the first run_ocr."""
+    for k, v in kw.items():
+        if k not in _options:
+            raise KeyError(k)
+        _options[k] = v
+
+
+def _label(steps) -> str:
+    return "+".join(s for s in steps if s != "original")
+
+
+def _steps(strategy) -> list:
+    return [strategy] if isinstance(strategy, str) else list(strategy)
+
+
+def _gpu_supported(steps) -> bool:
+    return all(s == "original" or s not in ("denoise", "remove_lines") for s in steps)
+
+
+def _open_array(image_path: str) -> np.ndarray:
+    img = Image.open(image_path)
+    arr = np.array(img)
+    if arr.dtype != np.uint8 or not (arr.ndim == 2 or (arr.ndim == 3 and arr.shape[2] == 3)):
+        raise ValueError(f"{image_path}: mode {img.mode} not supported; pages must be RGB or L "
+                         "(the reference does not convert modes either: tools.py:656)")
+    return arr
+
+
+def _save(arr: np.ndarray, image_path: str, label: str) -> str:
+    suffix = Path(image_path).suffix or ".png"
+    tmp = tempfile.NamedTemporaryFile(suffix=suffix, delete=False, prefix=f"ocr_{label}_")
+    tmp.close()
+    Image.fromarray(arr).save(tmp.name)
+    return tmp.name
+
+
+def preprocess_image(image_path: str, strategy) -> str:
+    """tools.py:633-673: apply the strategy on the GPU, save a temp file with the input's suffix,
+    return its path ("original" / [] return the input path untouched)."""
+    steps = _steps(strategy)
+    if steps == ["original"] or not steps:
+        return image_path
+    label = _label(steps)
+    print(f"  [preprocess] Applying {label}...")
+    cached = _by_original.get(image_path, {}).get(label)
+    if cached is not None and os.path.exists(cached):
+        return cached
+    arr = _open_array(image_path)
+    x = preprocess.to_device(arr)
+    wanted = [steps]
+    if _options["speculative"]:
+        for s in getattr(config, "PREPROCESSING_STRATEGIES", []):
+            s = _steps(s)
+            if _label(s) and _gpu_supported(s) and all(_label(s) != _label(w) for w in wanted):
+                wanted.append(s)
+    result = None
+    for s in wanted:
+        lab = _label(s)
+        if lab in _by_original.get(image_path, {}):
+            continue
+        try:
+            y = preprocess.apply_strategy(x, s)
+        except NotImplementedError:
+            if s is steps:
+                raise
+            continue
+        path = _save(y[0].cpu().numpy(), image_path, lab)
+        _processed[path] = (y, image_path, lab)
+        _by_original.setdefault(image_path, {})[lab] = path
+        if s is steps:
+            result = path
+    return result if result is not None else _by_original[image_path][label]
+
+
+def _load_ocr_model():
+    """tools.py:683-711.  The checkpoint named by config.OLMOCR_MODEL cannot be downloaded offline:
+    weights come from a local safetensors directory (OCRB_CHECKPOINT) or are random-initialised at
+    the configured dimensions."""
+    global _ocr_engine
+    if _ocr_engine is not None:
+        return _ocr_engine
+    if not torch.cuda.is_available():
+        raise _lib.OcrbError("run_ocr needs a CUDA device: handwritten-ocr_b200 has no CPU fallback")
+    from .engine import OcrEngine
+    from .vlm import VLMWeights
+    from .vlm_config import VLMConfig
+    cfg = _options["vlm_config"] or VLMConfig.olmocr_7b()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    print(f"  [ocr] Loading {getattr(config, 'OLMOCR_MODEL', cfg.name)} on cuda...")
+    if _options["checkpoint"]:
+        from safetensors.torch import load_file
+        sd = {}
+        for f in sorted(Path(_options["checkpoint"]).glob("*.safetensors")):
+            sd.update(load_file(str(f), device=str(dev)))
+        w = VLMWeights.from_state_dict(cfg, sd, free_source=True)
+    else:
+        w = VLMWeights.random(cfg, dev, seed=_options["seed"])
+    _ocr_engine = OcrEngine(w, max_batch=_options["max_batch"],
+                            max_new_tokens=int(getattr(config, "OCR_MAX_NEW_TOKENS", 2048)),
+                            min_pixels=int(getattr(config, "OCR_MIN_PIXELS", 256 * 256)),
+                            max_pixels=int(getattr(config, "OCR_MAX_PIXELS", 1024 * 1024)))
+    print("  [ocr] Model loaded.")
+    return _ocr_engine
+
+
+def unload_ocr_model():
+    """tools.py:714-725.  On a 180 GB B200 the weights stay resident unless keep_resident=False."""
+    global _ocr_engine
+    if not _options["keep_resident"]:
+        _ocr_engine = None
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+    print("  [ocr] Model unloaded, memory freed.")
+
+
+def _load_page_for_model(image_path: str) -> torch.Tensor:
+    """HF load_image (image_utils.py:462-501): open, exif_transpose, convert("RGB")."""
+    img = ImageOps.exif_transpose(Image.open(image_path)).convert("RGB")
+    return preprocess.to_device(np.array(img))
+
+
+def run_ocr(image_path: str, params: dict | None = None) -> str:
+    """tools.py:728-771: greedy transcription of the (already preprocessed) image."""
+    print(f"  [ocr] Running OCR on {Path(image_path).name}...")
+    params = params or {}
+    engine = _load_ocr_model()
+    prompt = params.get("prompt", config.OCR_PROMPT)
+    max_new_tokens = int(params.get("max_new_tokens", config.OCR_MAX_NEW_TOKENS))
+    default_call = "prompt" not in params and "max_new_tokens" not in params
+    entry = _processed.get(image_path)
+    lossless = Path(image_path).suffix.lower() in _LOSSLESS
+    if entry is not None and lossless and default_call:
+        _, original, label = entry
+        texts = _texts.setdefault(original, {})
+        if label not in texts:
+            # one batched read for every preprocessed variant of this page that has no text yet
+            todo = [(lab, p) for lab, p in _by_original.get(original, {}).items() if lab not in texts]
+            todo = todo[: engine.max_batch]
+            if (label, image_path) not in todo:
+                todo = [(label, image_path)] + todo[: engine.max_batch - 1]
+            groups: dict = {}
+            for lab, p in todo:
+                groups.setdefault(tuple(_processed[p][0].shape), []).append((lab, p))
+            for same in groups.values():
+                batch = torch.cat([_processed[p][0] for _, p in same], 0)
+                toks = engine.read_batch(batch, prompt=prompt, max_new_tokens=max_new_tokens)
+                for (lab, _), tk in zip(same, toks):
+                    texts[lab] = engine.detokenize(tk)
+        result = texts[label]
+    else:
+        page = entry[0] if (entry is not None and lossless) else _load_page_for_model(image_path)
+        toks = engine.read_batch(page, prompt=prompt, max_new_tokens=max_new_tokens)
+        result = engine.detokenize(toks[0])
+    print(f"  [ocr] Done ({len(result)} chars)")
+    return result
+
+
+def transcribe(image: str, strategy) -> str:
+    """The read the pipeline's initial_ocr / reocr nodes perform (nodes.py:41,52) as one call."""
+    return run_ocr(preprocess_image(image, strategy))
+
+
+def forget(image_path: str | None = None) -> None:
+    """Drop cached preprocessed pages / texts (all, or those of one original)."""
+    keys = [image_path] if image_path else list(_by_original)
+    for k in keys:
+        for p in _by_original.pop(k, {}).values():
+            _processed.pop(p, None)
+        _texts.pop(k, None)
+
+
+# non-hot names the reference's callers import from tools (agents.py:12, transcribe.py:33,
+# eval_final.py:22): re-exported from the reference when it is importable.
+try:
+    from ocr_agent.tools import call_llm, call_llm_json, parse_ground_truth, parse_json_response  # type: ignore  # noqa: F401
+except Exception:  # pragma: no cover
+    def call_llm_json(*a, **k):
+        raise RuntimeError("call_llm_json is the reference's Ollama client (tools.py:246-299), out of scope "
+                           "here; install `ollama` so ocr_agent.tools imports, or supply your own")
+
+    call_llm = call_llm_json
+
+    def parse_ground_truth(file_path):
+        p = Path(file_path)
+        if not p.exists():
+            return None
+        raw = p.read_text(encoding="utf-8")
+        i = raw.find("## Ground Truth")
+        text = raw.strip() if i == -1 else raw[i + len("## Ground Truth"):].strip()
+        return text or None

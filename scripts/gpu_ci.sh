@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 rc=0
 for f in "$@"; do
   name=$(basename "$f" .py)
-  timeout 900 python -m pytest "$f" -q -m gpu > "gpurun_out/$name.log" 2>&1
+  timeout 900 python -m pytest "$f" -q -s -m gpu > "gpurun_out/$name.log" 2>&1
   code=$?
   echo "$name exit=$code" | tee -a gpurun_out/ci_summary.txt
   tail -n 25 "gpurun_out/$name.log"
