@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- the OCR read path's headline benchmark (BASELINE.json: page-reads/s + decode tok/s).
+
+A "step" is ONE pass of the hot path over one page's initial_ocr phase (BASELINE.json configs[1]):
+2 preprocessing strategies + the tiebreaker strategy (tools.py:633 preprocess_image x3), ONE batched
+read of the 3 candidates (vision tower -> prefill -> 512-token paged greedy decode; tools.py:728
+run_ocr x3 in the reference), then compare_versions + merge_versions (tools.py:326,411).
+`--pages P` batches P pages per step (B = 3P sequences), default 1 = configs[1] as written.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, bounded sample
+
+N > 1: launched under torchrun, one rank per GPU, pages sharded page-wise, no data-path collective
+(weak scaling: every rank reads its own pages; only the timing is reduced).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+STRATEGIES = [["deskew", "high_contrast", "binarize"], ["high_contrast", "binarize"],
+              ["deskew", "high_contrast", "sharpen"]]        # config.py:29-31 (two initial reads + tiebreaker)
+NEW_TOKENS = 512                                             # BASELINE.json configs[0..3]
+PROMPT = "Extract and return all the text from this handwritten document."   # config.py:20
+METRIC, UNIT = "ocr_page_reads_per_s", "page-reads/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ─────────────────────────────── this repo's arm ───────────────────────────────
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import handwritten_ocr_b200  # noqa: F401
+    from handwritten_ocr_b200 import _lib, engine as eng_mod, preprocess, synth, textops, tools, vlm
+    from handwritten_ocr_b200.vlm_config import VLMConfig
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this package has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    P = args.pages
+    B = 3 * P
+    cfg = VLMConfig.tiny() if args.tiny else VLMConfig.olmocr_7b()
+    w = vlm.VLMWeights.random(cfg, dev, seed=0)
+    eng = eng_mod.OcrEngine(w, max_batch=B, max_new_tokens=NEW_TOKENS, max_prompt=1600)
+    n_steps_total = args.warmup + args.steps
+    # synthetic pages: page index = global step * world*P + rank*P + p  (every rank reads its own pages)
+    n_distinct = min(n_steps_total, 4)
+    host_pages = [[synth.page((s * world + rank) * P + p) for p in range(P)] for s in range(n_distinct)]
+    dev_pages = [preprocess.to_device(pp) for pp in host_pages]
+    torch.cuda.synchronize()
+
+    def step_device(s):
+        x = dev_pages[s % n_distinct]
+        cands = [preprocess.apply_strategy(x, st) for st in STRATEGIES]          # each [P,H,W] gray
+        batch = torch.stack(cands, 1).reshape((B,) + tuple(cands[0].shape[1:]))   # page-major: p0s0,p0s1,p0s2,p1s0..
+        toks = eng.read_batch(batch, prompt=PROMPT, max_new_tokens=NEW_TOKENS)
+        texts = [eng.detokenize(t) for t in toks]
+        res = []
+        for p in range(P):
+            t3 = texts[3 * p: 3 * p + 3]
+            res.append((textops.compare_versions(t3[0], t3[1]), textops.merge_versions(t3)))
+        return toks, res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for s in range(args.warmup):
+        step_device(s)
+    barrier()
+
+    # ---- timed region (device-resident inputs) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.launch_count_reset()
+    eng.dec.replayed_launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tok_count, decode_ms, vision_ms, prefill_ms, dec_steps, kv_tok = 0, 0.0, 0.0, 0.0, 0, 0
+    barrier()
+    e0.record()
+    for s in range(args.warmup, n_steps_total):
+        toks, _ = step_device(s)
+        tok_count += sum(len(t) for t in toks)
+        tm = eng.timings
+        decode_ms += tm["decode_ms"]; vision_ms += tm["vision_ms"]; prefill_ms += tm["prefill_ms"]
+        dec_steps += tm["steps"] - 1
+        kv_tok += B * sum(tm["prompt_len"] + 1 + i for i in range(tm["steps"] - 1))
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() + eng.dec.replayed_launches
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+
+    # ---- e2e: the reference-facing calls with host inputs (PNG files -> text), copies inside ----
+    tmpdir = tempfile.mkdtemp(prefix="ocrb_bench_")
+    from PIL import Image
+    paths = []
+    for s in range(n_distinct):
+        for p in range(P):
+            fn = os.path.join(tmpdir, f"page_r{rank}_{s}_{p}.png")
+            Image.fromarray(host_pages[s][p]).save(fn)
+            paths.append(fn)
+    tools._ocr_engine = eng
+    tools.configure(speculative=True, max_batch=B)
+    tools.config.OCR_MAX_NEW_TOKENS = NEW_TOKENS
+    tools.config.PREPROCESSING_STRATEGIES = STRATEGIES
+
+    def step_e2e(s):
+        out = []
+        for p in range(P):
+            img = paths[(s % n_distinct) * P + p]
+            tools.forget(img)
+            # nodes.py:86-114 call order: read S0, read S1, compare, tiebreaker S2, merge
+            t0_ = tools.run_ocr(tools.preprocess_image(img, STRATEGIES[0]))
+            t1_ = tools.run_ocr(tools.preprocess_image(img, STRATEGIES[1]))
+            cmpd = tools.compare_versions(t0_, t1_)
+            t2_ = tools.run_ocr(tools.preprocess_image(img, STRATEGIES[2]))
+            out.append((cmpd, tools.merge_versions([t0_, t1_, t2_])))
+        return out
+
+    import contextlib
+    import io
+    e2e_steps = max(1, min(args.steps, 3))
+    with contextlib.redirect_stdout(io.StringIO()):
+        step_e2e(0)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(e2e_steps):
+            step_e2e(s + 1)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s_max = float(t.item())
+    H, W_ = host_pages[0][0].shape[:2]
+    h2d = P * (H * W_ * 3) + B * 4 * 1100                      # pages + prompt ids / index tables (approx. upper bound)
+    d2h = P * 3 * H * W_ + B * NEW_TOKENS * 4                  # preprocessed pages written back as temp files + token ids
+
+    # ---- roofline of the dominant kernel family (decode weight streaming, HBM-bound) ----
+    peak, peak_src = peaks()
+    wbytes = w.decode_weight_bytes()
+    kv_bytes_tok = cfg.text.layers * 2 * cfg.text.kv_heads * cfg.text.head_dim * 2
+    alg_bytes_step = wbytes + (kv_tok / max(dec_steps, 1)) * kv_bytes_tok + B * cfg.text.hidden * 2
+    step_ms = decode_ms / max(dec_steps, 1)
+    achieved = alg_bytes_step / (step_ms * 1e-3) / 1e9
+    # the weight-streaming kernel alone: same launches as one decode step, all layers, back to back
+    iso = eng.dec.time_weight_stream(B, reps=3)
+    roofline = {"bound": "hbm", "kernel": "gemv_kernel (decode weight streaming; whole decode step timed in situ)",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_decode_step": int(alg_bytes_step), "decode_step_ms": round(step_ms, 4),
+                "kernel_only": {"achieved": round(iso["gbs"], 1), "frac": round(iso["gbs"] / peak, 4),
+                                "launches": iso["launches"], "avg_launch_us": round(iso["avg_us"], 2),
+                                "bytes": iso["bytes"]}}
+
+    if rank == 0:
+        reads = args.steps * B * world
+        value = reads / (total_ms_max * 1e-3)
+        line = {
+            "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(total_ms_max / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: initial_ocr phase, 2 strategies + tiebreaker read batched (B=%d) on 1 "
+                                   "B200 per rank, 512 new tokens, Levenshtein agreement + majority-vote merge" % B,
+                       "pages_per_step_per_gpu": P, "page": "1024x768 RGB synthetic", "new_tokens": NEW_TOKENS,
+                       "vlm": cfg.name + " random-init bf16", "l2": "working set (16.6 GB weights) >> 126 MB L2; no flush needed",
+                       "parallelism": f"page-wise dp{world}"},
+            "decode_tok_per_s": round(tok_count * world / (total_ms_max * 1e-3), 1),
+            "decode_phase_tok_per_s": round(B * dec_steps * world / (decode_ms * 1e-3), 1),
+            "phase_ms_per_step": {"vision": round(vision_ms / args.steps, 2), "prefill": round(prefill_ms / args.steps, 2),
+                                  "decode": round(decode_ms / args.steps, 2)},
+            "e2e": {"value": round(e2e_steps * B * world / e2e_s_max, 4), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "api": "tools.preprocess_image/run_ocr/compare_versions/merge_versions on PNG files"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(cfg, host_pages[0][0], P)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ─────────────────────────────── CPU baseline / reference arm ───────────────────────────────
+_READER = None
+
+
+def cpu_sample(cfg, page, P=1):
+    """One bounded sample of the reference CPU path for one page's initial_ocr phase; returns the
+    estimated seconds of the full step and the detail of what was measured."""
+    global _READER
+    import torch
+    from PIL import Image
+    from transformers import Qwen2VLImageProcessor
+
+    from handwritten_ocr_b200 import synth
+    from handwritten_ocr_b200.vlm_config import SyntheticTokenizer, build_prompt_ids
+    from oracle import cpu_path
+    outs, t_pre, kind = cpu_path.preprocess_cpu(page)
+    ip = Qwen2VLImageProcessor(min_pixels=256 * 256, max_pixels=1024 * 1024)
+    t0 = time.perf_counter()
+    r = ip(images=[Image.fromarray(outs[0]).convert("RGB")], return_tensors="pt")
+    t_ip = time.perf_counter() - t0
+    if _READER is None:
+        _READER = cpu_path.HFCpuReader(cfg, threads=cpu_path.host_threads())
+    gh, gw = [int(v) for v in r["image_grid_thw"][0, 1:]]
+    tok = SyntheticTokenizer()
+    ids = build_prompt_ids(tok, PROMPT, gh * gw // 4)
+    rd = _READER.read(r["pixel_values"], (gh, gw), ids, 6, NEW_TOKENS)
+    texts = [synth.text(11 + i, NEW_TOKENS) for i in range(3)]
+    t_text, text_detail = cpu_path.text_ops_cpu(texts)
+    est_step = P * (t_pre + 3 * (t_ip + rd["est_read_s"]) + t_text)
+    detail = {"preprocess_s": round(t_pre, 4), "preprocess_backend": kind, "image_processor_s": round(t_ip, 4),
+              "hf_read": {k: (round(v, 5) if isinstance(v, float) else v) for k, v in rd.items()},
+              "text_ops_s": round(t_text, 3), "text": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in text_detail.items()}}
+    return est_step, detail, _READER.threads
+
+
+SAMPLE_DESC = ("per step: cv2 preprocessing of 3 strategies (full), HF image processor (1 of 3 reads), HF Qwen2.5-VL bf16 eager "
+               "generate at full width with 2 of 28 decoder layers + 2 of 32 vision blocks and 6 of 512 new tokens "
+               "(extrapolated linearly in depth and steps, x3 reads), pure-Python Levenshtein/LCS on 700-char / 160-word "
+               "prefixes scaled by DP cells")
+
+
+def cpu_baseline(cfg, page, P=1):
+    est, detail, threads = cpu_sample(cfg, page, P)
+    return {"value": round(3 * P / est, 6), "unit": UNIT, "cores": threads, "kind": "port", "sample": SAMPLE_DESC,
+            "est_step_s": round(est, 2), "detail": detail}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import handwritten_ocr_b200  # noqa: F401
+    from handwritten_ocr_b200 import synth
+    from handwritten_ocr_b200.vlm_config import VLMConfig
+    cfg = VLMConfig.olmocr_7b()
+    P = args.pages
+    ests, detail, threads = [], None, None
+    t_all0 = time.perf_counter()
+    for s in range(args.warmup + args.steps):
+        est, detail, threads = cpu_sample(cfg, synth.page(s), P)
+        if s >= args.warmup:
+            ests.append(est)
+    wall = time.perf_counter() - t_all0
+    est_step = float(np.mean(ests))
+    value = 3 * P / est_step
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 6), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(est_step * 1e3, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: initial_ocr phase of one page on the host CPU (reference path: cv2 + HF "
+                                   "transformers eager + pure-Python text ops), 512 new tokens, extrapolated from a bounded sample",
+                       "pages_per_step_per_gpu": P, "new_tokens": NEW_TOKENS, "vlm": cfg.name + " random-fill bf16"},
+            "cpu_baseline": {"value": round(value, 6), "unit": UNIT, "cores": threads, "kind": "port", "sample": SAMPLE_DESC,
+                             "wall_s_of_samples": round(wall, 1), "detail": detail},
+            "e2e": {"value": round(value, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pages", type=int, default=1, help="pages batched per step per GPU (B = 3*pages sequences)")
+    ap.add_argument("--tiny", action="store_true", help="tiny VLM dims (plumbing check only; not a bench number)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -326,7 +326,7 @@ class Decoder:
     def __init__(self, w: VLMWeights, kv: PagedKV, max_batch: int, max_ctx: int):
         self.w, self.kv, self.cfg = w, kv, w.cfg
         self.max_batch, self.max_ctx = max_batch, max_ctx
-        self._graphs = {}
+        self.replayed_launches = 0      # kernel launches issued through CUDA-graph replays (bench `gpu_launches`)
 
     # ---- prefill: T_total tokens of n_seq sequences (cu_seqlens), embeddings already assembled ----
     def prefill(self, h: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, cu: torch.Tensor, n_seq: int,
@@ -391,6 +391,44 @@ class Decoder:
                   st.out_tokens.data_ptr(), st.next_ids.data_ptr(), st.finished.data_ptr(), st.ctx_len.data_ptr(),
                   st.step.data_ptr(), 1, _sp())
 
+    def time_weight_stream(self, B: int, reps: int = 3) -> dict:
+        """Time the weight-streaming launches of one decode step alone (every layer's qkv / o / gate-up /
+        down GEMV + lm_head, back to back, CUDA events on the launching stream).  The 14 GB of weights
+        far exceed L2, so every rep streams from HBM.  Returns achieved GB/s on the algorithmic bytes
+        (each weight byte once per step)."""
+        t = self.cfg.text
+        dev = self.w.device
+        x = torch.randn((B, t.hidden), device=dev).to(BF)
+        qkv = torch.empty((B, (t.heads + 2 * t.kv_heads) * t.head_dim), dtype=BF, device=dev)
+        att = torch.randn((B, t.heads * t.head_dim), device=dev).to(BF)
+        act = torch.empty((B, t.intermediate_padded), dtype=BF, device=dev)
+        y = torch.empty_like(x)
+        logits = torch.empty((B, t.vocab), dtype=BF, device=dev)
+
+        def one():
+            for lay in self.w.layers:
+                for b0 in range(0, B, 8):
+                    sl = slice(b0, min(B, b0 + 8))
+                    gemv(x[sl], lay["qkv_w"], qkv[sl], bias=lay["qkv_b"], norm_w=lay["ln1"], eps=t.rms_eps)
+                    gemv(att[sl], lay["o_w"], y[sl], residual=x[sl], epilogue=EPI_RESIDUAL)
+                    gemv(x[sl], lay["gu_w"], act[sl], epilogue=EPI_SWIGLU, norm_w=lay["ln2"], eps=t.rms_eps)
+                    gemv(act[sl], lay["down_w"], y[sl], residual=x[sl], epilogue=EPI_RESIDUAL)
+            self.logits_last(x, logits)
+
+        one()
+        before = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = (_lib.launch_count() - before) // reps
+        ms = e0.elapsed_time(e1) / reps
+        nbytes = self.w.decode_weight_bytes()
+        return {"ms": ms, "launches": launches, "avg_us": ms * 1e3 / max(launches, 1), "bytes": nbytes,
+                "gbs": nbytes / (ms * 1e-3) / 1e9}
+
     def decode(self, st: "DecodeState", n_steps: int, use_graph: bool = True, check_every: int = 64):
         """Run up to n_steps decode steps; stops early when every sequence has emitted EOS."""
         if n_steps <= 0:
@@ -413,12 +451,15 @@ class Decoder:
             torch.cuda.current_stream().wait_stream(s)
             st.restore(snap)
             g = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
             with torch.cuda.graph(g):
                 self._step(st)
+            st.graph_launches = _lib.launch_count() - before
             st.restore(snap)
             st.graph = g
         for i in range(n_steps):
             g.replay()
+            self.replayed_launches += st.graph_launches
             if (i + 1) % check_every == 0 and bool(st.finished.all()):
                 break
 
@@ -453,6 +494,7 @@ class DecodeState:
         self.n_splits = int(min(max(want, math.ceil(max_ctx / 512)), max(1, max_ctx // 32)))
         self.split_ws = torch.empty(B * t.heads * self.n_splits * (t.head_dim + 2), dtype=torch.float32, device=dev)
         self.graph = None
+        self.graph_launches = 0
 
     def snapshot(self):
         return [x.clone() for x in (self.ctx_len, self.next_ids, self.finished, self.step, self.out_tokens)]

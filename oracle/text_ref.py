@@ -172,6 +172,33 @@ def align_to_backbone(backbone: list, words: list) -> list:
     return [words[j] if j >= 0 else None for j in out]
 
 
+def align_to_backbone_py(backbone: list, words: list) -> list:
+    """tools.py:465-493 in pure Python (full (n+1)x(m+1) table, `.lower()` per cell as the reference
+    does): used for small cases and as the timed CPU baseline of the merge step."""
+    n, m = len(backbone), len(words)
+    tab = [[0] * (m + 1) for _ in range(n + 1)]
+    for i in range(n):
+        row, nxt = tab[i], tab[i + 1]
+        bi = backbone[i]
+        for j in range(m):
+            if bi.lower() == words[j].lower():
+                nxt[j + 1] = row[j] + 1
+            else:
+                up, left = row[j + 1], nxt[j]
+                nxt[j + 1] = up if up >= left else left
+    out = [None] * n
+    i, j = n, m
+    while i > 0 and j > 0:
+        if backbone[i - 1].lower() == words[j - 1].lower():
+            out[i - 1] = words[j - 1]
+            i, j = i - 1, j - 1
+        elif tab[i - 1][j] >= tab[i][j - 1]:
+            i -= 1
+        else:
+            j -= 1
+    return out
+
+
 def merge_versions(versions: list) -> str:
     if not versions:
         return ""
