@@ -232,7 +232,7 @@ def run_b200(args):
     achieved = alg_bytes_step / (step_ms * 1e-3) / 1e9
     # the weight-streaming kernel alone: same launches as one decode step, all layers, back to back
     iso = eng.dec.time_weight_stream(B, reps=3)
-    roofline = {"bound": "hbm", "kernel": "gemv_kernel (decode weight streaming; whole decode step timed in situ)",
+    roofline = {"bound": "hbm", "kernel": "skinny_gemm_kernel (tcgen05 swap-AB weight streaming; whole decode step timed in situ)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "peak_source": peak_src, "traffic": None,
                 "algorithmic_bytes_per_decode_step": int(alg_bytes_step), "decode_step_ms": round(step_ms, 4),

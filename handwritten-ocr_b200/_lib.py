@@ -38,6 +38,7 @@ _SIGS = {
     "ocrb_normalize_patchify": [_P, _P, _I, _I, _I, _I, _P, _I, _P],
     "ocrb_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P],
     "ocrb_gemv_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P, _F, _P],
+    "ocrb_skinny_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P, _F, _P, _P],
     "ocrb_rmsnorm_bf16": [_P, _L, _P, _P, _L, _I, _I, _F, _P],
     "ocrb_rope_vision": [_P, _I, _I, _I, _P, _P, _P],
     "ocrb_rope_text": [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _P],
@@ -50,7 +51,8 @@ _SIGS = {
     "ocrb_decode_rope_table": [_P, _P, _P, _I, _I, _P, _P, _P],
 }
 
-EXPORTS = ["ocrb_version", "ocrb_last_error", "ocrb_launch_count", "ocrb_launch_count_reset"] + list(_SIGS)
+EXPORTS = ["ocrb_version", "ocrb_last_error", "ocrb_launch_count", "ocrb_launch_count_reset",
+           "ocrb_skinny_workspace_bytes"] + list(_SIGS)
 
 
 def load():
@@ -67,6 +69,7 @@ def load():
     L.ocrb_last_error.restype = ctypes.c_char_p
     L.ocrb_launch_count.restype = c_uint64
     L.ocrb_launch_count_reset.restype = None
+    L.ocrb_skinny_workspace_bytes.restype = c_int64
     for name, args in _SIGS.items():
         fn = getattr(L, name)
         fn.argtypes = args

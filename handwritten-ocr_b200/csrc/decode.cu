@@ -214,7 +214,8 @@ gemv_kernel(const bf16 *__restrict__ X, long long ldx, const bf16 *__restrict__ 
 // q,k (bf16 arithmetic, as HF) and appends k,v to the cache; every CTA re-derives the roped q,k it
 // needs from qkv, so there is no inter-CTA dependency.
 constexpr int DA_MAXG = 8;
-constexpr int DA_THREADS = 128;
+constexpr int DA_THREADS = 256;
+constexpr int DA_TPK = 4;          // threads per key in the score phase
 
 __device__ __forceinline__ float rope_elem_bf16(const bf16 *vec, int i, int hd, const bf16 *c, const bf16 *s) {
   const int half = hd >> 1;
@@ -235,12 +236,24 @@ decode_attn_partial_kernel(const bf16 *__restrict__ qkv, long long ldqkv, bf16 *
   const int G = n_q / n_kv;
   float *s_q = reinterpret_cast<float *>(da_smem);   // [G][hd]
   float *s_knew = s_q + G * hd;                      // [hd] roped new key
-  float *s_p = s_knew + hd;                          // [G][chunk]
+  float *s_p = s_knew + hd;                          // [chunk][8]  scores, then probabilities (key-major)
+  float *s_red = s_p + (size_t)chunk * DA_MAXG;      // [4 warps][G][hd] partial P.V
+  int *s_row = reinterpret_cast<int *>(s_red + (size_t)(DA_THREADS / 32) * G * hd);   // [chunk] cache row of each key
   __shared__ float s_m[DA_MAXG], s_l[DA_MAXG];
   const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) pdl_launch_dependents();
+  pdl_wait();                          // qkv comes from the preceding skinny GEMM
   const int ctx = ctx_len[b];          // tokens already cached; the new token sits at position ctx
   const int total = ctx + 1;
+  const int k0 = split * chunk;
+  const int k1 = min(total, k0 + chunk);
+  float *ws = split_ws + (((size_t)b * n_q + (size_t)kvh * G) * n_splits + split) * (hd + 2);
+  const size_t ws_head = (size_t)n_splits * (hd + 2);
+  if (k0 >= k1 && split != 0) {        // chunk beyond the context: publish an empty partial and leave
+    for (int g = tid; g < G; g += DA_THREADS) { ws[g * ws_head] = -INFINITY; ws[g * ws_head + 1] = 0.f; }
+    return;
+  }
   const bf16 *row = qkv + (size_t)b * ldqkv;
   const bf16 *c = cosT + (size_t)b * hd, *s = sinT + (size_t)b * hd;
   const bf16 *knew = row + (size_t)n_q * hd + (size_t)kvh * hd;
@@ -250,66 +263,102 @@ decode_attn_partial_kernel(const bf16 *__restrict__ qkv, long long ldqkv, bf16 *
     s_q[i] = rope_elem_bf16(row + (size_t)(kvh * G + g) * hd, d, hd, c, s);
   }
   for (int d = tid; d < hd; d += DA_THREADS) s_knew[d] = rope_elem_bf16(knew, d, hd, c, s);
+  const int32_t *bt = block_table + (size_t)b * max_pages;
+  for (int i = tid; i < k1 - k0; i += DA_THREADS) {
+    const int key = k0 + i;
+    s_row[i] = (key < ctx) ? bt[key / page_size] * page_size + key % page_size : -1;   // -1: the new token (not cached yet)
+  }
   __syncthreads();
   const size_t tok_stride = (size_t)n_kv * hd;
   if (split == 0) {
     // append the new token's k (roped) and v
-    const int page = block_table[(size_t)b * max_pages + ctx / page_size];
+    const int page = bt[ctx / page_size];
     const size_t dst = ((size_t)page * page_size + ctx % page_size) * tok_stride + (size_t)kvh * hd;
     for (int d = tid; d < hd; d += DA_THREADS) {
       k_cache[dst + d] = __float2bfloat16_rn(s_knew[d]);
       v_cache[dst + d] = vnew[d];
     }
   }
-  const int k0 = split * chunk;
-  const int k1 = min(total, k0 + chunk);
-  float *ws = split_ws + (((size_t)b * n_q + (size_t)kvh * G) * n_splits + split) * (hd + 2);
-  const size_t ws_head = (size_t)n_splits * (hd + 2);
-  if (k0 >= k1) {
-    for (int g = tid; g < G; g += DA_THREADS) { ws[g * ws_head] = -INFINITY; ws[g * ws_head + 1] = 0.f; }
-    return;
-  }
-  // phase 1: scores
-  for (int key = k0 + tid; key < k1; key += DA_THREADS) {
-    float sc[DA_MAXG];
+  const int nk = k1 - k0;
+  // phase 1: scores.  DA_TPK threads share a key (each owns hd/DA_TPK contiguous dims, fetched before the first
+  // FMA), partial dot products meet through two xor-shuffles: short dependent chains, 8 warps per CTA.
+  {
+    const int part = tid & (DA_TPK - 1);
+    const int dpp = hd / DA_TPK;                 // dims per part (multiple of 8)
+    const int dbase = part * dpp;
+    for (int base = k0; base < k1; base += DA_THREADS / DA_TPK) {   // block-uniform trip count (shuffles below)
+      const int key = base + tid / DA_TPK;
+      const bool live = key < k1;
+      float sc[DA_MAXG];
 #pragma unroll
-    for (int g = 0; g < DA_MAXG; ++g) sc[g] = 0.f;
-    if (key == ctx) {
-      for (int d = 0; d < hd; ++d) {
-        const float kv = s_knew[d];
+      for (int g = 0; g < DA_MAXG; ++g) sc[g] = 0.f;
+      if (live) {
+        const int r = s_row[key - k0];
+        if (r < 0) {
+          for (int d = dbase; d < dbase + dpp; ++d) {
+            const float kv = s_knew[d];
 #pragma unroll
-        for (int g = 0; g < DA_MAXG; ++g)
-          if (g < G) sc[g] = fmaf(s_q[g * hd + d], kv, sc[g]);
+            for (int g = 0; g < DA_MAXG; ++g)
+              if (g < G) sc[g] = fmaf(s_q[g * hd + d], kv, sc[g]);
+          }
+        } else {
+          const bf16 *kr = k_cache + (size_t)r * tok_stride + (size_t)kvh * hd + dbase;
+          if (dpp == 32) {
+            uint4 raw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) raw[j] = *reinterpret_cast<const uint4 *>(kr + j * 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float kf[8];
+              unpack8(raw[j], kf);
+#pragma unroll
+              for (int g = 0; g < DA_MAXG; ++g)
+                if (g < G) {
+                  const float4 qa = *reinterpret_cast<const float4 *>(s_q + g * hd + dbase + j * 8);
+                  const float4 qb = *reinterpret_cast<const float4 *>(s_q + g * hd + dbase + j * 8 + 4);
+                  float a = sc[g];
+                  a = fmaf(qa.x, kf[0], a); a = fmaf(qa.y, kf[1], a); a = fmaf(qa.z, kf[2], a); a = fmaf(qa.w, kf[3], a);
+                  a = fmaf(qb.x, kf[4], a); a = fmaf(qb.y, kf[5], a); a = fmaf(qb.z, kf[6], a); a = fmaf(qb.w, kf[7], a);
+                  sc[g] = a;
+                }
+            }
+          } else {
+            for (int d8 = 0; d8 < dpp; d8 += 8) {
+              float kf[8];
+              unpack8(*reinterpret_cast<const uint4 *>(kr + d8), kf);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+#pragma unroll
+                for (int g = 0; g < DA_MAXG; ++g)
+                  if (g < G) sc[g] = fmaf(s_q[g * hd + dbase + d8 + e], kf[e], sc[g]);
+            }
+          }
+        }
       }
-    } else {
-      const int page = block_table[(size_t)b * max_pages + key / page_size];
-      const bf16 *kr = k_cache + ((size_t)page * page_size + key % page_size) * tok_stride + (size_t)kvh * hd;
-      for (int d8 = 0; d8 < hd; d8 += 8) {
-        float kf[8];
-        unpack8(*reinterpret_cast<const uint4 *>(kr + d8), kf);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-#pragma unroll
-          for (int g = 0; g < DA_MAXG; ++g)
-            if (g < G) sc[g] = fmaf(s_q[g * hd + d8 + e], kf[e], sc[g]);
+      for (int g = 0; g < DA_MAXG; ++g) {
+        sc[g] += __shfl_xor_sync(0xffffffffu, sc[g], 1);
+        sc[g] += __shfl_xor_sync(0xffffffffu, sc[g], 2);
+      }
+      if (live && part == 0) {
+        float4 lo = make_float4(sc[0] * scale, sc[1] * scale, sc[2] * scale, sc[3] * scale);
+        float4 hi = make_float4(sc[4] * scale, sc[5] * scale, sc[6] * scale, sc[7] * scale);
+        *reinterpret_cast<float4 *>(s_p + (size_t)(key - k0) * DA_MAXG) = lo;
+        *reinterpret_cast<float4 *>(s_p + (size_t)(key - k0) * DA_MAXG + 4) = hi;
       }
     }
-#pragma unroll
-    for (int g = 0; g < DA_MAXG; ++g)
-      if (g < G) s_p[g * chunk + (key - k0)] = sc[g] * scale;
   }
   __syncthreads();
   // phase 2: per-head max / exp / sum (warp w handles heads w, w+4, ...)
-  const int nk = k1 - k0;
   for (int g = warp; g < G; g += DA_THREADS / 32) {
     float m = -INFINITY;
-    for (int i = lane; i < nk; i += 32) m = fmaxf(m, s_p[g * chunk + i]);
+    for (int i = lane; i < nk; i += 32) m = fmaxf(m, s_p[i * DA_MAXG + g]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     float l = 0.f;
     for (int i = lane; i < nk; i += 32) {
-      const float p = __expf(s_p[g * chunk + i] - m);
-      s_p[g * chunk + i] = p;
+      const float p = __expf(s_p[i * DA_MAXG + g] - m);
+      s_p[i * DA_MAXG + g] = p;
       l += p;
     }
 #pragma unroll
@@ -317,25 +366,63 @@ decode_attn_partial_kernel(const bf16 *__restrict__ qkv, long long ldqkv, bf16 *
     if (lane == 0) { s_m[g] = m; s_l[g] = l; }
   }
   __syncthreads();
-  // phase 3: P.V, thread per output dim
-  for (int d = tid; d < hd; d += DA_THREADS) {
-    float acc[DA_MAXG];
+  // phase 3: P.V.  Warp w takes keys w, w+4, ...; lane l owns dims [4l, 4l+4) (+128 per pass for hd > 128),
+  // so every V row is read once, coalesced, 8 bytes per lane.  Partial sums meet in shared memory.
+  for (int d0 = 0; d0 < hd; d0 += 128) {
+    const int d = d0 + lane * 4;
+    const bool d_ok = d < hd;
+    float acc[DA_MAXG][4];
 #pragma unroll
-    for (int g = 0; g < DA_MAXG; ++g) acc[g] = 0.f;
-    for (int key = k0; key < k1; ++key) {
-      float vv;
-      if (key == ctx) vv = __bfloat162float(vnew[d]);
-      else {
-        const int page = block_table[(size_t)b * max_pages + key / page_size];
-        vv = __bfloat162float(v_cache[((size_t)page * page_size + key % page_size) * tok_stride + (size_t)kvh * hd + d]);
+    for (int g = 0; g < DA_MAXG; ++g) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f;
+    constexpr int NW = DA_THREADS / 32;
+    constexpr int VB = 8;                      // V rows in flight per lane
+    for (int i0 = warp; i0 < nk; i0 += NW * VB) {
+      uint2 raw[VB];
+#pragma unroll
+      for (int j = 0; j < VB; ++j) {
+        const int i = i0 + j * NW;
+        raw[j] = make_uint2(0, 0);
+        if (i < nk && d_ok) {
+          const int r = s_row[i];
+          const bf16 *vp = (r < 0) ? (vnew + d) : (v_cache + (size_t)r * tok_stride + (size_t)kvh * hd + d);
+          raw[j] = *reinterpret_cast<const uint2 *>(vp);
+        }
       }
 #pragma unroll
-      for (int g = 0; g < DA_MAXG; ++g)
-        if (g < G) acc[g] = fmaf(s_p[g * chunk + (key - k0)], vv, acc[g]);
-    }
+      for (int j = 0; j < VB; ++j) {
+        const int i = i0 + j * NW;
+        if (i < nk) {
+          const float v0 = __uint_as_float(raw[j].x << 16), v1 = __uint_as_float(raw[j].x & 0xffff0000u);
+          const float v2 = __uint_as_float(raw[j].y << 16), v3 = __uint_as_float(raw[j].y & 0xffff0000u);
+          const float4 pa = *reinterpret_cast<const float4 *>(s_p + (size_t)i * DA_MAXG);
+          const float4 pb = *reinterpret_cast<const float4 *>(s_p + (size_t)i * DA_MAXG + 4);
+          const float pp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
-    for (int g = 0; g < DA_MAXG; ++g)
-      if (g < G) ws[g * ws_head + 2 + d] = acc[g];
+          for (int g = 0; g < DA_MAXG; ++g)
+            if (g < G) {
+              acc[g][0] = fmaf(pp[g], v0, acc[g][0]);
+              acc[g][1] = fmaf(pp[g], v1, acc[g][1]);
+              acc[g][2] = fmaf(pp[g], v2, acc[g][2]);
+              acc[g][3] = fmaf(pp[g], v3, acc[g][3]);
+            }
+        }
+      }
+    }
+    if (d_ok) {
+#pragma unroll
+      for (int g = 0; g < DA_MAXG; ++g)
+        if (g < G)
+          *reinterpret_cast<float4 *>(s_red + ((size_t)warp * G + g) * hd + d) =
+              make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < G * hd; i += DA_THREADS) {
+    const int g = i / hd, d = i - g * hd;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < DA_THREADS / 32; ++w) a += s_red[((size_t)w * G + g) * hd + d];
+    ws[g * ws_head + 2 + d] = a;
   }
   for (int g = tid; g < G; g += DA_THREADS) { ws[g * ws_head] = s_m[g]; ws[g * ws_head + 1] = s_l[g]; }
 }
@@ -344,6 +431,8 @@ decode_attn_partial_kernel(const bf16 *__restrict__ qkv, long long ldqkv, bf16 *
 __global__ void decode_attn_combine_kernel(const float *__restrict__ split_ws, int n_q, int n_splits, int hd,
                                            bf16 *__restrict__ out, long long ldo) {
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  if (d == 0) pdl_launch_dependents();
+  pdl_wait();
   const float *ws = split_ws + ((size_t)b * n_q + h) * n_splits * (hd + 2);
   float M = -INFINITY;
   for (int s = 0; s < n_splits; ++s) M = fmaxf(M, ws[(size_t)s * (hd + 2)]);
@@ -418,12 +507,13 @@ extern "C" int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cac
                                      int32_t n_splits, void *stream) {
   OCRB_REQUIRE(qkv && k_cache && v_cache && block_table && ctx_len && cosT && sinT && out && split_ws,
                "decode_attention: null pointer");
-  OCRB_REQUIRE(B > 0 && n_kv > 0 && n_q % n_kv == 0 && n_q / n_kv <= DA_MAXG && hd % 8 == 0 && hd <= 256 && n_splits > 0,
+  OCRB_REQUIRE(B > 0 && n_kv > 0 && n_q % n_kv == 0 && n_q / n_kv <= DA_MAXG && hd % 32 == 0 && hd <= 256 && n_splits > 0,
                "decode_attention: bad sizes");
   const int max_ctx = max_pages * page_size;
   const int chunk = cdiv(max_ctx, n_splits);
   const int G = n_q / n_kv;
-  const size_t smem = ((size_t)G * hd + hd + (size_t)G * chunk) * sizeof(float);
+  const size_t smem = ((size_t)G * hd + hd + (size_t)DA_MAXG * chunk + (size_t)(DA_THREADS / 32) * G * hd) * sizeof(float) +
+                      (size_t)chunk * sizeof(int);
   OCRB_REQUIRE(smem <= 200 * 1024, "decode_attention: chunk too large, raise n_splits");
   cudaStream_t st = (cudaStream_t)stream;
   static size_t attr_smem = 48 * 1024;
@@ -431,11 +521,13 @@ extern "C" int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cac
     OCRB_CUDA(cudaFuncSetAttribute(decode_attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  decode_attn_partial_kernel<<<dim3(n_splits, n_kv, B), DA_THREADS, smem, st>>>(
-      (const bf16 *)qkv, ldqkv, (bf16 *)k_cache, (bf16 *)v_cache, block_table, max_pages, ctx_len, page_size, n_q, n_kv, hd,
-      (const bf16 *)cosT, (const bf16 *)sinT, scale, split_ws, n_splits, chunk);
+  OCRB_CUDA(launch_pdl(decode_attn_partial_kernel, dim3(n_splits, n_kv, B), dim3(DA_THREADS), smem, st, (const bf16 *)qkv,
+                       (long long)ldqkv, (bf16 *)k_cache, (bf16 *)v_cache, block_table, (int)max_pages, ctx_len,
+                       (int)page_size, (int)n_q, (int)n_kv, (int)hd, (const bf16 *)cosT, (const bf16 *)sinT, scale, split_ws,
+                       (int)n_splits, chunk));
   int rc = check_launch("decode_attn_partial_kernel");
   if (rc) return rc;
-  decode_attn_combine_kernel<<<dim3(n_q, B), hd, 0, st>>>(split_ws, n_q, n_splits, hd, (bf16 *)out, ldo);
+  OCRB_CUDA(launch_pdl(decode_attn_combine_kernel, dim3(n_q, B), dim3(hd), 0, st, (const float *)split_ws, (int)n_q,
+                       (int)n_splits, (int)hd, (bf16 *)out, (long long)ldo));
   return check_launch("decode_attn_combine_kernel");
 }

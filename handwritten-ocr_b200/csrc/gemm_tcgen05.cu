@@ -11,94 +11,16 @@
 //   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns -> registers -> bias / residual / SwiGLU / GELU with
 //              HF's bf16 rounding points -> 16-byte global stores
 // M/N/K tails are handled by TMA zero fill on loads and predicated stores.
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 #include <math.h>
 #include <mutex>
 
 namespace ocrb {
 
-typedef __nv_bfloat16 bf16;
-
 constexpr int GM_BM = 128;
 constexpr int GM_BK = 64;          // 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int GM_STAGES = 4;
 constexpr int GM_THREADS = 192;
-constexpr int UMMA_K = 16;
-
-// ───────────── PTX wrappers ─────────────
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must fail fast (trap) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("ocrb gemm: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3ffff) >> 4);   // start address
-  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 8 rows * 128 B
-  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-  return d;
-}
 
 __device__ __forceinline__ float silu_bf16r(float g) { return bf16_round(g / (1.0f + expf(-g))); }
 __device__ __forceinline__ float gelu_bf16r(float x) { return bf16_round(0.5f * x * (1.0f + erff(x * 0.70710678118654752440f))); }
@@ -284,7 +206,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle.
-static int make_map(CUtensorMap *m, const void *ptr, long long rows, long long cols, long long ld, int box_rows) {
+int make_tensor_map_bf16(CUtensorMap *m, const void *ptr, long long rows, long long cols, long long ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("gemm_bf16: cuTensorMapEncodeTiled not available from the driver");
@@ -349,9 +271,9 @@ extern "C" int ocrb_gemm_bf16(const void *A, int64_t lda, const void *W, int64_t
   const bool wide = (N % 256 == 0) && ((long long)cdiv(N, 256) * cdiv(M, GM_BM) >= 148);
   const int BN = wide ? 256 : 128;
   CUtensorMap ma, mw;
-  int rc = make_map(&ma, A, M, K, lda, GM_BM);
+  int rc = make_tensor_map_bf16(&ma, A, M, K, lda, GM_BM);
   if (rc) return rc;
-  rc = make_map(&mw, W, N, K, ldw, BN);
+  rc = make_tensor_map_bf16(&mw, W, N, K, ldw, BN);
   if (rc) return rc;
   if (wide) return launch_gemm<256>(ma, mw, p, (cudaStream_t)stream);
   return launch_gemm<128>(ma, mw, p, (cudaStream_t)stream);

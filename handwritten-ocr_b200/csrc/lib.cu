@@ -1,10 +1,19 @@
 // Library-level entry points: version, error text, launch counter.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace ocrb {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("OCRB_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 void set_error(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

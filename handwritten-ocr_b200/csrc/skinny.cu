@@ -1,0 +1,548 @@
+// Weight-streaming "skinny" GEMM for batched greedy decode (HF generation loop utils.py:2743-2806: one new
+// token per sequence per step, so every nn.Linear of the decoder sees only B <= 64 activation rows):
+//
+//     D[b, n] = epilogue( sum_k X[b, k] * W[n, k] )          X: [B, K] bf16,  W: [N, K] bf16
+//
+// HBM-bound: each weight byte must cross HBM exactly once per step whatever B is.  Design (sm_100a):
+//   * swap-AB on the 5th-gen tensor cores: the 128 x 64 WEIGHT tile is the UMMA "A" operand (M = 128 weight
+//     rows), the activations are the "B" operand (N = BP = 16/32/64 batch columns), fp32 accumulators
+//     [128 lanes x BP columns] in TMEM, double buffered so the epilogue of one tile overlaps the MMAs of the next;
+//   * weights arrive through a TMA ring (cp.async.bulk.tensor, 128B swizzle, L2 evict-first) that never
+//     depends on the activations, so it starts before the previous kernel's results are needed;
+//   * stream-K: the (tile, k-block) iteration space is cut into gridDim.x equal contiguous spans, one per SM,
+//     so a 3584x3584 o_proj (28 tiles) fills the machine as evenly as the 152064-row lm_head.  A span that
+//     does not finish its tile publishes an fp32 partial; the CTA that finishes the tile adds the partials in
+//     k order (deterministic, independent of B => batch-invariant results);
+//   * activations: 4 producer warps write the X k-slices into the ring in the UMMA swizzled layout,
+//     optionally applying HF's RMSNorm on the fly (modeling_qwen2_5_vl.py:66-71: fp32 normalise -> bf16 ->
+//     bf16 multiply by the weight), so no separate norm kernel / launch sits in front of qkv, gate-up, lm_head;
+//   * epilogue warps: tcgen05.ld -> bias -> bf16 round -> residual / SwiGLU / GELU with HF's rounding points.
+//
+// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue (TMEM lane
+// quadrant = warp % 4), 6..9 = activation producers.
+#include "tc_common.cuh"
+#include <math.h>
+
+namespace ocrb {
+
+constexpr int SK_BM = 128;          // weight rows per tile
+constexpr int SK_BK = 64;           // k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int SK_STAGES = 5;           // 5 x 18 KiB (BP=16): two CTAs of consecutive kernels fit one SM under PDL
+constexpr int SK_PF = 4;             // activation prefetch distance (units)
+constexpr int SK_THREADS = 320;
+constexpr int SK_MAX_GRID = 296;    // workspace slots (2 x 148)
+constexpr int SK_MAXBP = 64;
+constexpr uint32_t SK_W_BYTES = SK_BM * SK_BK * 2;   // 16 KiB
+
+struct SkinnyParams {
+  const bf16 *X; long long ldx;
+  bf16 *D; long long ldd;
+  const bf16 *bias;
+  const bf16 *residual; long long ldr;
+  const bf16 *norm_w; float eps;
+  int B, N, K;
+  int epilogue;
+  int num_tiles, num_kb;
+  float *partials;       // [SK_MAX_GRID][BP][128] fp32
+  int *flags;            // [SK_MAX_GRID]
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t *r);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ float sk_silu(float g) { return bf16_round(g / (1.0f + expf(-g))); }
+__device__ __forceinline__ float sk_gelu(float x) { return bf16_round(0.5f * x * (1.0f + erff(x * 0.70710678118654752440f))); }
+
+__device__ __forceinline__ void unpack8f(const uint4 &raw, float *f) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f[2 * k] = __uint_as_float(w[k] << 16);
+    f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+  }
+}
+
+// Span of the (tile, k-block) iteration space owned by CTA `cta` (all int32: total units < 2^31 is checked on the host).
+__device__ __forceinline__ void sk_span(int cta, int grid, int total, int &begin, int &end) {
+  const int per = total / grid, rem = total % grid;
+  begin = cta * per + (cta < rem ? cta : rem);
+  end = begin + per + (cta < rem ? 1 : 0);
+}
+
+// Processing order inside a span: tiles in REVERSE order (k-blocks ascending inside a tile).  The tail segment --
+// the only one that may end before its tile does -- is therefore computed and published first, and the head
+// segment -- the only one that may need other CTAs' partials -- last: nobody waits on a CTA that itself waits.
+struct SkSpan {
+  int u_begin, u_end, KB, T0, T1;
+  __device__ __forceinline__ void init(int cta, int grid, int num_tiles, int kb) {
+    KB = kb;
+    sk_span(cta, grid, num_tiles * kb, u_begin, u_end);
+    T0 = u_begin / KB;
+    T1 = (u_end - 1) / KB;
+  }
+  __device__ __forceinline__ int num_units() const { return u_end - u_begin; }
+  __device__ __forceinline__ int num_segs() const { return T1 - T0 + 1; }
+  // segment i in processing order -> tile, first k-block, number of k-blocks
+  __device__ __forceinline__ void seg(int i, int &tile, int &kb0, int &nkb) const {
+    tile = T1 - i;
+    const int ts = tile * KB;
+    const int a = ts > u_begin ? ts : u_begin;
+    const int b = (ts + KB) < u_end ? (ts + KB) : u_end;
+    kb0 = a - ts;
+    nkb = b - a;
+  }
+};
+
+// Walks the units of a span in processing order without divisions.
+struct SkCursor {
+  int seg, tile, kb, kb_end;
+  bool valid;
+  __device__ __forceinline__ void init(const SkSpan &sp) {
+    seg = 0;
+    valid = sp.num_units() > 0;
+    int kb0 = 0, nkb = 0;
+    tile = 0;
+    if (valid) sp.seg(0, tile, kb0, nkb);
+    kb = kb0;
+    kb_end = kb0 + nkb;
+  }
+  __device__ __forceinline__ void advance(const SkSpan &sp) {
+    if (++kb == kb_end) {
+      if (++seg < sp.num_segs()) {
+        int kb0, nkb;
+        sp.seg(seg, tile, kb0, nkb);
+        kb = kb0;
+        kb_end = kb0 + nkb;
+      } else {
+        valid = false;
+      }
+    }
+  }
+};
+
+// HF RMSNorm statistics (modeling_qwen2_5_vl.py:66-71): rstd[b] = rsqrt(mean(x[b]^2) + eps) in fp32.  Warps 2..9
+// (256 threads) share the rows; one warp per row, up to 16 independent 16-byte loads in flight per lane, fixed
+// summation order (lane-strided partial sums, xor-shuffle tree) so the result never depends on B.
+__device__ __forceinline__ void sk_row_rstd(const SkinnyParams &p, int w8, int lane, float *s_rstd) {
+  const int kvec = p.K >> 3;
+  for (int b = w8; b < p.B; b += 8) {
+    const bf16 *xr = p.X + (size_t)b * p.ldx;
+    float ss = 0.f;
+    for (int v0 = lane; v0 < kvec; v0 += 32 * 16) {
+      uint4 raw[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int v = v0 + i * 32;
+        raw[i] = make_uint4(0, 0, 0, 0);
+        if (v < kvec) raw[i] = *reinterpret_cast<const uint4 *>(xr + v * 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float f[8];
+        unpack8f(raw[i], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ss = fmaf(f[k], f[k], ss);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) s_rstd[b] = rsqrtf(ss / (float)p.K + p.eps);
+  }
+}
+
+template <int BP>
+__global__ void __launch_bounds__(SK_THREADS, (BP <= 16) ? 2 : 1)
+skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
+  constexpr uint32_t X_BYTES = BP * SK_BK * 2;
+  constexpr uint32_t STAGE_BYTES = SK_W_BYTES + X_BYTES;
+  constexpr int TMEM_COLS = (2 * BP < 32) ? 32 : 2 * BP;
+  extern __shared__ uint8_t sk_smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sk_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full_w = reinterpret_cast<uint64_t *>(smem + SK_STAGES * STAGE_BYTES);
+  uint64_t *full_x = full_w + SK_STAGES;
+  uint64_t *empty = full_x + SK_STAGES;
+  uint64_t *tmem_full = empty + SK_STAGES;     // [2]
+  uint64_t *tmem_empty = tmem_full + 2;        // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+  float *s_rstd = reinterpret_cast<float *>(tmem_slot + 2);        // [BP]
+  float *s_part = s_rstd + SK_MAXBP;                               // [4 warps][BP]
+  float *s_up = s_part + 4 * SK_MAXBP;                             // [64][BP] SwiGLU exchange
+  volatile int *s_flag = reinterpret_cast<volatile int *>(s_up + 64 * BP);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.num_kb;
+  SkSpan sp;
+  sp.init(blockIdx.x, gridDim.x, p.num_tiles, KB);
+  const int n_units = sp.num_units();
+  const int n_segs = sp.num_segs();
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < SK_STAGES; ++s) {
+      mbar_init(&full_w[s], 1);
+      mbar_init(&full_x[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_launch_dependents();   // the next kernel may start its own weight prefetch now
+  if (warp >= 2) pdl_wait();                        // activations / residual / workspace belong to predecessors
+
+  if (warp == 0) {
+    // ───────────── TMA producer: weights only; independent of the previous kernel's output ─────────────
+    if (lane == 0) {
+      uint64_t policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      SkCursor cur;
+      cur.init(sp);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < n_units; ++it) {
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full_w[s], SK_W_BYTES);
+        tma_load_2d_hint(smem + s * STAGE_BYTES, &map_w, &full_w[s], cur.kb * SK_BK, cur.tile * SK_BM, policy);
+        cur.advance(sp);
+        if (++s == SK_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ───────────── MMA issuer ─────────────
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BP >> 3) << 17) | ((uint32_t)(SK_BM >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int seg = 0; seg < n_segs; ++seg) {
+        int tile, kb0, nkb;
+        sp.seg(seg, tile, kb0, nkb);
+        const int acc = seg & 1;
+        mbar_wait(&tmem_empty[acc], ((seg >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + acc * BP;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(&full_w[s], ph);
+          mbar_wait(&full_x[s], ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + SK_W_BYTES);
+#pragma unroll
+          for (int k = 0; k < SK_BK / UMMA_K; ++k)
+            umma_bf16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);
+          if (++s == SK_STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (warp >= 6) {
+    // ───────────── activation producers (128 threads) ─────────────
+    const int t = threadIdx.x - 192;
+    const int pw = t >> 5;
+    const bool norm = p.norm_w != nullptr;
+    if (norm) {
+      sk_row_rstd(p, warp - 2, lane, s_rstd);
+      named_bar_sync(2, 256);                    // rstd[] complete (warps 2..9)
+    }            // rstd[] written by warps 2..9 (sk_row_rstd)
+    // thread -> (row r, 16-byte chunk j) of the [BP x 64] k-slice; BP/16 rows per thread.
+    // The global (L2) loads run SK_PF units ahead of their use, so the ~1 us load latency is hidden.
+    const int j = t & 7;
+    const int r0 = t >> 3;                       // 0..15
+    constexpr int Q = BP / 16;
+    uint4 xq[SK_PF][Q];
+    uint4 wq[SK_PF];
+    SkCursor fc;                                 // fetch cursor, SK_PF units ahead of the consume position
+    fc.init(sp);
+    auto fetch = [&](uint4 *xv, uint4 &wv) {
+      const int k = fc.kb * SK_BK + j * 8;
+      const bool ok = fc.valid && (k < p.K);
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int r = r0 + q * 16;
+        xv[q] = make_uint4(0, 0, 0, 0);
+        if (ok && r < p.B) xv[q] = *reinterpret_cast<const uint4 *>(p.X + (size_t)r * p.ldx + k);
+      }
+      wv = make_uint4(0, 0, 0, 0);
+      if (norm && ok) wv = *reinterpret_cast<const uint4 *>(p.norm_w + k);
+      if (fc.valid) fc.advance(sp);
+    };
+#pragma unroll
+    for (int i = 0; i < SK_PF; ++i) fetch(xq[i], wq[i]);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ib = 0; ib < n_units; ib += SK_PF) {
+#pragma unroll
+      for (int i = 0; i < SK_PF; ++i) {
+        const int it = ib + i;
+        if (it < n_units) {
+          uint4 xv[Q];
+#pragma unroll
+          for (int q = 0; q < Q; ++q) xv[q] = xq[i][q];
+          const uint4 wv = wq[i];
+          fetch(xq[i], wq[i]);                     // refill this slot for SK_PF units later
+          if (norm) {
+            float wf[8];
+            unpack8f(wv, wf);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+              const int r = r0 + q * 16;
+              if (r < p.B) {
+                const float rs = s_rstd[r];
+                float f[8];
+                unpack8f(xv[q], f);
+                bf16 *oe = reinterpret_cast<bf16 *>(&xv[q]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) oe[e] = __float2bfloat16_rn(wf[e] * bf16_round(f[e] * rs));
+              }
+            }
+          }
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t *xs = smem + s * STAGE_BYTES + SK_W_BYTES;
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            const int r = r0 + q * 16;
+            *reinterpret_cast<uint4 *>(xs + r * 128 + ((j ^ (r & 7)) << 4)) = xv[q];
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&full_x[s]);
+          if (++s == SK_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ───────────── epilogue warps 2..5 ─────────────
+    if (p.norm_w != nullptr) {
+      sk_row_rstd(p, warp - 2, lane, s_rstd);
+      named_bar_sync(2, 256);
+    }
+    const int quad = warp & 3;
+    const int et = quad * 32 + lane;             // TMEM lane = weight row inside the tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int seg = 0; seg < n_segs; ++seg) {
+      int tile, kb0, nkb;
+      sp.seg(seg, tile, kb0, nkb);
+      const int acc = seg & 1;
+      mbar_wait(&tmem_full[acc], (seg >> 1) & 1);
+      tcgen05_fence_after();
+      float v[BP];
+#pragma unroll
+      for (int c = 0; c < BP; c += 16) {
+        uint32_t r[16];
+        tmem_ld_cols<16>(lane_addr + acc * BP + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[c + i] = __uint_as_float(r[i]);
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty[acc]);             // accumulator drained: the MMA warp may reuse it
+
+      const bool finishes = (kb0 + nkb == KB);
+      if (!finishes) {
+        // partial span: publish fp32 partials, then the flag
+        float *slot = p.partials + (size_t)blockIdx.x * BP * 128;
+#pragma unroll
+        for (int b = 0; b < BP; ++b) __stcg(slot + b * 128 + et, v[b]);
+        __threadfence();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags + blockIdx.x), "r"(1) : "memory");
+        }
+      } else {
+        if (kb0 > 0) {
+          // this CTA finishes a tile that earlier CTAs started: add their partials in k order, then ours
+          const int tile_first = tile * KB;
+          // first contributing CTA: the one whose span contains unit tile_first
+          const int total = p.num_tiles * KB;
+          const int per = total / (int)gridDim.x, rem = total % (int)gridDim.x;
+          const int big = rem * (per + 1);
+          const int c0 = (tile_first < big) ? tile_first / (per + 1) : rem + (tile_first - big) / per;
+          float sum[BP];
+#pragma unroll
+          for (int b = 0; b < BP; ++b) sum[b] = 0.f;
+          constexpr int FX = (BP <= 16) ? 2 : 1;   // contributors fetched together
+          for (int cb = c0; cb < (int)blockIdx.x; cb += FX) {
+            const int nc = min(FX, (int)blockIdx.x - cb);
+            if (et < nc) {
+              const int c = cb + et;
+              int f;
+              const long long t0 = clock64();
+              do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.flags + c) : "memory");
+                if (!f && clock64() - t0 > 4000000000LL) {
+                  printf("ocrb skinny gemm: partial of CTA %d never arrived (CTA %d)\n", c, blockIdx.x);
+                  __trap();
+                }
+              } while (!f);
+            }
+            named_bar_sync(1, 128);
+            float pv[FX][BP];
+#pragma unroll
+            for (int i = 0; i < FX; ++i) {
+              const float *slot = p.partials + (size_t)(cb + (i < nc ? i : 0)) * BP * 128;
+#pragma unroll
+              for (int b = 0; b < BP; ++b) pv[i][b] = __ldcg(slot + b * 128 + et);
+            }
+#pragma unroll
+            for (int i = 0; i < FX; ++i)
+              if (i < nc) {
+#pragma unroll
+                for (int b = 0; b < BP; ++b) sum[b] += pv[i][b];
+              }
+            named_bar_sync(1, 128);
+            if (et < nc) p.flags[cb + et] = 0;   // consumed: ready for the next launch
+          }
+#pragma unroll
+          for (int b = 0; b < BP; ++b) v[b] = sum[b] + v[b];
+        }
+        // ───── epilogue math on the complete accumulator (HF rounding points) ─────
+        const int n = tile * SK_BM + et;
+        const bool n_ok = n < p.N;
+        float bv = (p.bias && n_ok) ? __bfloat162float(p.bias[n]) : 0.f;
+#pragma unroll
+        for (int b = 0; b < BP; ++b) v[b] = bf16_round(v[b] + bv);
+        if (p.epilogue == OCRB_EPI_SWIGLU) {
+          // tile rows 0..63 = gate, 64..127 = up of output columns tile*64 + j
+          if (et >= 64) {
+#pragma unroll
+            for (int b = 0; b < BP; ++b) s_up[(et - 64) * BP + b] = v[b];
+          }
+          named_bar_sync(1, 128);
+          if (et < 64 && n_ok) {
+            const int oc = tile * 64 + et;
+            for (int b = 0; b < p.B; ++b) {
+              float vb = 0.f, ub = 0.f;
+#pragma unroll
+              for (int q = 0; q < BP; ++q)
+                if (q == b) { vb = v[q]; ub = s_up[et * BP + q]; }
+              p.D[(size_t)b * p.ldd + oc] = __float2bfloat16_rn(sk_silu(vb) * ub);
+            }
+          }
+          named_bar_sync(1, 128);
+        } else if (n_ok) {
+#pragma unroll
+          for (int b = 0; b < BP; ++b) {
+            if (b < p.B) {
+              float o = v[b];
+              if (p.epilogue == OCRB_EPI_RESIDUAL) o += __bfloat162float(p.residual[(size_t)b * p.ldr + n]);
+              else if (p.epilogue == OCRB_EPI_GELU) o = sk_gelu(o);
+              p.D[(size_t)b * p.ldd + n] = __float2bfloat16_rn(o);
+            }
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BP>
+static int launch_skinny(const CUtensorMap &mw, const SkinnyParams &p, int grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)SK_STAGES * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 256 /*barriers*/ +
+                          (SK_MAXBP + 4 * SK_MAXBP + 64 * BP) * sizeof(float) + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OCRB_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<BP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  OCRB_CUDA(launch_pdl(skinny_gemm_kernel<BP>, dim3(grid), dim3(SK_THREADS), smem, st, mw, p));
+  return check_launch("skinny_gemm_kernel");
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace ocrb
+
+using namespace ocrb;
+
+extern "C" int64_t ocrb_skinny_workspace_bytes(void) {
+  return (int64_t)SK_MAX_GRID * SK_MAXBP * 128 * sizeof(float) + (int64_t)SK_MAX_GRID * sizeof(int) + 256;
+}
+
+extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, int64_t ldw, void *D, int64_t ldd, int32_t B,
+                                     int32_t N, int32_t K, const void *bias, const void *residual, int64_t ldr,
+                                     int32_t epilogue, const void *norm_w, float eps, void *workspace, void *stream) {
+  OCRB_REQUIRE(X && W && D && workspace, "skinny_gemm_bf16: null pointer");
+  OCRB_REQUIRE(B >= 1 && B <= SK_MAXBP, "skinny_gemm_bf16: B must be in 1..64 (use ocrb_gemm_bf16 for larger batches)");
+  OCRB_REQUIRE(N > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0,
+               "skinny_gemm_bf16: K and row strides must be multiples of 8");
+  OCRB_REQUIRE(((uintptr_t)X & 15) == 0 && ((uintptr_t)W & 15) == 0 && (!norm_w || ((uintptr_t)norm_w & 15) == 0),
+               "skinny_gemm_bf16: X, W, norm_w must be 16-byte aligned");
+  OCRB_REQUIRE(epilogue >= 0 && epilogue <= 3, "skinny_gemm_bf16: bad epilogue");
+  OCRB_REQUIRE(epilogue != OCRB_EPI_RESIDUAL || residual, "skinny_gemm_bf16: residual epilogue without residual");
+  OCRB_REQUIRE(epilogue != OCRB_EPI_SWIGLU || N % 128 == 0, "skinny_gemm_bf16: SwiGLU needs packed N % 128 == 0");
+  SkinnyParams p;
+  p.X = (const bf16 *)X; p.ldx = ldx;
+  p.D = (bf16 *)D; p.ldd = ldd;
+  p.bias = (const bf16 *)bias;
+  p.residual = (epilogue == OCRB_EPI_RESIDUAL) ? (const bf16 *)residual : nullptr;
+  p.ldr = ldr;
+  p.norm_w = (const bf16 *)norm_w; p.eps = eps;
+  p.B = B; p.N = N; p.K = K;
+  p.epilogue = epilogue;
+  p.num_tiles = cdiv(N, SK_BM);
+  p.num_kb = cdiv(K, SK_BK);
+  p.partials = (float *)workspace;
+  p.flags = (int *)((char *)workspace + (size_t)SK_MAX_GRID * SK_MAXBP * 128 * sizeof(float));
+  const long long total = (long long)p.num_tiles * p.num_kb;
+  OCRB_REQUIRE(total < (1ll << 30), "skinny_gemm_bf16: problem too large (tiles x k-blocks must be < 2^30)");
+  // one CTA per SM; spans of at least 4 k-blocks so tiny problems do not pay 148 fix-ups.
+  // The split depends only on (N, K) and the SM count -- never on B -- so results are batch-invariant.
+  int grid = sm_count();
+  if (grid > SK_MAX_GRID) grid = SK_MAX_GRID;
+  if (total / 4 < grid) grid = (int)(total / 4 > 1 ? total / 4 : 1);
+  CUtensorMap mw;
+  int rc = make_tensor_map_bf16(&mw, W, N, K, ldw, SK_BM);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B <= 16) return launch_skinny<16>(mw, p, grid, st);
+  if (B <= 32) return launch_skinny<32>(mw, p, grid, st);
+  return launch_skinny<64>(mw, p, grid, st);
+}

@@ -46,10 +46,37 @@ def gemv(X, W, out, *, bias=None, residual=None, epilogue=EPI_NONE, norm_w=None,
     return out
 
 
+_SKINNY_WS = {}
+
+
+def skinny_workspace(device) -> torch.Tensor:
+    """Per-device stream-K workspace of ocrb_skinny_gemm_bf16 (zeroed once; launches are stream-ordered)."""
+    key = torch.device(device).index or 0
+    ws = _SKINNY_WS.get(key)
+    if ws is None:
+        n = int(_lib.load().ocrb_skinny_workspace_bytes())
+        ws = torch.zeros(n, dtype=torch.uint8, device=device)
+        _SKINNY_WS[key] = ws
+    return ws
+
+
+SKINNY_MAX_ROWS = 64
+
+
+def skinny(X, W, out, *, bias=None, residual=None, epilogue=EPI_NONE, norm_w=None, eps=1e-6):
+    """out[B, N'] = epilogue(X[B,K] @ W[N,K]^T), B <= 64: every weight byte crosses HBM once (tcgen05 swap-AB)."""
+    B, K = X.shape
+    _lib.call("ocrb_skinny_gemm_bf16", X.data_ptr(), X.stride(0), W.data_ptr(), W.stride(0), out.data_ptr(),
+              out.stride(0), B, W.shape[0], K, _lib.ptr(bias), _lib.ptr(residual),
+              residual.stride(0) if residual is not None else 0, epilogue, _lib.ptr(norm_w), float(eps),
+              skinny_workspace(X.device).data_ptr(), _sp())
+    return out
+
+
 def linear_small_or_big(X, W, out, **kw):
-    """Row count decides the datapath: <= 8 rows stream the weights once (GEMV), else tensor cores."""
-    if X.shape[0] <= 8:
-        return gemv(X, W, out, **kw)
+    """Row count decides the datapath: <= 64 rows stream the weights once (skinny GEMM), else full tiles."""
+    if X.shape[0] <= SKINNY_MAX_ROWS:
+        return skinny(X, W, out, **kw)
     return gemm(X, W, out, **kw)
 
 
@@ -360,8 +387,9 @@ class Decoder:
     def logits_last(self, h_last: torch.Tensor, out: torch.Tensor):
         """final norm + lm_head for <= 8 rows (fused in the weight-streaming kernel)."""
         B = h_last.shape[0]
-        for b0 in range(0, B, 8):
-            gemv(h_last[b0:b0 + 8], self.w.lm_head, out[b0:b0 + 8], norm_w=self.w.final_norm, eps=self.cfg.text.rms_eps)
+        for b0 in range(0, B, SKINNY_MAX_ROWS):
+            sl = slice(b0, b0 + SKINNY_MAX_ROWS)
+            skinny(h_last[sl], self.w.lm_head, out[sl], norm_w=self.w.final_norm, eps=self.cfg.text.rms_eps)
         return out
 
     # ---- one decode step for B sequences (all state on the device) ----
@@ -374,18 +402,18 @@ class Decoder:
                   st.cos.data_ptr(), st.sin.data_ptr(), _sp())
         max_pages = st.block_table.shape[1]
         for li, lay in enumerate(self.w.layers):
-            for b0 in range(0, B, 8):
-                sl = slice(b0, min(B, b0 + 8))
-                gemv(st.x[sl], lay["qkv_w"], st.qkv[sl], bias=lay["qkv_b"], norm_w=lay["ln1"], eps=t.rms_eps)
+            for b0 in range(0, B, SKINNY_MAX_ROWS):
+                sl = slice(b0, min(B, b0 + SKINNY_MAX_ROWS))
+                skinny(st.x[sl], lay["qkv_w"], st.qkv[sl], bias=lay["qkv_b"], norm_w=lay["ln1"], eps=t.rms_eps)
             _lib.call("ocrb_decode_attention", st.qkv.data_ptr(), st.qkv.stride(0), self.kv.k[li].data_ptr(),
                       self.kv.v[li].data_ptr(), st.block_table.data_ptr(), max_pages, st.ctx_len.data_ptr(), B,
                       self.kv.page, nq, nkv, hd, st.cos.data_ptr(), st.sin.data_ptr(), float(hd ** -0.5),
                       st.att.data_ptr(), st.att.stride(0), st.split_ws.data_ptr(), st.n_splits, _sp())
-            for b0 in range(0, B, 8):
-                sl = slice(b0, min(B, b0 + 8))
-                gemv(st.att[sl], lay["o_w"], st.x[sl], residual=st.x[sl], epilogue=EPI_RESIDUAL)
-                gemv(st.x[sl], lay["gu_w"], st.act[sl], epilogue=EPI_SWIGLU, norm_w=lay["ln2"], eps=t.rms_eps)
-                gemv(st.act[sl], lay["down_w"], st.x[sl], residual=st.x[sl], epilogue=EPI_RESIDUAL)
+            for b0 in range(0, B, SKINNY_MAX_ROWS):
+                sl = slice(b0, min(B, b0 + SKINNY_MAX_ROWS))
+                skinny(st.att[sl], lay["o_w"], st.x[sl], residual=st.x[sl], epilogue=EPI_RESIDUAL)
+                skinny(st.x[sl], lay["gu_w"], st.act[sl], epilogue=EPI_SWIGLU, norm_w=lay["ln2"], eps=t.rms_eps)
+                skinny(st.act[sl], lay["down_w"], st.x[sl], residual=st.x[sl], epilogue=EPI_RESIDUAL)
         self.logits_last(st.x, st.logits)
         _lib.call("ocrb_argmax_step", st.logits.data_ptr(), st.logits.stride(0), B, t.vocab, EOS, EOS, st.max_new,
                   st.out_tokens.data_ptr(), st.next_ids.data_ptr(), st.finished.data_ptr(), st.ctx_len.data_ptr(),
@@ -407,12 +435,12 @@ class Decoder:
 
         def one():
             for lay in self.w.layers:
-                for b0 in range(0, B, 8):
-                    sl = slice(b0, min(B, b0 + 8))
-                    gemv(x[sl], lay["qkv_w"], qkv[sl], bias=lay["qkv_b"], norm_w=lay["ln1"], eps=t.rms_eps)
-                    gemv(att[sl], lay["o_w"], y[sl], residual=x[sl], epilogue=EPI_RESIDUAL)
-                    gemv(x[sl], lay["gu_w"], act[sl], epilogue=EPI_SWIGLU, norm_w=lay["ln2"], eps=t.rms_eps)
-                    gemv(act[sl], lay["down_w"], y[sl], residual=x[sl], epilogue=EPI_RESIDUAL)
+                for b0 in range(0, B, SKINNY_MAX_ROWS):
+                    sl = slice(b0, min(B, b0 + SKINNY_MAX_ROWS))
+                    skinny(x[sl], lay["qkv_w"], qkv[sl], bias=lay["qkv_b"], norm_w=lay["ln1"], eps=t.rms_eps)
+                    skinny(att[sl], lay["o_w"], y[sl], residual=x[sl], epilogue=EPI_RESIDUAL)
+                    skinny(x[sl], lay["gu_w"], act[sl], epilogue=EPI_SWIGLU, norm_w=lay["ln2"], eps=t.rms_eps)
+                    skinny(act[sl], lay["down_w"], y[sl], residual=x[sl], epilogue=EPI_RESIDUAL)
             self.logits_last(x, logits)
 
         one()
@@ -489,9 +517,8 @@ class DecodeState:
         self.cos = torch.empty((B, t.head_dim), dtype=BF, device=dev)
         self.sin = torch.empty((B, t.head_dim), dtype=BF, device=dev)
         max_ctx = block_table.shape[1] * dec.kv.page
-        # enough splits that (splits x kv heads x B) CTAs cover the machine; chunk <= 512 keys
-        want = max(1, math.ceil(148 / max(1, B * t.kv_heads)))
-        self.n_splits = int(min(max(want, math.ceil(max_ctx / 512)), max(1, max_ctx // 32)))
+        # split-KV: 64-key chunks, one CTA per (chunk, kv head, sequence); chunks beyond the context exit at once
+        self.n_splits = int(max(1, math.ceil(max_ctx / 64)))
         self.split_ws = torch.empty(B * t.heads * self.n_splits * (t.head_dim + 2), dtype=torch.float32, device=dev)
         self.graph = None
         self.graph_launches = 0

@@ -123,6 +123,18 @@ int ocrb_gemv_bf16(const void *A, int64_t lda, const void *W, int64_t ldw, void 
                    int32_t B, int32_t N, int32_t K, const void *bias, const void *residual,
                    int64_t ldr, int32_t epilogue, const void *norm_w, float eps, void *stream);
 
+/* Weight-streaming skinny GEMM for decode on tcgen05 (swap-AB: the 128x64 weight tile is the UMMA M operand,
+ * the B <= 64 activation rows are the N operand; TMA weight ring; stream-K split over all SMs with a
+ * deterministic, batch-invariant fix-up).  Same contract and epilogues as ocrb_gemv_bf16, B in 1..64.
+ * workspace: ocrb_skinny_workspace_bytes() bytes, ZERO-initialised once by the caller and then owned by
+ * this entry point (it holds stream-K partials and their ready flags; flags are returned to zero by every
+ * launch).  One workspace must not be shared by launches that can run concurrently. */
+int64_t ocrb_skinny_workspace_bytes(void);
+int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, int64_t ldw, void *D, int64_t ldd,
+                          int32_t B, int32_t N, int32_t K, const void *bias, const void *residual,
+                          int64_t ldr, int32_t epilogue, const void *norm_w, float eps, void *workspace,
+                          void *stream);
+
 /* HF Qwen2_5_VLRMSNorm (modeling:66-71): y = w * bf16( x_f32 * rsqrt(mean(x^2)+eps) ) */
 int ocrb_rmsnorm_bf16(const void *x, int64_t ldx, const void *w, void *y, int64_t ldy, int32_t rows,
                       int32_t dim, float eps, void *stream);

@@ -164,6 +164,89 @@ def test_gemv_batch_invariance(L):
         assert torch.equal(D1[0], D5[b])
 
 
+# ───────────── skinny GEMM (tcgen05 swap-AB, stream-K): the decode weight-streaming kernel ─────────────
+@pytest.fixture(scope="module")
+def skws(L):
+    n = int(L.load().ocrb_skinny_workspace_bytes())
+    return torch.zeros(n, dtype=torch.uint8, device="cuda")
+
+
+def skinny_call(L, ws, X, W, D, B, N, K, bias=None, res=None, epi=0, norm_w=None, eps=0.0, ldx=None, ldd=None):
+    L.call("ocrb_skinny_gemm_bf16", X.data_ptr(), ldx or X.stride(0), W.data_ptr(), W.stride(0), D.data_ptr(),
+           ldd or D.stride(0), B, N, K, L.ptr(bias), L.ptr(res), res.stride(0) if res is not None else 0, epi,
+           L.ptr(norm_w), eps, ws.data_ptr(), sp())
+
+
+@pytest.mark.parametrize("B", [1, 3, 8, 16, 17, 32, 40, 64])
+@pytest.mark.parametrize("N,K", [(512, 256), (4608, 3584), (3584, 18944), (1000, 328), (128, 64), (152064, 512)])
+def test_skinny_plain_bias_residual(L, skws, B, N, K):
+    X, W, b, R = rnd(B, K, seed=20), rnd(N, K, scale=K ** -0.5, seed=21), rnd(N, seed=22), rnd(B, N, seed=23)
+    for epi, bias in [(0, None), (0, b), (1, None)]:
+        D = torch.full((B, N), float("nan"), device="cuda", dtype=BF)
+        skinny_call(L, skws, X, W, D, B, N, K, bias=bias, res=R if epi == 1 else None, epi=epi)
+        torch.cuda.synchronize()
+        lin = ref_linear(X, W, bias)
+        want = (lin.float() + R.float()).to(BF) if epi == 1 else lin
+        close_bf16(D, want, f"skinny B={B} {N}x{K} epi={epi}", mag=lin)
+    assert int(skws.view(torch.int32)[-296 - 64:].abs().sum()) == 0, "stream-K flags must return to zero"
+
+
+@pytest.mark.parametrize("B", [1, 3, 24])
+def test_skinny_fused_norm_swiglu_gelu(L, skws, B):
+    K, I = 3584, 1024
+    X, nw = rnd(B, K, seed=30), (1 + 0.1 * rnd(K, seed=31).float()).to(BF)
+    Wg, Wu = rnd(I, K, scale=K ** -0.5, seed=32), rnd(I, K, scale=K ** -0.5, seed=33)
+    Wp = pack_swiglu(Wg, Wu)
+    D = torch.full((B, I), float("nan"), device="cuda", dtype=BF)
+    skinny_call(L, skws, X, Wp, D, B, 2 * I, K, epi=2, norm_w=nw, eps=1e-6)
+    torch.cuda.synchronize()
+    xn = hf_rmsnorm(X, nw, 1e-6)
+    g, u = ref_linear(xn, Wg), ref_linear(xn, Wu)
+    close_bf16(D, torch.nn.functional.silu(g) * u, "skinny norm+swiglu", ulps=4.0, frac_exact=0.9,
+               mag=g.float().abs() * u.float().abs())
+    bias = rnd(I, seed=34)
+    D2 = torch.full((B, I), float("nan"), device="cuda", dtype=BF)
+    skinny_call(L, skws, X, Wg, D2, B, I, K, bias=bias, epi=3)
+    torch.cuda.synchronize()
+    lin = ref_linear(X, Wg, bias)
+    close_bf16(D2, torch.nn.functional.gelu(lin), "skinny gelu", ulps=3.0, frac_exact=0.9, mag=lin)
+
+
+def test_skinny_strided_and_inplace_residual(L, skws):
+    B, N, K = 5, 3584, 3584
+    Xbig, W = rnd(B, K + 64, seed=35), rnd(N, K, scale=K ** -0.5, seed=36)
+    X = Xbig[:, 8:8 + K]
+    H = rnd(B, N, seed=37)
+    H0 = H.clone()
+    skinny_call(L, skws, X, W, H, B, N, K, res=H, epi=1)          # x += o_proj(att), in place as the decoder does
+    torch.cuda.synchronize()
+    lin = ref_linear(X, W)
+    close_bf16(H, (lin.float() + H0.float()).to(BF), "skinny in-place residual", mag=lin)
+
+
+def test_skinny_batch_invariance(L, skws):
+    """A sequence decoded in a batch of 3, 16, 17 (BP=32) or 64 (BP=64) produces the bits it produces alone."""
+    N, K = 4608, 3584
+    X, W, nw = rnd(64, K, seed=40), rnd(N, K, scale=K ** -0.5, seed=41), (1 + 0.1 * rnd(K, seed=42).float()).to(BF)
+    alone = []
+    for b in range(4):
+        D1 = torch.empty((1, N), device="cuda", dtype=BF)
+        skinny_call(L, skws, X[b:b + 1], W, D1, 1, N, K, norm_w=nw, eps=1e-6)
+        alone.append(D1[0].clone())
+    for Bb in (3, 16, 17, 64):
+        D = torch.empty((Bb, N), device="cuda", dtype=BF)
+        skinny_call(L, skws, X[:Bb], W, D, Bb, N, K, norm_w=nw, eps=1e-6)
+        torch.cuda.synchronize()
+        for b in range(3):
+            assert torch.equal(alone[b], D[b]), f"row {b} differs between B=1 and B={Bb}"
+    # and run-to-run determinism of the stream-K fix-up
+    D_a = torch.empty((16, N), device="cuda", dtype=BF)
+    D_b = torch.empty((16, N), device="cuda", dtype=BF)
+    skinny_call(L, skws, X[:16], W, D_a, 16, N, K)
+    skinny_call(L, skws, X[:16], W, D_b, 16, N, K)
+    assert torch.equal(D_a, D_b)
+
+
 @pytest.mark.parametrize("rows,dim", [(7, 1280), (3, 3584), (999, 5120)])
 def test_rmsnorm(L, rows, dim):
     x, w = rnd(rows, dim, seed=50), (1 + 0.1 * rnd(dim, seed=51).float()).to(BF)
@@ -247,10 +330,11 @@ def test_attention_varlen(L, hd, nq, nkv, causal, lens):
         off += n
 
 
-def test_decode_attention_paged(L):
-    B, nq, nkv, hd, page = 3, 28, 4, 128, 16
+@pytest.mark.parametrize("n_splits,max_pages,nq,nkv,hd", [(6, 20, 28, 4, 128), (1, 20, 28, 4, 128), (3, 24, 28, 4, 128),
+                                                         (4, 20, 4, 2, 128), (2, 20, 8, 2, 64)])
+def test_decode_attention_paged(L, n_splits, max_pages, nq, nkv, hd):
+    B, page = 3, 16
     ctx = [100, 37, 250]
-    max_pages = 20
     n_pages = B * max_pages
     kc = rnd(n_pages, page, nkv, hd, seed=80)
     vc = rnd(n_pages, page, nkv, hd, seed=81)
@@ -261,7 +345,6 @@ def test_decode_attention_paged(L):
     emb = torch.cat((ang, ang), -1)
     cos, sin = emb.cos().to(BF).contiguous(), emb.sin().to(BF).contiguous()
     ctx_d = torch.tensor(ctx, dtype=torch.int32, device="cuda")
-    n_splits = 6
     ws = torch.empty(B * nq * n_splits * (hd + 2), device="cuda", dtype=torch.float32)
     out = torch.empty(B, nq * hd, device="cuda", dtype=BF)
     kc0, vc0 = kc.clone(), vc.clone()
