@@ -3,6 +3,7 @@
 // per step for all B sequences) with HF's rounding points fused in, and split-KV paged attention.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace ocrb {
 
@@ -427,12 +428,190 @@ decode_attn_partial_kernel(const bf16 *__restrict__ qkv, long long ldqkv, bf16 *
   for (int g = tid; g < G; g += DA_THREADS) { ws[g * ws_head] = s_m[g]; ws[g * ws_head + 1] = s_l[g]; }
 }
 
+// ───────────── tensor-core variant (hd = 128, chunk <= 64 keys, G <= 16 query heads per KV head) ─────────────
+// The SIMT kernel above is bound by per-warp instruction latency (~5k dependent instructions per warp).  Here the
+// G query heads of one KV head are the M = 16 rows of mma.sync.m16n8k16 tiles (rows >= G are zero), so a 64-key chunk
+// costs 32 MMAs per warp: S = Q.K^T with K rows as the "col" operand, softmax in fp32 in shared memory, O = P.V with
+// V through ldmatrix.trans.  K/V rows are fetched with cp.async BEFORE griddepcontrol.wait (they were written by
+// earlier steps, not by the preceding qkv GEMM), so the loads overlap the predecessor's tail under PDL.
+constexpr int DM_CH = 64;              // keys per CTA
+constexpr int DM_HD = 128;
+constexpr int DM_PITCH = DM_HD + 8;    // bf16 elements per shared row (272 B: conflict-free ldmatrix)
+constexpr int DM_SP = DM_CH + 8;       // P row pitch (bf16)
+constexpr int DM_SS = DM_CH + 4;       // S row pitch (fp32)
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void *p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void *p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128)
+decode_attn_mma_kernel(const bf16 *__restrict__ qkv, long long ldqkv, bf16 *__restrict__ k_cache, bf16 *__restrict__ v_cache,
+                       const int32_t *__restrict__ block_table, int max_pages, const int32_t *__restrict__ ctx_len,
+                       int page_size, int n_q, int n_kv, const bf16 *__restrict__ cosT, const bf16 *__restrict__ sinT,
+                       float scale, float *__restrict__ split_ws, int n_splits, int chunk, int early) {
+  constexpr int hd = DM_HD;
+  __shared__ __align__(16) bf16 sQ[16 * DM_PITCH];
+  __shared__ __align__(16) bf16 sK[DM_CH * DM_PITCH];
+  __shared__ __align__(16) bf16 sV[DM_CH * DM_PITCH];
+  __shared__ __align__(16) float sS[16 * DM_SS];
+  __shared__ __align__(16) bf16 sP[16 * DM_SP];
+  __shared__ float s_m[16], s_l[16];
+  const int G = n_q / n_kv;
+  const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) pdl_launch_dependents();
+  if (early == 0) pdl_wait();
+  const int ctx = ctx_len[b];          // written by the previous step's argmax kernel: complete long before this launch
+  const int total = ctx + 1;
+  const int k0 = split * chunk;
+  const int k1 = min(total, k0 + chunk);
+  float *ws = split_ws + (((size_t)b * n_q + (size_t)kvh * G) * n_splits + split) * (hd + 2);
+  const size_t ws_head = (size_t)n_splits * (hd + 2);
+  if (k0 >= k1) {
+    if (early != 0) pdl_wait();        // split_ws may still be read by the previous layer's combine kernel
+    for (int g = tid; g < G; g += 128) { ws[g * ws_head] = -INFINITY; ws[g * ws_head + 1] = 0.f; }
+    return;
+  }
+  const int nk = k1 - k0;
+  const size_t tok_stride = (size_t)n_kv * hd;
+  const int32_t *bt = block_table + (size_t)b * max_pages;
+  if (early == 1) pdl_wait();
+  // ---- K / V rows of already cached tokens: 16-byte cp.async, 16 per thread; other rows are zero-filled ----
+  {
+    const int c16 = tid & 15;                      // 16-byte column of the row
+#pragma unroll
+    for (int i = 0; i < DM_CH / 8; ++i) {
+      const int r = (tid >> 4) + i * 8;
+      const int key = k0 + r;
+      bf16 *dk = sK + r * DM_PITCH + c16 * 8, *dv = sV + r * DM_PITCH + c16 * 8;
+      if (key < ctx) {
+        const size_t row = (size_t)bt[key / page_size] * page_size + key % page_size;
+        cp_async16(dk, k_cache + row * tok_stride + (size_t)kvh * hd + c16 * 8);
+        cp_async16(dv, v_cache + row * tok_stride + (size_t)kvh * hd + c16 * 8);
+      } else if (key != ctx) {
+        *reinterpret_cast<uint4 *>(dk) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(dv) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int i = tid; i < 16 * DM_SP / 2; i += 128) reinterpret_cast<uint32_t *>(sP)[i] = 0u;
+  if (early == 2) pdl_wait();          // qkv comes from the preceding skinny GEMM
+  const bf16 *row = qkv + (size_t)b * ldqkv;
+  const bf16 *c = cosT + (size_t)b * hd, *s = sinT + (size_t)b * hd;
+  for (int i = tid; i < 16 * hd; i += 128) {
+    const int g = i >> 7, d = i & 127;
+    float v = 0.f;
+    if (g < G) v = rope_elem_bf16(row + (size_t)(kvh * G + g) * hd, d, hd, c, s);
+    sQ[g * DM_PITCH + d] = __float2bfloat16_rn(v);
+  }
+  if (ctx >= k0 && ctx < k0 + chunk) {
+    // this chunk holds the new token: rope its key, place k/v in the tile and append them to the cache
+    const bf16 *knew = row + (size_t)n_q * hd + (size_t)kvh * hd;
+    const bf16 *vnew = row + (size_t)(n_q + n_kv) * hd + (size_t)kvh * hd;
+    const size_t dst = ((size_t)bt[ctx / page_size] * page_size + ctx % page_size) * tok_stride + (size_t)kvh * hd;
+    const int r = ctx - k0;
+    for (int d = tid; d < hd; d += 128) {
+      const bf16 kr = __float2bfloat16_rn(rope_elem_bf16(knew, d, hd, c, s));
+      const bf16 vr = vnew[d];
+      sK[r * DM_PITCH + d] = kr;
+      sV[r * DM_PITCH + d] = vr;
+      k_cache[dst + d] = kr;
+      v_cache[dst + d] = vr;
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  // ---- S = Q.K^T: warp w owns keys [16w, 16w+16) ----
+  {
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const int m = lane >> 3, l8 = lane & 7;
+#pragma unroll
+    for (int kk = 0; kk < hd / 16; ++kk) {
+      uint32_t a[4], bb[4];
+      ldmatrix_x4(a, sQ + ((m & 1) * 8 + l8) * DM_PITCH + kk * 16 + (m >> 1) * 8);
+      ldmatrix_x4(bb, sK + (warp * 16 + (m >> 1) * 8 + l8) * DM_PITCH + kk * 16 + (m & 1) * 8);
+      mma_bf16_16816(acc[0], a, bb[0], bb[1]);
+      mma_bf16_16816(acc[1], a, bb[2], bb[3]);
+    }
+    const int r0 = lane >> 2, cq = (lane & 3) * 2;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int col = warp * 16 + j * 8 + cq;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = (col + e) < nk;
+        sS[r0 * DM_SS + col + e] = ok ? acc[j][e] * scale : -INFINITY;
+        sS[(r0 + 8) * DM_SS + col + e] = ok ? acc[j][2 + e] * scale : -INFINITY;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- softmax statistics of the chunk (fp32) and P in bf16: warp w handles heads w, w+4, ... ----
+  for (int g = warp; g < G; g += 4) {
+    const float x0 = sS[g * DM_SS + lane], x1 = sS[g * DM_SS + 32 + lane];
+    float mx = fmaxf(x0, x1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float p0 = __expf(x0 - mx), p1 = __expf(x1 - mx);
+    float l = p0 + p1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    sP[g * DM_SP + lane] = __float2bfloat16_rn(p0);
+    sP[g * DM_SP + 32 + lane] = __float2bfloat16_rn(p1);
+    if (lane == 0) { s_m[g] = mx; s_l[g] = l; }
+  }
+  __syncthreads();
+  // ---- O = P.V: warp w owns dims [32w, 32w+32) ----
+  {
+    float o[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+    const int m = lane >> 3, l8 = lane & 7;
+#pragma unroll
+    for (int ks = 0; ks < DM_CH / 16; ++ks) {
+      uint32_t a[4];
+      ldmatrix_x4(a, sP + ((m & 1) * 8 + l8) * DM_SP + ks * 16 + (m >> 1) * 8);
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        uint32_t bb[4];
+        ldmatrix_x4_trans(bb, sV + (ks * 16 + (m & 1) * 8 + l8) * DM_PITCH + warp * 32 + jj * 16 + (m >> 1) * 8);
+        mma_bf16_16816(o[jj * 2], a, bb[0], bb[1]);
+        mma_bf16_16816(o[jj * 2 + 1], a, bb[2], bb[3]);
+      }
+    }
+    const int r0 = lane >> 2, cq = (lane & 3) * 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = warp * 32 + j * 8 + cq;
+      if (r0 < G) *reinterpret_cast<float2 *>(ws + r0 * ws_head + 2 + d) = make_float2(o[j][0], o[j][1]);
+      if (r0 + 8 < G) *reinterpret_cast<float2 *>(ws + (r0 + 8) * ws_head + 2 + d) = make_float2(o[j][2], o[j][3]);
+    }
+  }
+  for (int g = tid; g < G; g += 128) { ws[g * ws_head] = s_m[g]; ws[g * ws_head + 1] = s_l[g]; }
+}
+
 // grid = (n_q, B), hd threads
 __global__ void decode_attn_combine_kernel(const float *__restrict__ split_ws, int n_q, int n_splits, int hd,
                                            bf16 *__restrict__ out, long long ldo) {
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
-  if (d == 0) pdl_launch_dependents();
   pdl_wait();
+  // Trigger only now: the o_proj GEMM behind this kernel then overlaps this (short) kernel, not the attention
+  // kernel before it.  Letting the GEMM prologue start during decode_attn_mma_kernel faulted on small grids
+  // (illegal address, cause not established -- DESIGN.md "PDL"), and measured no faster.
+  if (d == 0) pdl_launch_dependents();
   const float *ws = split_ws + ((size_t)b * n_q + h) * n_splits * (hd + 2);
   float M = -INFINITY;
   for (int s = 0; s < n_splits; ++s) M = fmaxf(M, ws[(size_t)s * (hd + 2)]);
@@ -521,13 +700,30 @@ extern "C" int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cac
     OCRB_CUDA(cudaFuncSetAttribute(decode_attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  OCRB_CUDA(launch_pdl(decode_attn_partial_kernel, dim3(n_splits, n_kv, B), dim3(DA_THREADS), smem, st, (const bf16 *)qkv,
+  static int use_mma = -1, early = 2;
+  if (use_mma < 0) {
+    const char *e = getenv("OCRB_ATTN_SIMT");
+    use_mma = (e && e[0] == '1') ? 0 : 1;
+    const char *e2 = getenv("OCRB_ATTN_EARLY");
+    if (e2) early = atoi(e2);
+  }
+  if (use_mma && hd == DM_HD && G <= 16 && chunk <= DM_CH) {
+    OCRB_CUDA(launch_pdl_bit(2, decode_attn_mma_kernel, dim3(n_splits, n_kv, B), dim3(128), 0, st, (const bf16 *)qkv, (long long)ldqkv,
+                         (bf16 *)k_cache, (bf16 *)v_cache, block_table, (int)max_pages, ctx_len, (int)page_size, (int)n_q,
+                         (int)n_kv, (const bf16 *)cosT, (const bf16 *)sinT, scale, split_ws, (int)n_splits, chunk, early));
+    int rc = check_launch("decode_attn_mma_kernel");
+    if (rc) return rc;
+    OCRB_CUDA(launch_pdl_bit(4, decode_attn_combine_kernel, dim3(n_q, B), dim3(hd), 0, st, (const float *)split_ws, (int)n_q,
+                         (int)n_splits, (int)hd, (bf16 *)out, (long long)ldo));
+    return check_launch("decode_attn_combine_kernel");
+  }
+  OCRB_CUDA(launch_pdl_bit(2, decode_attn_partial_kernel, dim3(n_splits, n_kv, B), dim3(DA_THREADS), smem, st, (const bf16 *)qkv,
                        (long long)ldqkv, (bf16 *)k_cache, (bf16 *)v_cache, block_table, (int)max_pages, ctx_len,
                        (int)page_size, (int)n_q, (int)n_kv, (int)hd, (const bf16 *)cosT, (const bf16 *)sinT, scale, split_ws,
                        (int)n_splits, chunk));
   int rc = check_launch("decode_attn_partial_kernel");
   if (rc) return rc;
-  OCRB_CUDA(launch_pdl(decode_attn_combine_kernel, dim3(n_q, B), dim3(hd), 0, st, (const float *)split_ws, (int)n_q,
+  OCRB_CUDA(launch_pdl_bit(4, decode_attn_combine_kernel, dim3(n_q, B), dim3(hd), 0, st, (const float *)split_ws, (int)n_q,
                        (int)n_splits, (int)hd, (bf16 *)out, (long long)ldo));
   return check_launch("decode_attn_combine_kernel");
 }

@@ -6,13 +6,13 @@
 namespace ocrb {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
-bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char *e = getenv("OCRB_PDL");
-    on = (e && e[0] == '0') ? 0 : 1;
+bool pdl_enabled(int bit) {
+  static int mask = -1;
+  if (mask < 0) {
+    const char *e = getenv("OCRB_PDL");      // bit mask: 1 = skinny GEMM, 2 = decode attention, 4 = attention combine
+    mask = e ? atoi(e) : 7;
   }
-  return on == 1;
+  return (mask & bit) != 0;
 }
 void set_error(const char *fmt, ...) {
   va_list ap;

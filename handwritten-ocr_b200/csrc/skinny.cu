@@ -73,6 +73,19 @@ __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t *r) {
       : "r"(taddr));
 }
 
+template <>
+__device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, uint32_t *r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld_cols<4>(uint32_t taddr, uint32_t *r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+
 __device__ __forceinline__ float sk_silu(float g) { return bf16_round(g / (1.0f + expf(-g))); }
 __device__ __forceinline__ float sk_gelu(float x) { return bf16_round(0.5f * x * (1.0f + erff(x * 0.70710678118654752440f))); }
 
@@ -173,7 +186,9 @@ __device__ __forceinline__ void sk_row_rstd(const SkinnyParams &p, int w8, int l
   }
 }
 
-template <int BP>
+// BP = MMA N (activation rows staged per k-block: 16/32/64); BC = accumulator columns the epilogue actually reads,
+// publishes and stores (4/8/16/32/64 >= B): with B = 3 sequences the fix-up moves 4 columns, not 16.
+template <int BP, int BC>
 __global__ void __launch_bounds__(SK_THREADS, (BP <= 16) ? 2 : 1)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
   constexpr uint32_t X_BYTES = BP * SK_BK * 2;
@@ -358,14 +373,17 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
       const int acc = seg & 1;
       mbar_wait(&tmem_full[acc], (seg >> 1) & 1);
       tcgen05_fence_after();
-      float v[BP];
+      float v[BC];
+      {
+        constexpr int LC = (BC < 16) ? BC : 16;
 #pragma unroll
-      for (int c = 0; c < BP; c += 16) {
-        uint32_t r[16];
-        tmem_ld_cols<16>(lane_addr + acc * BP + c, r);
-        tmem_ld_wait();
+        for (int c = 0; c < BC; c += LC) {
+          uint32_t r[LC];
+          tmem_ld_cols<LC>(lane_addr + acc * BP + c, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[c + i] = __uint_as_float(r[i]);
+          for (int i = 0; i < LC; ++i) v[c + i] = __uint_as_float(r[i]);
+        }
       }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);             // accumulator drained: the MMA warp may reuse it
@@ -373,9 +391,9 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
       const bool finishes = (kb0 + nkb == KB);
       if (!finishes) {
         // partial span: publish fp32 partials, then the flag
-        float *slot = p.partials + (size_t)blockIdx.x * BP * 128;
+        float *slot = p.partials + (size_t)blockIdx.x * BC * 128;
 #pragma unroll
-        for (int b = 0; b < BP; ++b) __stcg(slot + b * 128 + et, v[b]);
+        for (int b = 0; b < BC; ++b) __stcg(slot + b * 128 + et, v[b]);
         __threadfence();
         named_bar_sync(1, 128);
         if (et == 0) {
@@ -390,10 +408,10 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
           const int per = total / (int)gridDim.x, rem = total % (int)gridDim.x;
           const int big = rem * (per + 1);
           const int c0 = (tile_first < big) ? tile_first / (per + 1) : rem + (tile_first - big) / per;
-          float sum[BP];
+          float sum[BC];
 #pragma unroll
-          for (int b = 0; b < BP; ++b) sum[b] = 0.f;
-          constexpr int FX = (BP <= 16) ? 2 : 1;   // contributors fetched together
+          for (int b = 0; b < BC; ++b) sum[b] = 0.f;
+          constexpr int FX = (BC <= 4) ? 8 : ((BC <= 8) ? 4 : ((BC <= 16) ? 2 : 1));   // contributors fetched together
           for (int cb = c0; cb < (int)blockIdx.x; cb += FX) {
             const int nc = min(FX, (int)blockIdx.x - cb);
             if (et < nc) {
@@ -409,52 +427,48 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
               } while (!f);
             }
             named_bar_sync(1, 128);
-            float pv[FX][BP];
+            float pv[FX][BC];
 #pragma unroll
             for (int i = 0; i < FX; ++i) {
-              const float *slot = p.partials + (size_t)(cb + (i < nc ? i : 0)) * BP * 128;
+              const float *slot = p.partials + (size_t)(cb + (i < nc ? i : 0)) * BC * 128;
 #pragma unroll
-              for (int b = 0; b < BP; ++b) pv[i][b] = __ldcg(slot + b * 128 + et);
+              for (int b = 0; b < BC; ++b) pv[i][b] = __ldcg(slot + b * 128 + et);
             }
 #pragma unroll
             for (int i = 0; i < FX; ++i)
               if (i < nc) {
 #pragma unroll
-                for (int b = 0; b < BP; ++b) sum[b] += pv[i][b];
+                for (int b = 0; b < BC; ++b) sum[b] += pv[i][b];
               }
             named_bar_sync(1, 128);
             if (et < nc) p.flags[cb + et] = 0;   // consumed: ready for the next launch
           }
 #pragma unroll
-          for (int b = 0; b < BP; ++b) v[b] = sum[b] + v[b];
+          for (int b = 0; b < BC; ++b) v[b] = sum[b] + v[b];
         }
         // ───── epilogue math on the complete accumulator (HF rounding points) ─────
         const int n = tile * SK_BM + et;
         const bool n_ok = n < p.N;
         float bv = (p.bias && n_ok) ? __bfloat162float(p.bias[n]) : 0.f;
 #pragma unroll
-        for (int b = 0; b < BP; ++b) v[b] = bf16_round(v[b] + bv);
+        for (int b = 0; b < BC; ++b) v[b] = bf16_round(v[b] + bv);
         if (p.epilogue == OCRB_EPI_SWIGLU) {
           // tile rows 0..63 = gate, 64..127 = up of output columns tile*64 + j
           if (et >= 64) {
 #pragma unroll
-            for (int b = 0; b < BP; ++b) s_up[(et - 64) * BP + b] = v[b];
+            for (int b = 0; b < BC; ++b) s_up[(et - 64) * BC + b] = v[b];
           }
           named_bar_sync(1, 128);
           if (et < 64 && n_ok) {
             const int oc = tile * 64 + et;
-            for (int b = 0; b < p.B; ++b) {
-              float vb = 0.f, ub = 0.f;
 #pragma unroll
-              for (int q = 0; q < BP; ++q)
-                if (q == b) { vb = v[q]; ub = s_up[et * BP + q]; }
-              p.D[(size_t)b * p.ldd + oc] = __float2bfloat16_rn(sk_silu(vb) * ub);
-            }
+            for (int b = 0; b < BC; ++b)
+              if (b < p.B) p.D[(size_t)b * p.ldd + oc] = __float2bfloat16_rn(sk_silu(v[b]) * s_up[et * BC + b]);
           }
           named_bar_sync(1, 128);
         } else if (n_ok) {
 #pragma unroll
-          for (int b = 0; b < BP; ++b) {
+          for (int b = 0; b < BC; ++b) {
             if (b < p.B) {
               float o = v[b];
               if (p.epilogue == OCRB_EPI_RESIDUAL) o += __bfloat162float(p.residual[(size_t)b * p.ldr + n]);
@@ -474,16 +488,16 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
   }
 }
 
-template <int BP>
+template <int BP, int BC>
 static int launch_skinny(const CUtensorMap &mw, const SkinnyParams &p, int grid, cudaStream_t st) {
   constexpr size_t smem = (size_t)SK_STAGES * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 256 /*barriers*/ +
                           (SK_MAXBP + 4 * SK_MAXBP + 64 * BP) * sizeof(float) + 64;
   static bool attr_set = false;
   if (!attr_set) {
-    OCRB_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<BP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OCRB_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<BP, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  OCRB_CUDA(launch_pdl(skinny_gemm_kernel<BP>, dim3(grid), dim3(SK_THREADS), smem, st, mw, p));
+  OCRB_CUDA(launch_pdl(skinny_gemm_kernel<BP, BC>, dim3(grid), dim3(SK_THREADS), smem, st, mw, p));
   return check_launch("skinny_gemm_kernel");
 }
 
@@ -542,7 +556,9 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
   int rc = make_tensor_map_bf16(&mw, W, N, K, ldw, SK_BM);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (B <= 16) return launch_skinny<16>(mw, p, grid, st);
-  if (B <= 32) return launch_skinny<32>(mw, p, grid, st);
-  return launch_skinny<64>(mw, p, grid, st);
+  if (B <= 4) return launch_skinny<16, 4>(mw, p, grid, st);
+  if (B <= 8) return launch_skinny<16, 8>(mw, p, grid, st);
+  if (B <= 16) return launch_skinny<16, 16>(mw, p, grid, st);
+  if (B <= 32) return launch_skinny<32, 32>(mw, p, grid, st);
+  return launch_skinny<64, 64>(mw, p, grid, st);
 }
