@@ -102,7 +102,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import handwritten_ocr_b200  # noqa: F401
-    from handwritten_ocr_b200 import _lib, engine as eng_mod, preprocess, synth, textops, tools, vlm
+    from handwritten_ocr_b200 import _lib, engine as eng_mod, folder, preprocess, synth, textops, tools, vlm
     from handwritten_ocr_b200.vlm_config import VLMConfig
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -160,15 +160,22 @@ def run_b200(args):
     tok_count, decode_ms, vision_ms, prefill_ms, dec_steps, kv_tok = 0, 0.0, 0.0, 0.0, 0, 0
     barrier()
     e0.record()
+    local_results = {}
     for s in range(args.warmup, n_steps_total):
-        toks, _ = step_device(s)
+        toks, res = step_device(s)
+        for p_ in range(P):                       # global page index of (step, rank, p)
+            local_results[((s - args.warmup) * world + rank) * P + p_] = res[p_][1]
         tok_count += sum(len(t) for t in toks)
         tm = eng.timings
         decode_ms += tm["decode_ms"]; vision_ms += tm["vision_ms"]; prefill_ms += tm["prefill_ms"]
         dec_steps += tm["steps"] - 1
         kv_tok += B * sum(tm["prompt_len"] + 1 + i for i in range(tm["steps"] - 1))
+    # the job's only collective: one final gather of the merged transcriptions (folder.py)
+    gathered = folder.gather_results(local_results, args.steps * world * P)
     e1.record()
     barrier()
+    if rank == 0:
+        assert gathered is not None and len(gathered) == args.steps * world * P
     total_ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() + eng.dec.replayed_launches
     clocks = sampler.stop() if rank == 0 else None
