@@ -148,6 +148,7 @@ def run_b200(args):
     # ---- warm-up ----
     for s in range(args.warmup):
         step_device(s)
+    folder.gather_results({rank: "warm-up"}, world)      # builds the communicator outside the timed region
     barrier()
 
     # ---- timed region (device-resident inputs) ----

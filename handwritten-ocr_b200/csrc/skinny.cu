@@ -22,12 +22,16 @@
 // quadrant = warp % 4), 6..9 = activation producers.
 #include "tc_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace ocrb {
 
 constexpr int SK_BM = 128;          // weight rows per tile
 constexpr int SK_BK = 64;           // k-block: 64 bf16 = one 128-byte swizzle row
-constexpr int SK_STAGES = 5;           // 5 x 18 KiB (BP=16): two CTAs of consecutive kernels fit one SM under PDL
+#ifndef SK_STAGES_N
+#define SK_STAGES_N 5
+#endif
+constexpr int SK_STAGES = SK_STAGES_N;           // 5 x 18 KiB (BP=16): two CTAs of consecutive kernels fit one SM under PDL
 constexpr int SK_PF = 4;             // activation prefetch distance (units)
 constexpr int SK_THREADS = 320;
 constexpr int SK_MAX_GRID = 296;    // workspace slots (2 x 148)
@@ -43,6 +47,8 @@ struct SkinnyParams {
   int B, N, K;
   int epilogue;
   int num_tiles, num_kb;
+  int l2_prefetch;       // weight tiles prefetched into L2 ahead of the TMA ring (per CTA)
+  unsigned long long *trace;   // optional [grid][64] globaltimer stamps (debug / profiling), or nullptr
   float *partials;       // [SK_MAX_GRID][BP][128] fp32
   int *flags;            // [SK_MAX_GRID]
 };
@@ -60,6 +66,18 @@ __device__ __forceinline__ void tma_load_2d_hint(void *dst, const CUtensorMap *m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
+}
+
+__device__ __forceinline__ void sk_stamp(const SkinnyParams &p, int slot) {
+  if (p.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.trace[(size_t)blockIdx.x * 64 + slot] = t;
+  }
+}
+
+__device__ __forceinline__ void tma_prefetch_l2(const CUtensorMap *map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 
 template <int NC>
@@ -190,7 +208,7 @@ __device__ __forceinline__ void sk_row_rstd(const SkinnyParams &p, int w8, int l
 // publishes and stores (4/8/16/32/64 >= B): with B = 3 sequences the fix-up moves 4 columns, not 16.
 template <int BP, int BC>
 __global__ void __launch_bounds__(SK_THREADS, (BP <= 16) ? 2 : 1)
-skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
+skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, SkinnyParams p) {
   constexpr uint32_t X_BYTES = BP * SK_BK * 2;
   constexpr uint32_t STAGE_BYTES = SK_W_BYTES + X_BYTES;
   constexpr int TMEM_COLS = (2 * BP < 32) ? 32 : 2 * BP;
@@ -208,6 +226,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
   volatile int *s_flag = reinterpret_cast<volatile int *>(s_up + 64 * BP);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) sk_stamp(p, 0);            // CTA start
   const int KB = p.num_kb;
   SkSpan sp;
   sp.init(blockIdx.x, gridDim.x, p.num_tiles, KB);
@@ -216,9 +235,10 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     for (int s = 0; s < SK_STAGES; ++s) {
       mbar_init(&full_w[s], 1);
-      mbar_init(&full_x[s], 128);
+      mbar_init(&full_x[s], p.norm_w ? 4 : 1);   // norm: one arrival per producer warp; else the TMA transaction
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -235,22 +255,46 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) pdl_launch_dependents();   // the next kernel may start its own weight prefetch now
+  if (threadIdx.x == 0) { sk_stamp(p, 1); pdl_launch_dependents(); }   // the next kernel may start its own weight prefetch now
   if (warp >= 2) pdl_wait();                        // activations / residual / workspace belong to predecessors
+  if (threadIdx.x == 64) sk_stamp(p, 2);            // wait returned
 
   if (warp == 0) {
-    // ───────────── TMA producer: weights only; independent of the previous kernel's output ─────────────
+    // ───────────── TMA producer ─────────────
+    // Weights never depend on the previous kernel: their loads start at once (under PDL: while the predecessor is still
+    // running).  Without a fused RMSNorm the activation k-slices are TMA boxes of X itself ([BP rows x 64], rows >= B
+    // zero-filled by the hardware); they do depend on the predecessor, so they are issued after griddepcontrol.wait.
     if (lane == 0) {
       uint64_t policy;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      SkCursor cur;
+      const bool x_by_tma = (p.norm_w == nullptr);
+      SkCursor cur, xc;
       cur.init(sp);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < n_units; ++it) {
+      xc = cur;
+      const int head = n_units < SK_STAGES ? n_units : SK_STAGES;
+      for (int it = 0; it < head; ++it) {           // first pass over the ring: slots are free, weights only
+        mbar_expect_tx(&full_w[it], SK_W_BYTES);
+        tma_load_2d_hint(smem + it * STAGE_BYTES, &map_w, &full_w[it], cur.kb * SK_BK, cur.tile * SK_BM, policy);
+        cur.advance(sp);
+      }
+      if (x_by_tma) {
+        pdl_wait();
+        for (int it = 0; it < head; ++it) {
+          mbar_expect_tx(&full_x[it], X_BYTES);
+          tma_load_2d(smem + it * STAGE_BYTES + SK_W_BYTES, &map_x, &full_x[it], xc.kb * SK_BK, 0);
+          xc.advance(sp);
+        }
+      }
+      int s = head == SK_STAGES ? 0 : head;
+      uint32_t ph = head == SK_STAGES ? 1 : 0;
+      for (int it = head; it < n_units; ++it) {
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full_w[s], SK_W_BYTES);
         tma_load_2d_hint(smem + s * STAGE_BYTES, &map_w, &full_w[s], cur.kb * SK_BK, cur.tile * SK_BM, policy);
+        if (x_by_tma) {
+          mbar_expect_tx(&full_x[s], X_BYTES);
+          tma_load_2d(smem + s * STAGE_BYTES + SK_W_BYTES, &map_x, &full_x[s], cur.kb * SK_BK, 0);
+        }
         cur.advance(sp);
         if (++s == SK_STAGES) { s = 0; ph ^= 1; }
       }
@@ -270,7 +314,11 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
         const uint32_t tacc = tmem_base + acc * BP;
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(&full_w[s], ph);
+          if (seg == 0 && i == 0) sk_stamp(p, 3);   // first weight tile landed
+          if (p.trace && seg == 0 && i < 24) sk_stamp(p, 16 + 2 * i);
           mbar_wait(&full_x[s], ph);
+          if (seg == 0 && i == 0) sk_stamp(p, 4);   // first activation slice ready
+          if (p.trace && seg == 0 && i < 24) sk_stamp(p, 17 + 2 * i);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(sa);
@@ -285,7 +333,8 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
       }
     }
   } else if (warp >= 6) {
-    // ───────────── activation producers (128 threads) ─────────────
+    // ───────────── activation producers (128 threads): only with a fused RMSNorm ─────────────
+    if (p.norm_w != nullptr) {
     const int t = threadIdx.x - 192;
     const int pw = t >> 5;
     const bool norm = p.norm_w != nullptr;
@@ -352,11 +401,14 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
             const int r = r0 + q * 16;
             *reinterpret_cast<uint4 *>(xs + r * 128 + ((j ^ (r & 7)) << 4)) = xv[q];
           }
-          fence_proxy_async_smem();
-          mbar_arrive(&full_x[s]);
+          fence_proxy_async_smem();              // generic-proxy stores -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_x[s]);  // 4 arrivals per stage, not 128: mbarrier arrives serialise
+          if (p.trace && t == 0 && it < 12) sk_stamp(p, 40 + it);
           if (++s == SK_STAGES) { s = 0; ph ^= 1; }
         }
       }
+    }
     }
   } else {
     // ───────────── epilogue warps 2..5 ─────────────
@@ -372,6 +424,8 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
       sp.seg(seg, tile, kb0, nkb);
       const int acc = seg & 1;
       mbar_wait(&tmem_full[acc], (seg >> 1) & 1);
+      if (et == 0 && seg == 0) sk_stamp(p, 5);      // first segment accumulated
+      if (et == 0 && seg == n_segs - 1) sk_stamp(p, 6);   // last segment accumulated
       tcgen05_fence_after();
       float v[BC];
       {
@@ -398,6 +452,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
         named_bar_sync(1, 128);
         if (et == 0) {
           asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags + blockIdx.x), "r"(1) : "memory");
+          sk_stamp(p, 7);                           // partial published
         }
       } else {
         if (kb0 > 0) {
@@ -412,9 +467,10 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
 #pragma unroll
           for (int b = 0; b < BC; ++b) sum[b] = 0.f;
           constexpr int FX = (BC <= 4) ? 8 : ((BC <= 8) ? 4 : ((BC <= 16) ? 2 : 1));   // contributors fetched together
-          for (int cb = c0; cb < (int)blockIdx.x; cb += FX) {
-            const int nc = min(FX, (int)blockIdx.x - cb);
-            if (et < nc) {
+          // all contributors' flags first (one polling thread per contributor), then stream their partials
+          const int n_contrib = (int)blockIdx.x - c0;
+          for (int cb = c0; cb < (int)blockIdx.x; cb += 128) {
+            if (cb + et < (int)blockIdx.x) {
               const int c = cb + et;
               int f;
               const long long t0 = clock64();
@@ -426,7 +482,10 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
                 }
               } while (!f);
             }
-            named_bar_sync(1, 128);
+          }
+          named_bar_sync(1, 128);
+          for (int cb = c0; cb < (int)blockIdx.x; cb += FX) {
+            const int nc = min(FX, (int)blockIdx.x - cb);
             float pv[FX][BC];
 #pragma unroll
             for (int i = 0; i < FX; ++i) {
@@ -440,11 +499,13 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
 #pragma unroll
                 for (int b = 0; b < BC; ++b) sum[b] += pv[i][b];
               }
-            named_bar_sync(1, 128);
-            if (et < nc) p.flags[cb + et] = 0;   // consumed: ready for the next launch
           }
+          named_bar_sync(1, 128);
+          for (int c = c0 + et; c < (int)blockIdx.x; c += 128) p.flags[c] = 0;   // consumed: ready for the next launch
+          (void)n_contrib;
 #pragma unroll
           for (int b = 0; b < BC; ++b) v[b] = sum[b] + v[b];
+          if (et == 0) sk_stamp(p, 8);              // fix-up done
         }
         // ───── epilogue math on the complete accumulator (HF rounding points) ─────
         const int n = tile * SK_BM + et;
@@ -482,6 +543,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
     tcgen05_fence_before();
   }
   __syncthreads();
+  if (threadIdx.x == 0) sk_stamp(p, 9);             // CTA end
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -489,7 +551,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, SkinnyParams p) {
 }
 
 template <int BP, int BC>
-static int launch_skinny(const CUtensorMap &mw, const SkinnyParams &p, int grid, cudaStream_t st) {
+static int launch_skinny(const CUtensorMap &mw, const CUtensorMap &mx, const SkinnyParams &p, int grid, cudaStream_t st) {
   constexpr size_t smem = (size_t)SK_STAGES * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 256 /*barriers*/ +
                           (SK_MAXBP + 4 * SK_MAXBP + 64 * BP) * sizeof(float) + 64;
   static bool attr_set = false;
@@ -497,7 +559,7 @@ static int launch_skinny(const CUtensorMap &mw, const SkinnyParams &p, int grid,
     OCRB_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<BP, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  OCRB_CUDA(launch_pdl(skinny_gemm_kernel<BP, BC>, dim3(grid), dim3(SK_THREADS), smem, st, mw, p));
+  OCRB_CUDA(launch_pdl(skinny_gemm_kernel<BP, BC>, dim3(grid), dim3(SK_THREADS), smem, st, mw, mx, p));
   return check_launch("skinny_gemm_kernel");
 }
 
@@ -515,6 +577,10 @@ static int sm_count() {
 }  // namespace ocrb
 
 using namespace ocrb;
+
+static unsigned long long *g_sk_trace = nullptr;
+/* debug hook (not in the public header): device buffer [grid][16] of globaltimer stamps for the next launches */
+extern "C" void ocrb_skinny_set_trace(void *buf) { g_sk_trace = (unsigned long long *)buf; }
 
 extern "C" int64_t ocrb_skinny_workspace_bytes(void) {
   return (int64_t)SK_MAX_GRID * SK_MAXBP * 128 * sizeof(float) + (int64_t)SK_MAX_GRID * sizeof(int) + 256;
@@ -543,6 +609,15 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
   p.epilogue = epilogue;
   p.num_tiles = cdiv(N, SK_BM);
   p.num_kb = cdiv(K, SK_BK);
+  {
+    static int l2pf = -1;
+    if (l2pf < 0) {
+      const char *e = getenv("OCRB_L2PF");
+      l2pf = e ? atoi(e) : 0;      // default off: measured slower on B200 (profiles/r01_notes.md)
+    }
+    p.l2_prefetch = l2pf;
+  }
+  p.trace = g_sk_trace;
   p.partials = (float *)workspace;
   p.flags = (int *)((char *)workspace + (size_t)SK_MAX_GRID * SK_MAXBP * 128 * sizeof(float));
   const long long total = (long long)p.num_tiles * p.num_kb;
@@ -556,9 +631,15 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
   int rc = make_tensor_map_bf16(&mw, W, N, K, ldw, SK_BM);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (B <= 4) return launch_skinny<16, 4>(mw, p, grid, st);
-  if (B <= 8) return launch_skinny<16, 8>(mw, p, grid, st);
-  if (B <= 16) return launch_skinny<16, 16>(mw, p, grid, st);
-  if (B <= 32) return launch_skinny<32, 32>(mw, p, grid, st);
-  return launch_skinny<64, 64>(mw, p, grid, st);
+  const int BPsel = B <= 16 ? 16 : (B <= 32 ? 32 : 64);
+  CUtensorMap mx = mw;                              // unused by the kernel when the RMSNorm producers run
+  if (!norm_w) {
+    rc = make_tensor_map_bf16(&mx, X, B, K, ldx, BPsel);
+    if (rc) return rc;
+  }
+  if (B <= 4) return launch_skinny<16, 4>(mw, mx, p, grid, st);
+  if (B <= 8) return launch_skinny<16, 8>(mw, mx, p, grid, st);
+  if (B <= 16) return launch_skinny<16, 16>(mw, mx, p, grid, st);
+  if (B <= 32) return launch_skinny<32, 32>(mw, mx, p, grid, st);
+  return launch_skinny<64, 64>(mw, mx, p, grid, st);
 }

@@ -4,78 +4,75 @@
 
 namespace ocrb {
 
-// ───────────────────────── Levenshtein: one warp per pair ─────────────────────────
-// Rows are processed in bands of 32 (one DP row per lane).  At step t lane l computes cell
-// (row base+l+1, col t-l): a skewed anti-diagonal wavefront.  `up` and the b symbol flow from
-// lane l-1 by shuffle; the band's top boundary row lives in `rowbuf` (global, L1/L2 resident),
-// read by lane 0 through 32-wide coalesced chunks and rewritten in place by lane 31 (the write
-// column trails the read column by 31, so in-place is safe).
-constexpr int LEV_WARPS = 4;
-
-__global__ void __launch_bounds__(LEV_WARPS * 32)
+// ───────────────────────── Levenshtein: skewed anti-diagonal wavefront ─────────────────────────
+// One CTA per pair.  Thread t owns the column strip [t*C, (t+1)*C) of the DP matrix (previous-row values and the b
+// symbols of the strip live in registers); at step s it computes row i = s - t + 1 of its strip, so the active cells of
+// a step form an anti-diagonal band of T x C cells.  The only inter-thread traffic is the strip's right boundary
+// value, handed to thread t+1 through a double-buffered shared array, one __syncthreads per step.  Small pairs keep
+// the old formulation's granularity (one warp, C = 1..) simply by instantiating fewer threads.
+// Integer-exact: D[i][j] = min(D[i-1][j] + 1, D[i][j-1] + 1, D[i-1][j-1] + (a_i != b_j))   (tools.py:69-83).
+template <int C, int T>
+__global__ void __launch_bounds__(T)
 levenshtein_kernel(const int32_t *__restrict__ seq_a, const int32_t *__restrict__ off_a,
-                   const int32_t *__restrict__ seq_b, const int32_t *__restrict__ off_b, int n_pairs,
-                   int ws_stride, int32_t *__restrict__ out, int32_t *__restrict__ workspace) {
-  const int lane = threadIdx.x & 31;
-  const int pair = blockIdx.x * LEV_WARPS + (threadIdx.x >> 5);
-  if (pair >= n_pairs) return;
+                   const int32_t *__restrict__ seq_b, const int32_t *__restrict__ off_b, int32_t *__restrict__ out) {
+  __shared__ int bnd[2][T];
+  const int pair = blockIdx.x;
+  const int t = threadIdx.x;
   const int32_t *a = seq_a + off_a[pair];
   const int32_t *b = seq_b + off_b[pair];
   const int n = off_a[pair + 1] - off_a[pair];
   const int m = off_b[pair + 1] - off_b[pair];
   if (n == 0 || m == 0) {
-    if (lane == 0) out[pair] = n + m;
+    if (t == 0) out[pair] = n + m;
     return;
   }
-  volatile int32_t *rowbuf = workspace + (size_t)pair * ws_stride;  // D[base][0..m]
-  for (int j = lane; j <= m; j += 32) rowbuf[j] = j;
-  __syncwarp();
-  const unsigned full = 0xffffffffu;
-  for (int base = 0; base < n; base += 32) {
-    const int i = base + lane + 1;  // 1-based DP row of this lane
-    const bool row_ok = i <= n;
-    const int32_t ai = row_ok ? a[i - 1] : -1;
-    int left = i;       // D[i][0]
-    int diag = i - 1;   // D[i-1][0]
-    int val = 0;        // value computed at the previous step (passed down as `up`)
-    int32_t bch = 0;    // b symbol used at the previous step (passed down)
-    const int steps = m + 31;
-    for (int t0 = 1; t0 <= steps; t0 += 32) {
-      // coalesced chunk: columns t0 .. t0+31 of the boundary row and of b
-      const int jc = t0 + lane;
-      int chunk_up = 0;
-      int32_t chunk_b = 0;
-      if (jc <= m) {
-        chunk_up = rowbuf[jc];
-        chunk_b = b[jc - 1];
-      }
+  if (m > C * T) return;                       // handled by a wider instantiation (host dispatch guarantees this)
+  const int j0 = t * C;                        // 0-based first column of the strip (DP column j0 + 1)
+  int prev[C];
+  int32_t bs[C];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int t = t0 + k;
-        int up = __shfl_up_sync(full, val, 1);
-        int32_t bc = __shfl_up_sync(full, bch, 1);
-        const int up0 = __shfl_sync(full, chunk_up, k);
-        const int32_t b0 = __shfl_sync(full, chunk_b, k);
-        if (lane == 0) {
-          up = up0;
-          bc = b0;
-        }
-        const int j = t - lane;
-        if (row_ok && j >= 1 && j <= m) {
-          const int cost = (ai != bc) ? 1 : 0;
-          int v = min(up + 1, left + 1);
-          v = min(v, diag + cost);
-          diag = up;
-          left = v;
-          val = v;
-          if (lane == 31) rowbuf[j] = v;         // becomes D[base+32][j]
-          if (i == n && j == m) out[pair] = v;
-        }
-        bch = bc;
+  for (int c = 0; c < C; ++c) {
+    const int j = j0 + c;
+    prev[c] = j + 1;                           // D[0][j+1]
+    bs[c] = (j < m) ? b[j] : (int32_t)0x7fffffff;
+  }
+  int diag_in = j0;                            // D[i-1][j0] for the row about to be computed; row 0: D[0][j0] = j0
+  const int steps = n + T - 1;
+  const int own_t = (m - 1) / C, own_c = (m - 1) % C;   // strip / register holding column m
+  for (int s = 0; s < steps; ++s) {
+    const int i = s - t + 1;                   // 1-based row of this thread at this step
+    const bool active = (i >= 1) && (i <= n) && (j0 < m);
+    if (active) {
+      const int32_t ai = a[i - 1];
+      int left = (t == 0) ? i : bnd[(s + 1) & 1][t - 1];       // D[i][j0], written by thread t-1 in step s-1
+      int diag = (t == 0) ? i - 1 : diag_in;                   // D[i-1][j0]
+      diag_in = left;                                          // becomes the diagonal of the next row
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int up = prev[c];
+        const int v = min(min(up, left) + 1, diag + (ai != bs[c] ? 1 : 0));
+        diag = up;
+        left = v;
+        prev[c] = v;
+      }
+      bnd[s & 1][t] = left;                                    // D[i][j0 + C]
+      if (i == n && t == own_t) {
+        int r = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          if (c == own_c) r = prev[c];
+        out[pair] = r;
       }
     }
-    __syncwarp();
+    __syncthreads();
   }
+}
+
+template <int C, int T>
+static int launch_lev(const int32_t *seq_a, const int32_t *off_a, const int32_t *seq_b, const int32_t *off_b, int n_pairs,
+                      int32_t *out, cudaStream_t st) {
+  levenshtein_kernel<C, T><<<n_pairs, T, 0, st>>>(seq_a, off_a, seq_b, off_b, out);
+  return check_launch("levenshtein_kernel");
 }
 
 // ───────────────────────── LCS align: one CTA per (backbone, version) pair ─────────────────────────
@@ -155,10 +152,18 @@ extern "C" int ocrb_levenshtein_batch(const int32_t *seq_a, const int32_t *off_a
   using namespace ocrb;
   if (n_pairs == 0) return OCRB_OK;
   OCRB_REQUIRE(n_pairs > 0 && max_len_b >= 0, "levenshtein_batch: bad sizes");
-  OCRB_REQUIRE(seq_a && off_a && seq_b && off_b && out && workspace, "levenshtein_batch: null pointer");
-  levenshtein_kernel<<<cdiv(n_pairs, LEV_WARPS), LEV_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      seq_a, off_a, seq_b, off_b, n_pairs, max_len_b + 1, out, workspace);
-  return check_launch("levenshtein_kernel");
+  OCRB_REQUIRE(seq_a && off_a && seq_b && off_b && out, "levenshtein_batch: null pointer");
+  OCRB_REQUIRE(max_len_b <= 32 * 1024, "levenshtein_batch: sequences longer than 32768 symbols are not supported");
+  (void)workspace;   // kept in the ABI for callers that size it; the wavefront needs no global scratch
+  cudaStream_t st = (cudaStream_t)stream;
+  // strip width C x threads T >= max_len_b: narrow strips / few threads for short texts (shorter pipeline fill)
+  if (max_len_b <= 32) return launch_lev<1, 32>(seq_a, off_a, seq_b, off_b, n_pairs, out, st);
+  if (max_len_b <= 256) return launch_lev<4, 64>(seq_a, off_a, seq_b, off_b, n_pairs, out, st);
+  if (max_len_b <= 1024) return launch_lev<8, 128>(seq_a, off_a, seq_b, off_b, n_pairs, out, st);
+  if (max_len_b <= 4096) return launch_lev<16, 256>(seq_a, off_a, seq_b, off_b, n_pairs, out, st);
+  if (max_len_b <= 8192) return launch_lev<32, 256>(seq_a, off_a, seq_b, off_b, n_pairs, out, st);
+  if (max_len_b <= 16384) return launch_lev<16, 1024>(seq_a, off_a, seq_b, off_b, n_pairs, out, st);
+  return launch_lev<32, 1024>(seq_a, off_a, seq_b, off_b, n_pairs, out, st);
 }
 
 extern "C" int ocrb_lcs_align_batch(const int32_t *seq_bb, const int32_t *off_bb, const int32_t *seq_w,

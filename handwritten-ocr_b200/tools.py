@@ -89,7 +89,9 @@ def _save(arr: np.ndarray, image_path: str, label: str) -> str:
     suffix = Path(image_path).suffix or ".png"
     tmp = tempfile.NamedTemporaryFile(suffix=suffix, delete=False, prefix=f"ocr_{label}_")
     tmp.close()
-    Image.fromarray(arr).save(tmp.name)
+    # lossless either way; PNG level 1 instead of Pillow's default 6 only makes the temp file larger and the save ~4x faster
+    kw = {"compress_level": 1} if suffix.lower() == ".png" else {}
+    Image.fromarray(arr).save(tmp.name, **kw)
     return tmp.name
 
 

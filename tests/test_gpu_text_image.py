@@ -59,6 +59,21 @@ def test_levenshtein_random_vs_oracle(tx):
     assert got == want
 
 
+def test_levenshtein_dispatch_buckets(tx):
+    """Every strip-width / thread-count instantiation of the wavefront kernel, at its boundaries, in one batch."""
+    rng = np.random.default_rng(5)
+    sizes = [(40, 32), (40, 33), (300, 256), (300, 257), (1100, 1024), (900, 1025), (4200, 4096), (3000, 4097),
+             (2500, 8192), (2000, 8193), (1500, 16384), (1200, 16500), (8071, 8103)]
+    for n, m in sizes:
+        a = rng.integers(0, 6, n).astype(np.int32)
+        b = rng.integers(0, 6, m).astype(np.int32)
+        assert tx.levenshtein_ids_batch([(a, b)]) == [T._lev_ids(a, b)], (n, m)
+    # mixed lengths in one launch (the widest pair selects the instantiation; short pairs ride along)
+    pairs = [(rng.integers(0, 5, n).astype(np.int32), rng.integers(0, 5, m).astype(np.int32))
+             for n, m in [(3, 2000), (2000, 3), (700, 700), (1, 1), (0, 9), (2100, 1900)]]
+    assert tx.levenshtein_ids_batch(pairs) == [T._lev_ids(a, b) for a, b in pairs]
+
+
 def test_levenshtein_full_size_properties(tx, synth):
     """BASELINE sizes (2k and 8k chars): oracle equality + symmetry + identity + triangle bound."""
     a = synth.text(1, 350); b = synth.corrupt(a, 1, 0.06)
