@@ -48,6 +48,7 @@ _SIGS = {
     "ocrb_argmax_step": [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "ocrb_embed_gather": [_P, _P, _P, _I, _I, _P],
     "ocrb_rows_copy": [_P, _L, _P, _P, _L, _P, _I, _I, _P],
+    "ocrb_residual_add_bf16": [_P, _L, _P, _L, _I, _I, _P],
     "ocrb_decode_rope_table": [_P, _P, _P, _I, _I, _P, _P, _P],
 }
 

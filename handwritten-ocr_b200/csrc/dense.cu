@@ -241,6 +241,30 @@ extern "C" int ocrb_decode_rope_table(const int32_t *ctx_len, const int32_t *rop
   return check_launch("decode_rope_table_kernel");
 }
 
+// x[r, :] = bf16(x[r, :] + y[r, :]) -- the residual add that follows a tensor-parallel all-reduce (the fused residual
+// epilogue of the GEMMs cannot be used there: the sum over ranks has to happen first).
+__global__ void __launch_bounds__(256)
+residual_add_kernel(bf16 *__restrict__ x, long long ldx, const bf16 *__restrict__ y, long long ldy, int rows, int vec_per_row) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * vec_per_row) return;
+  const int r = (int)(idx / vec_per_row), v = (int)(idx % vec_per_row);
+  uint4 a = *reinterpret_cast<const uint4 *>(x + (size_t)r * ldx + v * 8);
+  const uint4 b = *reinterpret_cast<const uint4 *>(y + (size_t)r * ldy + v * 8);
+  bf16 *ae = reinterpret_cast<bf16 *>(&a);
+  const bf16 *be = reinterpret_cast<const bf16 *>(&b);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ae[k] = __float2bfloat16_rn(__bfloat162float(ae[k]) + __bfloat162float(be[k]));
+  *reinterpret_cast<uint4 *>(x + (size_t)r * ldx + v * 8) = a;
+}
+
+extern "C" int ocrb_residual_add_bf16(void *x, int64_t ldx, const void *y, int64_t ldy, int32_t rows, int32_t dim, void *stream) {
+  if (rows == 0) return OCRB_OK;
+  OCRB_REQUIRE(x && y && rows > 0 && dim > 0 && dim % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "residual_add_bf16: bad arguments");
+  const long long total = (long long)rows * (dim / 8);
+  residual_add_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((bf16 *)x, ldx, (const bf16 *)y, ldy, rows, dim / 8);
+  return check_launch("residual_add_kernel");
+}
+
 extern "C" int ocrb_rows_copy(const void *src, int64_t lds, const int32_t *src_idx, void *dst, int64_t ldd,
                               const int32_t *dst_idx, int32_t n_rows, int32_t dim, void *stream) {
   if (n_rows == 0) return OCRB_OK;

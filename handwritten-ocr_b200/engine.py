@@ -23,7 +23,7 @@ OCR_PROMPT = "Extract and return all the text from this handwritten document."
 class OcrEngine:
     def __init__(self, weights: VLMWeights, *, max_batch: int = 8, max_new_tokens: int = 2048,
                  max_prompt: int = 1600, page_size: int = 16, tokenizer=None, min_pixels: int = 256 * 256,
-                 max_pixels: int = 1024 * 1024):
+                 max_pixels: int = 1024 * 1024, tp=None):
         self.w = weights
         self.cfg: VLMConfig = weights.cfg
         self.dev = weights.device
@@ -32,7 +32,8 @@ class OcrEngine:
         self.min_pixels, self.max_pixels = min_pixels, max_pixels
         self.pages_per_seq = math.ceil((max_prompt + max_new_tokens) / page_size)
         self.kv = PagedKV(self.cfg, max_batch * self.pages_per_seq, page_size, self.dev)
-        self.dec = Decoder(weights, self.kv, max_batch, self.pages_per_seq * page_size)
+        self.tp = tp
+        self.dec = Decoder(weights, self.kv, max_batch, self.pages_per_seq * page_size, tp=tp)
         self._plans = {}
         self._states = {}
         self.timings = {}
@@ -116,7 +117,9 @@ class OcrEngine:
                 st.step.zero_()
                 st.out_tokens.fill_(EOS)
             last_c = last.contiguous()
-            self.dec.logits_last(last_c, st.logits)
+            self.dec.logits_last(last_c, st.logits_local)
+            if self.tp is not None:
+                self.tp.gather_vocab(st.logits_local, st.logits)
             prefill_logits = st.logits.clone() if return_debug else None
             _lib.call("ocrb_argmax_step", st.logits.data_ptr(), st.logits.stride(0), n, t.vocab, EOS, EOS, max_new,
                       st.out_tokens.data_ptr(), st.next_ids.data_ptr(), st.finished.data_ptr(), st.ctx_len.data_ptr(),
@@ -143,6 +146,14 @@ class OcrEngine:
             return out, {"prefill_logits": prefill_logits, "merged": merged, "plan": plan, "ids": ids, "pos3": pos3,
                          "delta": delta}
         return out
+
+    def close(self) -> None:
+        """Drop the captured decode graphs and cached states (call before tearing down a torch.distributed group:
+        a CUDA graph that captured NCCL collectives must not outlive its communicator)."""
+        for st in self._states.values():
+            st.graph = None
+        self._states.clear()
+        torch.cuda.synchronize()
 
     def detokenize(self, ids) -> str:
         return self.tok.decode(ids, skip_special_tokens=True)

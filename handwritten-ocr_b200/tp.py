@@ -1,0 +1,110 @@
+"""Tensor parallelism for the large (72B-class) VLM config (BASELINE.json configs[4]).
+
+The reference never shards anything (`device_map=device`, ocr_agent/tools.py:692-709); the plan here is the one
+HF ships for the model's text layers and never activates (`base_model_tp_plan`,
+HF:models/qwen2_5_vl/configuration_qwen2_5_vl.py:90-98):
+
+    q_proj / k_proj / v_proj / gate_proj / up_proj : column-parallel (output rows split; heads stay whole,
+                                                     q heads follow their KV head)
+    o_proj / down_proj                             : row-parallel (input columns split) -> all-reduce(sum)
+    lm_head                                        : vocab-split -> all-gather of the logits, then the usual
+                                                     first-index argmax
+    embeddings, norms, vision tower                : replicated
+
+One process per GPU; NCCL over NVLink/NVSwitch carries the two all-reduces per layer (`[rows, hidden]` bf16) and
+one small all-gather per step.  Everything else (weights-streaming GEMMs, attention over the rank's heads,
+paged KV of the rank's KV heads) is the single-GPU code on local shapes.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+
+from .vlm_config import TextCfg, VLMConfig
+
+BF = torch.bfloat16
+
+
+def local_config(cfg: VLMConfig, world: int) -> VLMConfig:
+    """Per-rank dimensions: heads, KV heads and MLP width divided by `world`; hidden, vocab, vision unchanged."""
+    t = cfg.text
+    if t.heads % world or t.kv_heads % world or t.intermediate % world or t.vocab % world:
+        raise ValueError(f"TP world {world} does not divide heads {t.heads} / kv {t.kv_heads} / "
+                         f"intermediate {t.intermediate} / vocab {t.vocab}")
+    lt = TextCfg(hidden=t.hidden, layers=t.layers, heads=t.heads // world, kv_heads=t.kv_heads // world,
+                 head_dim=t.head_dim, intermediate=t.intermediate // world, vocab=t.vocab, rms_eps=t.rms_eps,
+                 rope_theta=t.rope_theta, mrope_section=t.mrope_section)
+    return VLMConfig(vision=copy.deepcopy(cfg.vision), text=lt, name=f"{cfg.name}/tp{world}")
+
+
+_ROW_SPLIT = ("self_attn.q_proj.weight", "self_attn.q_proj.bias", "self_attn.k_proj.weight", "self_attn.k_proj.bias",
+              "self_attn.v_proj.weight", "self_attn.v_proj.bias", "mlp.gate_proj.weight", "mlp.up_proj.weight")
+_COL_SPLIT = ("self_attn.o_proj.weight", "mlp.down_proj.weight")
+
+
+def shard_state_dict(sd: dict, rank: int, world: int) -> dict:
+    """Slice a full HF-named state dict into rank `rank`'s shard (the text decoder and lm_head; the rest is
+    replicated).  Equal contiguous slices: with heads laid out head-major this keeps whole heads together and
+    gives rank r the KV heads its q heads attend to."""
+    out = {}
+    for name, w in sd.items():
+        if name.startswith("model.language_model.layers.") and name.endswith(_ROW_SPLIT) or name == "lm_head.weight":
+            n = w.shape[0] // world
+            out[name] = w[rank * n:(rank + 1) * n].contiguous()
+        elif name.startswith("model.language_model.layers.") and name.endswith(_COL_SPLIT):
+            n = w.shape[1] // world
+            out[name] = w[:, rank * n:(rank + 1) * n].contiguous()
+        else:
+            out[name] = w
+    return out
+
+
+class TPComm:
+    """The collectives of the tensor-parallel decoder on a torch.distributed group (NCCL on GPUs, gloo in the
+    CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self._gather = {}
+        self.n_all_reduce = 0
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.n_all_reduce += 1
+        return t
+
+    def gather_vocab(self, local: torch.Tensor, full: torch.Tensor) -> torch.Tensor:
+        """local: [B, V/world] logits of this rank's vocab slice -> full: [B, V] (slices in rank order)."""
+        B, vl = local.shape
+        buf = self._gather.get((B, vl))
+        if buf is None:
+            buf = torch.empty((self.world * B, vl), dtype=local.dtype, device=local.device)   # rank-major concatenation
+            self._gather[(B, vl)] = buf
+        self.dist.all_gather_into_tensor(buf, local.contiguous(), group=self.group)
+        full.view(B, self.world, vl).copy_(buf.view(self.world, B, vl).permute(1, 0, 2))
+        return full
+
+
+def random_weights_tp(cfg: VLMConfig, device, rank: int, world: int, seed: int = 0, **kw):
+    """Random-init weights of rank `rank` WITHOUT materialising the full model (a 72B-class model is 146 GB):
+    replicated tensors come from the common seed, sharded ones from a rank-specific seed.  Returns
+    (VLMWeights on local shapes, local VLMConfig)."""
+    from . import vlm
+    lcfg = local_config(cfg, world)
+    sd = vlm.random_state_dict(lcfg, device, seed, skip_tp_sharded=True, **kw)   # replicated tensors: same on all ranks
+    sharded = vlm.random_state_dict_text_only(lcfg, device, seed * 7919 + 1 + rank, vocab_rows=cfg.text.vocab // world, **kw)
+    sd.update(sharded)
+    w = vlm.VLMWeights.from_state_dict(lcfg, sd, free_source=True)
+    return w, lcfg
+
+
+def sharded_weights_from_full(cfg: VLMConfig, sd_full: dict, rank: int, world: int):
+    """Rank shard of a full state dict (small configs / real checkpoints that fit one device)."""
+    from . import vlm
+    lcfg = local_config(cfg, world)
+    return vlm.VLMWeights.from_state_dict(lcfg, shard_state_dict(sd_full, rank, world)), lcfg

@@ -80,6 +80,12 @@ def linear_small_or_big(X, W, out, **kw):
     return gemm(X, W, out, **kw)
 
 
+def residual_add(x, y):
+    """x += y (bf16, rounded once) -- after a tensor-parallel all-reduce."""
+    _lib.call("ocrb_residual_add_bf16", x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), x.shape[0], x.shape[1], _sp())
+    return x
+
+
 def rmsnorm(x, w, out, eps=1e-6):
     _lib.call("ocrb_rmsnorm_bf16", x.data_ptr(), x.stride(0), w.data_ptr(), out.data_ptr(), out.stride(0),
               x.shape[0], x.shape[1], float(eps), _sp())
@@ -95,7 +101,7 @@ def attention(q, k, v, out, cu, n_seq, max_len, n_q, n_kv, hd, causal):
 
 # ───────────────────────── weights ─────────────────────────
 def random_state_dict(cfg: VLMConfig, device, seed: int = 0, std: float = 0.02, bias_std: float = 0.02,
-                      lm_head_std: float | None = None) -> dict:
+                      lm_head_std: float | None = None, skip_tp_sharded: bool = False) -> dict:
     """Random-init weights in HF's state-dict naming (normal(0, 0.02) like HF `initializer_range`,
     norms = 1 + small noise so their multiply is exercised, non-zero biases so the bias paths are
     exercised).  The same dict is loaded into the HF oracle and into `VLMWeights.from_state_dict`."""
@@ -133,6 +139,8 @@ def random_state_dict(cfg: VLMConfig, device, seed: int = 0, std: float = 0.02, 
         p = f"model.language_model.layers.{i}."
         norm(p + "input_layernorm.weight", t.hidden)
         norm(p + "post_attention_layernorm.weight", t.hidden)
+        if skip_tp_sharded:
+            continue
         w(p + "self_attn.q_proj.weight", t.heads * t.head_dim, t.hidden)
         w(p + "self_attn.q_proj.bias", t.heads * t.head_dim, s=bias_std)
         w(p + "self_attn.k_proj.weight", t.kv_heads * t.head_dim, t.hidden)
@@ -144,7 +152,35 @@ def random_state_dict(cfg: VLMConfig, device, seed: int = 0, std: float = 0.02, 
         w(p + "mlp.up_proj.weight", t.intermediate, t.hidden)
         w(p + "mlp.down_proj.weight", t.hidden, t.intermediate)
     norm("model.language_model.norm.weight", t.hidden)
-    w("lm_head.weight", t.vocab, t.hidden, s=std if lm_head_std is None else lm_head_std)
+    if not skip_tp_sharded:
+        w("lm_head.weight", t.vocab, t.hidden, s=std if lm_head_std is None else lm_head_std)
+    return sd
+
+
+def random_state_dict_text_only(cfg: VLMConfig, device, seed: int, vocab_rows: int | None = None, std: float = 0.02,
+                                bias_std: float = 0.02, lm_head_std: float | None = None) -> dict:
+    """Only the tensors tensor parallelism shards (q/k/v/o, gate/up/down, lm_head) at the shapes of `cfg` (a local
+    config) -- used to give every rank its own random shard without building the full model."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    t = cfg.text
+
+    def w(name, *shape, s=std):
+        sd[name] = (torch.randn(*shape, generator=g, device=device, dtype=torch.float32) * s).to(BF)
+
+    for i in range(t.layers):
+        p = f"model.language_model.layers.{i}."
+        w(p + "self_attn.q_proj.weight", t.heads * t.head_dim, t.hidden)
+        w(p + "self_attn.q_proj.bias", t.heads * t.head_dim, s=bias_std)
+        w(p + "self_attn.k_proj.weight", t.kv_heads * t.head_dim, t.hidden)
+        w(p + "self_attn.k_proj.bias", t.kv_heads * t.head_dim, s=bias_std)
+        w(p + "self_attn.v_proj.weight", t.kv_heads * t.head_dim, t.hidden)
+        w(p + "self_attn.v_proj.bias", t.kv_heads * t.head_dim, s=bias_std)
+        w(p + "self_attn.o_proj.weight", t.hidden, t.heads * t.head_dim)
+        w(p + "mlp.gate_proj.weight", t.intermediate, t.hidden)
+        w(p + "mlp.up_proj.weight", t.intermediate, t.hidden)
+        w(p + "mlp.down_proj.weight", t.hidden, t.intermediate)
+    w("lm_head.weight", vocab_rows or t.vocab, t.hidden, s=std if lm_head_std is None else lm_head_std)
     return sd
 
 
@@ -350,10 +386,27 @@ class Decoder:
     of kernel launches whose per-step state (context lengths, next ids, step counter) lives on the
     device, so the step is captured once in a CUDA graph and replayed."""
 
-    def __init__(self, w: VLMWeights, kv: PagedKV, max_batch: int, max_ctx: int):
+    def __init__(self, w: VLMWeights, kv: PagedKV, max_batch: int, max_ctx: int, tp=None):
         self.w, self.kv, self.cfg = w, kv, w.cfg
         self.max_batch, self.max_ctx = max_batch, max_ctx
         self.replayed_launches = 0      # kernel launches issued through CUDA-graph replays (bench `gpu_launches`)
+        self.tp = tp                    # tp.TPComm for the tensor-parallel large-VLM config, else None
+        self._tp_tmp = {}
+
+    def _row_parallel(self, X, W, h):
+        """h += X @ W^T for a row-parallel linear (o_proj / down_proj).  Single GPU: residual fused in the GEMM
+        epilogue.  Tensor parallel (HF base_model_tp_plan 'rowwise'): every rank holds a K-slice, the bf16 partial
+        products are summed over ranks (NCCL all-reduce over NVLink), then the residual is added."""
+        if self.tp is None:
+            return linear_small_or_big(X, W, h, residual=h, epilogue=EPI_RESIDUAL)
+        key = (X.shape[0], h.shape[1])
+        tmp = self._tp_tmp.get(key)
+        if tmp is None:
+            tmp = torch.empty(key, dtype=BF, device=h.device)
+            self._tp_tmp[key] = tmp
+        linear_small_or_big(X, W, tmp)
+        self.tp.all_reduce(tmp)
+        return residual_add(h, tmp)
 
     # ---- prefill: T_total tokens of n_seq sequences (cu_seqlens), embeddings already assembled ----
     def prefill(self, h: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, cu: torch.Tensor, n_seq: int,
@@ -378,10 +431,10 @@ class Decoder:
                       self.kv.k[li].data_ptr(), self.kv.v[li].data_ptr(), block_table.data_ptr(), max_pages,
                       cu.data_ptr(), n_seq, TT, self.kv.page, nkv, hd, _sp())
             attention(q, k, v, att, cu, n_seq, max_len, nq, nkv, hd, True)
-            linear_small_or_big(att, lay["o_w"], h, residual=h, epilogue=EPI_RESIDUAL)
+            self._row_parallel(att, lay["o_w"], h)
             rmsnorm(h, lay["ln2"], xn, t.rms_eps)
             linear_small_or_big(xn, lay["gu_w"], act, epilogue=EPI_SWIGLU)
-            linear_small_or_big(act, lay["down_w"], h, residual=h, epilogue=EPI_RESIDUAL)
+            self._row_parallel(act, lay["down_w"], h)
         return h
 
     def logits_last(self, h_last: torch.Tensor, out: torch.Tensor):
@@ -411,10 +464,12 @@ class Decoder:
                       st.att.data_ptr(), st.att.stride(0), st.split_ws.data_ptr(), st.n_splits, _sp())
             for b0 in range(0, B, SKINNY_MAX_ROWS):
                 sl = slice(b0, min(B, b0 + SKINNY_MAX_ROWS))
-                skinny(st.att[sl], lay["o_w"], st.x[sl], residual=st.x[sl], epilogue=EPI_RESIDUAL)
+                self._row_parallel(st.att[sl], lay["o_w"], st.x[sl])
                 skinny(st.x[sl], lay["gu_w"], st.act[sl], epilogue=EPI_SWIGLU, norm_w=lay["ln2"], eps=t.rms_eps)
-                skinny(st.act[sl], lay["down_w"], st.x[sl], residual=st.x[sl], epilogue=EPI_RESIDUAL)
-        self.logits_last(st.x, st.logits)
+                self._row_parallel(st.act[sl], lay["down_w"], st.x[sl])
+        self.logits_last(st.x, st.logits_local)
+        if self.tp is not None:
+            self.tp.gather_vocab(st.logits_local, st.logits)     # vocab-split lm_head -> full [B, V] logits
         _lib.call("ocrb_argmax_step", st.logits.data_ptr(), st.logits.stride(0), B, t.vocab, EOS, EOS, st.max_new,
                   st.out_tokens.data_ptr(), st.next_ids.data_ptr(), st.finished.data_ptr(), st.ctx_len.data_ptr(),
                   st.step.data_ptr(), 1, _sp())
@@ -431,7 +486,7 @@ class Decoder:
         att = torch.randn((B, t.heads * t.head_dim), device=dev).to(BF)
         act = torch.empty((B, t.intermediate_padded), dtype=BF, device=dev)
         y = torch.empty_like(x)
-        logits = torch.empty((B, t.vocab), dtype=BF, device=dev)
+        logits = torch.empty((B, self.w.lm_head.shape[0]), dtype=BF, device=dev)
 
         def one():
             for lay in self.w.layers:
@@ -514,6 +569,8 @@ class DecodeState:
         self.att = torch.empty((B, t.heads * t.head_dim), dtype=BF, device=dev)
         self.act = torch.empty((B, t.intermediate_padded), dtype=BF, device=dev)
         self.logits = torch.empty((B, t.vocab), dtype=BF, device=dev)
+        v_local = dec.w.lm_head.shape[0]          # == vocab unless the lm_head is vocab-split (tensor parallel)
+        self.logits_local = self.logits if v_local == t.vocab else torch.empty((B, v_local), dtype=BF, device=dev)
         self.cos = torch.empty((B, t.head_dim), dtype=BF, device=dev)
         self.sin = torch.empty((B, t.head_dim), dtype=BF, device=dev)
         max_ctx = block_table.shape[1] * dec.kv.page

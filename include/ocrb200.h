@@ -194,6 +194,11 @@ int ocrb_embed_gather(const void *table, const int32_t *ids, void *out, int32_t 
 int ocrb_rows_copy(const void *src, int64_t lds, const int32_t *src_idx, void *dst, int64_t ldd,
                    const int32_t *dst_idx, int32_t n_rows, int32_t dim, void *stream);
 
+/* x[r, :dim] = bf16(x + y), row strides ldx/ldy: the residual add after a tensor-parallel all-reduce of the
+ * row-parallel o_proj / down_proj outputs (HF base_model_tp_plan, configuration_qwen2_5_vl.py:90-98). */
+int ocrb_residual_add_bf16(void *x, int64_t ldx, const void *y, int64_t ldy, int32_t rows, int32_t dim,
+                           void *stream);
+
 /* Per-step mRoPE tables for decode: pos[b] = ctx_len[b] + rope_delta[b]; writes bf16 cos/sin [B, hd]
  * (all three mrope sections share the position for text tokens). inv_freq: fp32[hd/2]. */
 int ocrb_decode_rope_table(const int32_t *ctx_len, const int32_t *rope_delta, const float *inv_freq,
