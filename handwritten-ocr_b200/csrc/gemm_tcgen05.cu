@@ -35,23 +35,45 @@ struct GemmParams {
   int epilogue;
 };
 
+// Tile order: the 148 concurrently processed tiles should share the LARGER operand panel through L2 and stream it from HBM
+// once.  N > M (prefill: weights 271 MB vs activations 22 MB): m fastest, so neighbours reuse the same weight tile;
+// otherwise (vision tower: M = 12k rows) n fastest, neighbours reuse the same activation rows.
+template <int BN>
+__device__ __forceinline__ void tile_origin(int tile, int num_n, int num_m, int &n0, int &m0) {
+  if (num_n * BN > num_m * GM_BM) {
+    n0 = (tile / num_m) * BN;
+    m0 = (tile % num_m) * GM_BM;
+  } else {
+    n0 = (tile % num_n) * BN;
+    m0 = (tile / num_n) * GM_BM;
+  }
+}
+
+// Persistent kernel: gridDim.x CTAs (one per SM) walk the 128 x BN output tiles (tile = m_blk * num_n + n_blk, so the
+// CTAs of a wave share A panels through L2).  Two TMEM accumulators of BN columns: the MMA warp fills one while the
+// epilogue warps drain the other, so bias / SwiGLU / GELU / residual arithmetic and the global stores of tile i overlap
+// the tensor-core work of tile i+1; the TMA ring runs ahead across tile boundaries.
 template <int BN>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, GemmParams p) {
   constexpr uint32_t A_BYTES = GM_BM * GM_BK * 2;   // 16 KiB
   constexpr uint32_t B_BYTES = BN * GM_BK * 2;      // 16 / 32 KiB
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;                 // 256 / 512 columns: two accumulators
   extern __shared__ uint8_t gm_smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(gm_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + GM_STAGES * STAGE_BYTES);
   uint64_t *empty_bar = full_bar + GM_STAGES;
-  uint64_t *accum_bar = empty_bar + GM_STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+  uint64_t *tmem_full = empty_bar + GM_STAGES;      // [2]
+  uint64_t *tmem_empty = tmem_full + 2;             // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM_BM;
   const int num_kb = (p.K + GM_BK - 1) / GM_BK;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_m = (p.M + GM_BM - 1) / GM_BM;
+  const int num_tiles = num_n * num_m;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -60,11 +82,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -74,106 +99,132 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % GM_STAGES;
-        const uint32_t ph = (kb / GM_STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        uint8_t *sa = smem + s * STAGE_BYTES;
-        tma_load_2d(sa, &map_a, &full_bar[s], kb * GM_BK, m0);
-        tma_load_2d(sa + A_BYTES, &map_w, &full_bar[s], kb * GM_BK, n0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int n0, m0;
+        tile_origin<BN>(tile, num_n, num_m, n0, m0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t *sa = smem + s * STAGE_BYTES;
+          tma_load_2d(sa, &map_a, &full_bar[s], kb * GM_BK, m0);
+          tma_load_2d(sa + A_BYTES, &map_w, &full_bar[s], kb * GM_BK, n0);
+          if (++s == GM_STAGES) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % GM_STAGES;
-        const uint32_t ph = (kb / GM_STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc(sa);
-        const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+        const uint32_t tacc = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < GM_BK / UMMA_K; ++k) {
-          // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < GM_BK / UMMA_K; ++k) {
+            // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
+          if (++s == GM_STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
+        umma_commit(&tmem_full[acc]);  // accumulator complete
       }
-      umma_commit(accum_bar);        // accumulator complete
     }
   } else {
     // ───────────── epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) ─────────────
     const int quad = warp & 3;
-    const int row = m0 + quad * 32 + lane;
-    mbar_wait(accum_bar, 0);
-    tcgen05_fence_after();
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const bool row_ok = row < p.M;
-    if (p.epilogue == OCRB_EPI_SWIGLU) {
-      // weight rows are packed per 128 as [gate 64 | up 64]; output column block = n0/2
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int n0, m0;
+      tile_origin<BN>(tile, num_n, num_m, n0, m0);
+      const int acc = it & 1;
+      const int row = m0 + quad * 32 + lane;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t lane_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+      const bool row_ok = row < p.M;
+      if (p.epilogue == OCRB_EPI_SWIGLU) {
+        // weight rows are packed per 128 as [gate 64 | up 64]; output column block = n0/2
 #pragma unroll 1
-      for (int blk = 0; blk < BN / 128; ++blk) {
+        for (int blk = 0; blk < BN / 128; ++blk) {
 #pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t g[32], u[32];
-          tmem_ld32(lane_addr + blk * 128 + c, g);
-          tmem_ld32(lane_addr + blk * 128 + 64 + c, u);
-          tmem_ld_wait();
-          const int ng = n0 + blk * 128 + c;        // packed row index of the gate columns
-          const int out_col = (n0 >> 1) + blk * 64 + c;
-          if (row_ok && ng < p.N) {
-            bf16 *drow = p.D + (size_t)row * p.ldd + out_col;
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t g[32], u[32];
+            tmem_ld32(lane_addr + blk * 128 + c, g);
+            tmem_ld32(lane_addr + blk * 128 + 64 + c, u);
+            tmem_ld_wait();
+            if (blk == BN / 128 - 1 && c == 32) {   // last TMEM read of this tile: hand the accumulator back
+              tcgen05_fence_before();
+              mbar_arrive_cta(&tmem_empty[acc]);
+            }
+            const int ng = n0 + blk * 128 + c;        // packed row index of the gate columns
+            const int out_col = (n0 >> 1) + blk * 64 + c;
+            if (row_ok && ng < p.N) {
+              bf16 *drow = p.D + (size_t)row * p.ldd + out_col;
 #pragma unroll
-            for (int v8 = 0; v8 < 4; ++v8) {
-              uint4 pk;
-              bf16 *pe = reinterpret_cast<bf16 *>(&pk);
+              for (int v8 = 0; v8 < 4; ++v8) {
+                uint4 pk;
+                bf16 *pe = reinterpret_cast<bf16 *>(&pk);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int i = v8 * 8 + e;
-                float gv = __uint_as_float(g[i]), uv = __uint_as_float(u[i]);
-                if (p.bias) {
-                  gv += __bfloat162float(p.bias[ng + i]);
-                  uv += __bfloat162float(p.bias[ng + 64 + i]);
+                for (int e = 0; e < 8; ++e) {
+                  const int i = v8 * 8 + e;
+                  float gv = __uint_as_float(g[i]), uv = __uint_as_float(u[i]);
+                  if (p.bias) {
+                    gv += __bfloat162float(p.bias[ng + i]);
+                    uv += __bfloat162float(p.bias[ng + 64 + i]);
+                  }
+                  pe[e] = __float2bfloat16_rn(silu_bf16r(bf16_round(gv)) * bf16_round(uv));
                 }
-                pe[e] = __float2bfloat16_rn(silu_bf16r(bf16_round(gv)) * bf16_round(uv));
+                *reinterpret_cast<uint4 *>(drow + v8 * 8) = pk;
               }
-              *reinterpret_cast<uint4 *>(drow + v8 * 8) = pk;
             }
           }
         }
-      }
-    } else {
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + c, r);
-        tmem_ld_wait();
-        const int n = n0 + c;
-        if (row_ok && n < p.N) {
-          bf16 *drow = p.D + (size_t)row * p.ldd + n;
-          const bf16 *rrow = p.residual ? p.residual + (size_t)row * p.ldr + n : nullptr;
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + c, r);
+          tmem_ld_wait();
+          if (c == BN - 32) {                        // last TMEM read of this tile
+            tcgen05_fence_before();
+            mbar_arrive_cta(&tmem_empty[acc]);
+          }
+          const int n = n0 + c;
+          if (row_ok && n < p.N) {
+            bf16 *drow = p.D + (size_t)row * p.ldd + n;
+            const bf16 *rrow = p.residual ? p.residual + (size_t)row * p.ldr + n : nullptr;
 #pragma unroll
-          for (int v8 = 0; v8 < 4; ++v8) {
-            if (n + v8 * 8 >= p.N) break;
-            uint4 pk, rk = make_uint4(0, 0, 0, 0);
-            bf16 *pe = reinterpret_cast<bf16 *>(&pk);
-            if (p.epilogue == OCRB_EPI_RESIDUAL) rk = *reinterpret_cast<const uint4 *>(rrow + v8 * 8);
-            const bf16 *re = reinterpret_cast<const bf16 *>(&rk);
+            for (int v8 = 0; v8 < 4; ++v8) {
+              if (n + v8 * 8 >= p.N) break;
+              uint4 pk, rk = make_uint4(0, 0, 0, 0);
+              bf16 *pe = reinterpret_cast<bf16 *>(&pk);
+              if (p.epilogue == OCRB_EPI_RESIDUAL) rk = *reinterpret_cast<const uint4 *>(rrow + v8 * 8);
+              const bf16 *re = reinterpret_cast<const bf16 *>(&rk);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int i = v8 * 8 + e;
-              float v = __uint_as_float(r[i]);
-              if (p.bias) v += __bfloat162float(p.bias[n + i]);
-              v = bf16_round(v);
-              if (p.epilogue == OCRB_EPI_RESIDUAL) v += __bfloat162float(re[e]);
-              else if (p.epilogue == OCRB_EPI_GELU) v = gelu_bf16r(v);
-              pe[e] = __float2bfloat16_rn(v);
+              for (int e = 0; e < 8; ++e) {
+                const int i = v8 * 8 + e;
+                float v = __uint_as_float(r[i]);
+                if (p.bias) v += __bfloat162float(p.bias[n + i]);
+                v = bf16_round(v);
+                if (p.epilogue == OCRB_EPI_RESIDUAL) v += __bfloat162float(re[e]);
+                else if (p.epilogue == OCRB_EPI_GELU) v = gelu_bf16r(v);
+                pe[e] = __float2bfloat16_rn(v);
+              }
+              *reinterpret_cast<uint4 *>(drow + v8 * 8) = pk;
             }
-            *reinterpret_cast<uint4 *>(drow + v8 * 8) = pk;
           }
         }
       }
@@ -183,7 +234,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -234,8 +285,15 @@ static int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mw, const GemmP
     OCRB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(cdiv(p.N, BN), cdiv(p.M, GM_BM));
-  gemm_tcgen05_kernel<BN><<<grid, GM_THREADS, smem, st>>>(ma, mw, p);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const int tiles = cdiv(p.N, BN) * cdiv(p.M, GM_BM);
+  gemm_tcgen05_kernel<BN><<<tiles < n_sm ? tiles : n_sm, GM_THREADS, smem, st>>>(ma, mw, p);
   return check_launch("gemm_tcgen05_kernel");
 }
 
