@@ -49,6 +49,9 @@ _SIGS = {
     "ocrb_embed_gather": [_P, _P, _P, _I, _I, _P],
     "ocrb_rows_copy": [_P, _L, _P, _P, _L, _P, _I, _I, _P],
     "ocrb_residual_add_bf16": [_P, _L, _P, _L, _I, _I, _P],
+    "ocrb_comm_ipc_handle": [_P, _P, _P],
+    "ocrb_comm_ipc_open": [_P, _L, _P],
+    "ocrb_allreduce_residual_bf16": [_P, _L, _P, _P, _I, _I, _P, _I, _I, _L, _P],
     "ocrb_decode_rope_table": [_P, _P, _P, _I, _I, _P, _P, _P],
 }
 

@@ -47,7 +47,6 @@ struct SkinnyParams {
   int B, N, K;
   int epilogue;
   int num_tiles, num_kb;
-  int l2_prefetch;       // weight tiles prefetched into L2 ahead of the TMA ring (per CTA)
   unsigned long long *trace;   // optional [grid][64] globaltimer stamps (debug / profiling), or nullptr
   float *partials;       // [SK_MAX_GRID][BP][128] fp32
   int *flags;            // [SK_MAX_GRID]
@@ -76,9 +75,6 @@ __device__ __forceinline__ void sk_stamp(const SkinnyParams &p, int slot) {
   }
 }
 
-__device__ __forceinline__ void tma_prefetch_l2(const CUtensorMap *map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
 
 template <int NC>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t *r);
@@ -609,14 +605,6 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
   p.epilogue = epilogue;
   p.num_tiles = cdiv(N, SK_BM);
   p.num_kb = cdiv(K, SK_BK);
-  {
-    static int l2pf = -1;
-    if (l2pf < 0) {
-      const char *e = getenv("OCRB_L2PF");
-      l2pf = e ? atoi(e) : 0;      // default off: measured slower on B200 (profiles/r01_notes.md)
-    }
-    p.l2_prefetch = l2pf;
-  }
   p.trace = g_sk_trace;
   p.partials = (float *)workspace;
   p.flags = (int *)((char *)workspace + (size_t)SK_MAX_GRID * SK_MAXBP * 128 * sizeof(float));

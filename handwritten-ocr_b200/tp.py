@@ -72,6 +72,16 @@ class TPComm:
         self.rank = dist.get_rank(group)
         self._gather = {}
         self.n_all_reduce = 0
+        self.peer = None            # PeerAllReduce for the decode step's small messages (enable_peer_all_reduce)
+
+    def enable_peer_all_reduce(self, device, hidden: int):
+        """Replace NCCL by the one-shot peer-memory kernel for messages of <= 64 rows (needs CUDA IPC between the
+        ranks' processes on one NVLink-connected box).  OCRB_TP_NCCL=1 keeps NCCL for everything."""
+        import os
+        if os.environ.get("OCRB_TP_NCCL") == "1":
+            return None
+        self.peer = PeerAllReduce(self, device, hidden)
+        return self.peer
 
     def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
@@ -88,6 +98,69 @@ class TPComm:
         self.dist.all_gather_into_tensor(buf, local.contiguous(), group=self.group)
         full.view(B, self.world, vl).copy_(buf.view(self.world, B, vl).permute(1, 0, 2))
         return full
+
+
+class PeerAllReduce:
+    """One-shot all-reduce + residual add over NVLink peer memory for the small [B, hidden] messages of the decode
+    step (csrc/comm.cu).  Every rank allocates two partial-sum slots and a flag array, shares them through CUDA IPC
+    (handles exchanged with all_gather_object), and maps its peers'.  The row-parallel GEMM writes its partial
+    straight into the current slot; `all_reduce_residual` then does flags + reads + sum + residual in one kernel.
+    Calls alternate between the two slots, which is safe without a second barrier (see comm.cu)."""
+
+    MAX_ROWS = 64
+
+    def __init__(self, comm: "TPComm", device, hidden: int):
+        import ctypes
+        from . import _lib
+        self._ct, self._lib = ctypes, _lib
+        self.comm, self.world, self.rank = comm, comm.world, comm.rank
+        self.hidden = hidden
+        self.local = torch.zeros((2, self.MAX_ROWS, hidden), dtype=BF, device=device)
+        self.flags = torch.zeros(16 * 8, dtype=torch.int32, device=device)
+        self.seq = torch.zeros(16, dtype=torch.int32, device=device)
+        torch.cuda.synchronize()
+
+        def handle(t):
+            h = ctypes.create_string_buffer(64)
+            off = ctypes.c_int64()
+            _lib.call("ocrb_comm_ipc_handle", t.data_ptr(), h, ctypes.byref(off))
+            return (h.raw, off.value)
+
+        mine = {"data": handle(self.local), "flags": handle(self.flags)}
+        everyone = [None] * self.world
+        comm.dist.all_gather_object(everyone, mine, group=comm.group)
+        slot_bytes = self.MAX_ROWS * hidden * 2
+        data_base, flag_ptr = [], []
+        for r, item in enumerate(everyone):
+            if r == self.rank:
+                data_base.append(self.local.data_ptr())
+                flag_ptr.append(self.flags.data_ptr())
+                continue
+            out = []
+            for key in ("data", "flags"):
+                raw, off = item[key]
+                p = ctypes.c_void_p()
+                _lib.call("ocrb_comm_ipc_open", ctypes.create_string_buffer(raw, 64), off, ctypes.byref(p))
+                out.append(p.value)
+            data_base.append(out[0])
+            flag_ptr.append(out[1])
+        arr = ctypes.c_void_p * self.world
+        self._data_ptrs = [arr(*[b + s * slot_bytes for b in data_base]) for s in range(2)]
+        self._flag_ptrs = arr(*flag_ptr)
+        self.calls = 0
+        comm.dist.barrier(group=comm.group)          # nobody launches before every mapping exists
+
+    def next_slot(self) -> int:
+        s = self.calls & 1
+        self.calls += 1
+        return s
+
+    def all_reduce_residual(self, x: torch.Tensor, rows: int, slot: int) -> torch.Tensor:
+        """x[rows, hidden] += sum over ranks of local[slot][:rows] (every rank's own partial in its slot)."""
+        self._lib.call("ocrb_allreduce_residual_bf16", x.data_ptr(), x.stride(0), self._data_ptrs[slot], self._flag_ptrs,
+                       self.world, self.rank, self.seq.data_ptr(), rows, self.hidden, self.hidden,
+                       torch.cuda.current_stream().cuda_stream)
+        return x
 
 
 def random_weights_tp(cfg: VLMConfig, device, rank: int, world: int, seed: int = 0, **kw):

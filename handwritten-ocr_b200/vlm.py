@@ -399,6 +399,13 @@ class Decoder:
         products are summed over ranks (NCCL all-reduce over NVLink), then the residual is added."""
         if self.tp is None:
             return linear_small_or_big(X, W, h, residual=h, epilogue=EPI_RESIDUAL)
+        peer = getattr(self.tp, "peer", None)
+        if peer is not None and X.shape[0] <= peer.MAX_ROWS:
+            # decode: the GEMM writes its partial into the peer-mapped slot, one kernel does all-reduce + residual
+            slot = peer.next_slot()
+            linear_small_or_big(X, W, peer.local[slot][: X.shape[0]])
+            self.tp.n_all_reduce += 1
+            return peer.all_reduce_residual(h, X.shape[0], slot)
         key = (X.shape[0], h.shape[1])
         tmp = self._tp_tmp.get(key)
         if tmp is None:

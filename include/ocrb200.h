@@ -199,6 +199,21 @@ int ocrb_rows_copy(const void *src, int64_t lds, const int32_t *src_idx, void *d
 int ocrb_residual_add_bf16(void *x, int64_t ldx, const void *y, int64_t ldy, int32_t rows, int32_t dim,
                            void *stream);
 
+/* ───────────── tensor-parallel collectives over NVLink peer memory (BASELINE configs[4]) ─────────────
+ * ocrb_comm_ipc_handle / ocrb_comm_ipc_open: CUDA-IPC plumbing so that every rank (one process per GPU) can map the
+ * other ranks' partial-sum buffers and flag arrays; handle64 is a 64-byte cudaIpcMemHandle_t, `offset` the position of
+ * `ptr` inside its allocation.
+ * ocrb_allreduce_residual_bf16: x[rows, dim] += bf16(sum_r partial_r[rows, dim]) in ONE kernel per rank: remote flag
+ * stores announce the partial, peers' partials are read directly over NVLink and added in rank order (bit-identical on
+ * all ranks).  data_ptrs / flag_ptrs: host arrays of `world` device pointers (this GPU's mappings); flags int32 [16][8]
+ * and seq int32 [16] zero-initialised once.  Replaces ncclAllReduce + residual add after the row-parallel o_proj /
+ * down_proj GEMMs of the decode step (HF configuration_qwen2_5_vl.py:90-98 "rowwise"). */
+int ocrb_comm_ipc_handle(const void *ptr, void *handle64, int64_t *offset);
+int ocrb_comm_ipc_open(const void *handle64, int64_t offset, void **ptr);
+int ocrb_allreduce_residual_bf16(void *x, int64_t ldx, const void *const *data_ptrs, void *const *flag_ptrs,
+                                 int32_t world, int32_t rank, int32_t *seq, int32_t rows, int32_t dim,
+                                 int64_t ld_part, void *stream);
+
 /* Per-step mRoPE tables for decode: pos[b] = ctx_len[b] + rope_delta[b]; writes bf16 cos/sin [B, hd]
  * (all three mrope sections share the position for text tokens). inv_freq: fp32[hd/2]. */
 int ocrb_decode_rope_table(const int32_t *ctx_len, const int32_t *rope_delta, const float *inv_freq,

@@ -23,6 +23,7 @@ cfg = VLMConfig.tiny() if args.tiny else VLMConfig.qwen72b()
 t0 = time.time()
 w, lcfg = tp.random_weights_tp(cfg, dev, rank, world, seed=0)
 comm = tp.TPComm()
+comm.enable_peer_all_reduce(dev, cfg.text.hidden)
 eng = engine.OcrEngine(w, max_batch=args.batch, max_new_tokens=args.new_tokens, max_prompt=1600, tp=comm)
 pages = preprocess.to_device([synth.page(i)[:, :, 1].copy() for i in range(args.batch)])   # gray candidates of B pages
 torch.cuda.synchronize(); dist.barrier()
@@ -50,7 +51,7 @@ if rank == 0:
                       "read_wall_s": round(float(t[1]), 3), "vision_ms": round(tm["vision_ms"], 1), "prefill_ms": round(tm["prefill_ms"], 1),
                       "weight_bytes_per_rank_per_step": wbytes, "hbm_gbs_per_rank": round(alg / (float(t[0]) * 1e-3) / 1e9, 1),
                       "hbm_frac_of_measured_peak": round(alg / (float(t[0]) * 1e-3) / 1e9 / peak, 4),
-                      "all_reduces_per_step": 2 * lcfg.text.layers, "init_s": round(t_init, 1), "tokens_generated": [len(x) for x in toks]}))
+                      "all_reduces_per_step": 2 * lcfg.text.layers, "all_reduce": "nccl" if comm.peer is None else "one-shot peer-memory kernel", "init_s": round(t_init, 1), "tokens_generated": [len(x) for x in toks]}))
 sys.stdout.flush()
 eng.close()
 dist.barrier()

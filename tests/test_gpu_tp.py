@@ -25,6 +25,36 @@ def _worker(rank, world, port, q):
     sd = vlm.random_state_dict(cfg, dev, seed=0)
     w_local, lcfg = tp.sharded_weights_from_full(cfg, sd, rank, world)
     comm = tp.TPComm()
+    comm.enable_peer_all_reduce(dev, cfg.text.hidden)
+    # direct check of the one-shot all-reduce kernel: eager calls and CUDA-graph replays, both slots
+    peer = comm.peer
+    if peer is not None:
+        g = torch.Generator(device=dev).manual_seed(7)       # same stream of numbers on both ranks
+        parts = [torch.randn(world, 5, cfg.text.hidden, generator=g, device=dev).to(torch.bfloat16) for _ in range(4)]
+        x = torch.zeros(5, cfg.text.hidden, device=dev, dtype=torch.bfloat16)
+        want = torch.zeros_like(x)
+
+        def one(i):
+            slot = peer.next_slot()
+            peer.local[slot][:5].copy_(parts[i % 4][rank])
+            peer.all_reduce_residual(x, 5, slot)
+
+        for i in range(4):
+            one(i)
+            want = (want.float() + parts[i % 4].float().sum(0).to(torch.bfloat16).float()).to(torch.bfloat16)
+        torch.cuda.synchronize()
+        assert torch.equal(x, want), "eager one-shot all-reduce differs"
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for i in range(4):
+                one(i)
+        for _ in range(3):
+            gr.replay()
+            for i in range(4):
+                want = (want.float() + parts[i % 4].float().sum(0).to(torch.bfloat16).float()).to(torch.bfloat16)
+        torch.cuda.synchronize()
+        assert torch.equal(x, want), "graph-replayed one-shot all-reduce differs"
+        del gr
     eng = engine.OcrEngine(w_local, max_batch=4, max_new_tokens=24, max_prompt=400, tp=comm)
     pages = preprocess.to_device([synth.page(100 + i, 504, 392) for i in range(2)])
     toks, dbg = eng.read_batch(pages, max_new_tokens=24, return_debug=True)
