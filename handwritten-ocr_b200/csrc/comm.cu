@@ -31,6 +31,8 @@ __global__ void __launch_bounds__(AR_THREADS)
 allreduce_residual_kernel(ArPeers peers, int world, int rank, int *__restrict__ seq, bf16 *__restrict__ x, long long ldx,
                           int rows, int dim, long long ld_part) {
   const int cta = blockIdx.x, tid = threadIdx.x;
+  // Launched as a normal kernel: a PDL launch (next GEMM prefetching during the exchange) measured no faster at TP-2
+  // and made the 2-rank tiny-config test hang (profiles/r01_notes.md).
   __shared__ int s_k;
   if (tid == 0) s_k = seq[cta] + 1;
   __syncthreads();
