@@ -1,0 +1,65 @@
+"""Parity at the BASELINE dimensions: the 7B-class config, one full-size 1024x768 synthetic page, the
+reference's preprocessing strategy 1, against HF transformers (`Qwen2_5_VLForConditionalGeneration`, the class the
+reference's AutoModelForImageTextToText resolves to -- tools.py:705-709) on the same GPU with the same random-init
+state dict.  Tolerances (60 bf16 layers deep, different summation order than cuBLAS / SDPA): prefill logits within 6 % of
+the oracle's max |logit| on the worst of the 152 064 entries, RMS error below 2 % of the RMS logit, cosine >= 0.999;
+greedy tokens identical up to the first step whose ORACLE top-1/top-2 margin is below the tolerance."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+TOL_REL = 0.06
+
+
+@pytest.mark.parametrize("lm_head_std", [0.5])
+def test_7b_read_matches_hf(pkg, synth, lm_head_std):
+    from transformers import Qwen2_5_VLForConditionalGeneration, initialization
+    from handwritten_ocr_b200 import engine, preprocess, vlm
+    from handwritten_ocr_b200.vlm_config import VLMConfig
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~40 GB of device memory")
+    dev = torch.device("cuda")
+    cfg = VLMConfig.olmocr_7b()
+    sd = vlm.random_state_dict(cfg, dev, seed=0, lm_head_std=lm_head_std)
+    with torch.device("cuda"), initialization.no_init_weights():
+        hf = Qwen2_5_VLForConditionalGeneration._from_config(cfg.to_hf(), dtype=BF).eval()
+    hf.load_state_dict(sd, strict=True)
+    w = vlm.VLMWeights.from_state_dict(cfg, sd)
+    del sd
+    n_new = 24
+    eng = engine.OcrEngine(w, max_batch=3, max_new_tokens=n_new, max_prompt=1600)
+    page = preprocess.to_device(synth.page(0))                                   # 768 x 1024 RGB
+    cand = preprocess.apply_strategy(page, ["high_contrast", "binarize"])        # what run_ocr would be given
+    pv, (gh, gw) = preprocess.pixel_values(cand, dtype=torch.float32)
+    assert pv.shape == (3996, 1176) and (gh, gw) == (54, 74)                     # 3 996 patches -> 999 tokens
+    plan = eng._plan((gh, gw), 1)
+    ids, pos3, delta = eng.build_inputs(plan, "Extract and return all the text from this handwritten document.")
+    t = torch.from_numpy(ids.astype(np.int64))[None].cuda()
+    inp = dict(input_ids=t, attention_mask=torch.ones_like(t), pixel_values=pv,
+               image_grid_thw=torch.tensor([[1, gh, gw]], device="cuda"), mm_token_type_ids=(t == 151655).int())
+    with torch.no_grad():
+        gen = hf.generate(**inp, max_new_tokens=n_new, do_sample=False, output_scores=True, return_dict_in_generate=True)
+    want = gen.sequences[0, t.shape[1]:].tolist()
+    # our read: the same candidate alone and inside a batch of three (batch invariance at full size)
+    toks, dbg = eng.read_batch(cand, max_new_tokens=n_new, return_debug=True)
+    got = toks[0]
+    l0 = gen.scores[0][0].float()
+    mine = dbg["prefill_logits"][0].float()
+    rel = ((mine - l0).abs().max() / l0.abs().max()).item()
+    cos = torch.nn.functional.cosine_similarity(mine, l0, dim=0).item()
+    rms = ((mine - l0).pow(2).mean().sqrt() / l0.pow(2).mean().sqrt()).item()
+    print(f"7B prefill logits: max rel err {rel:.4f}, rms rel err {rms:.4f}, cosine {cos:.6f}, prompt {t.shape[1]} tokens")
+    assert rel < TOL_REL and rms < 0.02 and cos > 0.999
+    first_diff = next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), None)
+    if first_diff is not None:
+        sc = gen.scores[first_diff][0].float()
+        top2 = torch.topk(sc, 2).values
+        margin, tol = (top2[0] - top2[1]).item(), TOL_REL * sc.abs().max().item()
+        print(f"7B greedy: first divergence at step {first_diff} of {n_new}: oracle margin {margin:.4f}, tolerance {tol:.4f}")
+        assert margin <= tol, f"token flip at step {first_diff} with oracle margin {margin} > tolerance {tol}"
+    else:
+        print(f"7B greedy: all {n_new} tokens identical to HF generate")
+    batch = eng.read_batch(torch.cat([cand, cand.flip(1), cand]), max_new_tokens=n_new)
+    assert batch[0] == got and batch[2] == got, "a candidate read in a batch of 3 must give the tokens it gives alone"
