@@ -63,3 +63,16 @@ def test_7b_read_matches_hf(pkg, synth, lm_head_std):
         print(f"7B greedy: all {n_new} tokens identical to HF generate")
     batch = eng.read_batch(torch.cat([cand, cand.flip(1), cand]), max_new_tokens=n_new)
     assert batch[0] == got and batch[2] == got, "a candidate read in a batch of 3 must give the tokens it gives alone"
+    # context for the tolerance: how far is HF's own bf16 result from the same model evaluated in fp32?
+    del eng, w
+    torch.cuda.empty_cache()
+    hf.float()
+    with torch.no_grad():
+        l32 = hf(**inp).logits[0, -1].float()
+
+    def rms_rel(a, b):
+        return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+
+    e_hf, e_us = rms_rel(l0, l32), rms_rel(mine, l32)
+    print(f"7B prefill logits vs the fp32 model: HF bf16 rms rel err {e_hf:.4f}, this repo {e_us:.4f}")
+    assert e_us < 2.0 * e_hf + 0.01, "our bf16 path is much further from the fp32 model than HF's bf16 path"
