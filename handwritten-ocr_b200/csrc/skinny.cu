@@ -615,6 +615,14 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
   int grid = sm_count();
   if (grid > SK_MAX_GRID) grid = SK_MAX_GRID;
   if (total / 4 < grid) grid = (int)(total / 4 > 1 ? total / 4 : 1);
+  {
+    static int grid_override = -1;          // experiments only (scripts/exp): OCRB_SK_GRID
+    if (grid_override < 0) {
+      const char *e = getenv("OCRB_SK_GRID");
+      grid_override = e ? atoi(e) : 0;
+    }
+    if (grid_override > 0 && grid_override < grid) grid = grid_override;
+  }
   CUtensorMap mw;
   int rc = make_tensor_map_bf16(&mw, W, N, K, ldw, SK_BM);
   if (rc) return rc;
