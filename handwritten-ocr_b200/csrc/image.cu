@@ -233,8 +233,8 @@ __device__ __forceinline__ long long cross3(int ox, int oy, int ax, int ay, int 
 }
 
 // (b) one CTA per image: monotone-chain hull of the <= 2H extent points (thread 0; the points are
-// already sorted: x = row ascending, y = min col then max col), then every hull edge in parallel:
-// fp32 projections in the pinned order, first-minimum area, angle by atan2 in double, rotation matrix.
+// already sorted: x = row ascending, y = min col then max col), then OpenCV's float32 rotating calipers
+// restated step by step (bit-equal angle), atan2 in double, rotation matrix.
 // The reference hands (row, col) to minAreaRect as (x, y) (tools.py:557-560).
 __global__ void __launch_bounds__(256)
 deskew_angle_kernel(const int32_t *__restrict__ ext, int H, int W, double *__restrict__ out_angle,
@@ -244,8 +244,6 @@ deskew_angle_kernel(const int32_t *__restrict__ ext, int H, int W, double *__res
   int32_t *pts = hull_ws + (size_t)img * (4 * H + 8) * 2;  // [2H+4][2] candidate points
   int32_t *hull = pts + (2 * H + 4) * 2;                   // [2H+4][2] hull
   __shared__ int s_np, s_nh, s_total;
-  __shared__ float s_area[256];
-  __shared__ int s_idx[256];
   if (threadIdx.x == 0) {
     int total = 0, np = 0;
     for (int y = 0; y < H; ++y) {
@@ -289,61 +287,82 @@ deskew_angle_kernel(const int32_t *__restrict__ ext, int H, int W, double *__res
     }
     return;
   }
-  float best_area = INFINITY;
-  int best_i = 0x7fffffff;
-  for (int i = threadIdx.x; i < nh; i += 256) {
-    const int j = (i + 1 == nh) ? 0 : i + 1;
-    const float vx = __fsub_rn((float)hull[2 * j], (float)hull[2 * i]);
-    const float vy = __fsub_rn((float)hull[2 * j + 1], (float)hull[2 * i + 1]);
-    const double nrm = sqrt(__dadd_rn(__dmul_rn((double)vx, (double)vx), __dmul_rn((double)vy, (double)vy)));
-    const float inv = (float)(1.0 / nrm);
-    const float lx = __fmul_rn(vx, inv), ly = __fmul_rn(vy, inv);
-    float amin = INFINITY, amax = -INFINITY, bmin = INFINITY, bmax = -INFINITY;
-    for (int q = 0; q < nh; ++q) {
-      const float px = (float)hull[2 * q], py = (float)hull[2 * q + 1];
-      const float a = __fadd_rn(__fmul_rn(px, lx), __fmul_rn(py, ly));
-      const float b = __fadd_rn(-__fmul_rn(px, ly), __fmul_rn(py, lx));
-      amin = fminf(amin, a); amax = fmaxf(amax, a);
-      bmin = fminf(bmin, b); bmax = fmaxf(bmax, b);
-    }
-    const float w = __fsub_rn(amax, amin), h = __fsub_rn(bmax, bmin);
-    const float area = __fmul_rn(w, h);
-    if (area < best_area) { best_area = area; best_i = i; }
-  }
-  s_area[threadIdx.x] = best_area;
-  s_idx[threadIdx.x] = best_i;
-  __syncthreads();
   if (threadIdx.x == 0) {
-    float ba = INFINITY; int bi = 0x7fffffff;
-    for (int t = 0; t < 256; ++t)
-      if (s_area[t] < ba || (s_area[t] == ba && s_idx[t] < bi)) { ba = s_area[t]; bi = s_idx[t]; }
-    // recompute the winning edge's frame
-    const int i = bi, j = (i + 1 == nh) ? 0 : i + 1;
-    const float vx = __fsub_rn((float)hull[2 * j], (float)hull[2 * i]);
-    const float vy = __fsub_rn((float)hull[2 * j + 1], (float)hull[2 * i + 1]);
-    const double nrm = sqrt(__dadd_rn(__dmul_rn((double)vx, (double)vx), __dmul_rn((double)vy, (double)vy)));
-    const float inv = (float)(1.0 / nrm);
-    const float lx = __fmul_rn(vx, inv), ly = __fmul_rn(vy, inv);
-    float amin = INFINITY, amax = -INFINITY, bmin = INFINITY, bmax = -INFINITY;
-    for (int q = 0; q < nh; ++q) {
-      const float px = (float)hull[2 * q], py = (float)hull[2 * q + 1];
-      const float a = __fadd_rn(__fmul_rn(px, lx), __fmul_rn(py, ly));
-      const float b = __fadd_rn(-__fmul_rn(px, ly), __fmul_rn(py, lx));
-      amin = fminf(amin, a); amax = fmaxf(amax, a);
-      bmin = fminf(bmin, b); bmax = fmaxf(bmax, b);
+    // ---- cv::minAreaRect (OpenCV 4.13) restated: hull in cv2.convexHull(clockwise=false) order (same vertices as the
+    // monotone chain, starting at the vertex with the largest x, ties -> largest y), then rotatingCalipers in float32
+    // with every operation rounded separately; the advancing caliper is chosen by exact cross products between the four
+    // candidate edges rotated into one frame (firstVecIsRight); `area <= minarea` keeps the LAST minimum.  Sequential
+    // by nature (each step depends on the previous caliper state); the hull has a few dozen vertices.
+    int start = 0;
+    for (int i = 1; i < nh; ++i)
+      if (hull[2 * i] > hull[2 * start] || (hull[2 * i] == hull[2 * start] && hull[2 * i + 1] > hull[2 * start + 1])) start = i;
+    auto PX = [&](int i) { int q = start + i; if (q >= nh) q -= nh; return (float)hull[2 * q]; };
+    auto PY = [&](int i) { int q = start + i; if (q >= nh) q -= nh; return (float)hull[2 * q + 1]; };
+    auto VX = [&](int i) { return __fsub_rn(PX(i + 1 == nh ? 0 : i + 1), PX(i)); };   // exact: small integers
+    auto VY = [&](int i) { return __fsub_rn(PY(i + 1 == nh ? 0 : i + 1), PY(i)); };
+    auto INV = [&](int i) {
+      const double dx = (double)VX(i), dy = (double)VY(i);
+      return (float)(1.0 / sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+    };
+    int left = 0, bottom = 0, right = 0, top = 0;
+    float left_x = PX(0), right_x = PX(0), top_y = PY(0), bottom_y = PY(0);
+    for (int i = 0; i < nh; ++i) {
+      const float x = PX(i), y = PY(i);
+      if (x < left_x) { left_x = x; left = i; }
+      if (x > right_x) { right_x = x; right = i; }
+      if (y > top_y) { top_y = y; top = i; }
+      if (y < bottom_y) { bottom_y = y; bottom = i; }
     }
-    const float w = __fsub_rn(amax, amin), h = __fsub_rn(bmax, bmin);
-    float cx[4], cy[4];
-    cx[0] = __fmul_rn(lx, w);  cy[0] = __fmul_rn(ly, w);
-    cx[1] = __fmul_rn(-ly, h); cy[1] = __fmul_rn(lx, h);
-    cx[2] = -cx[0]; cy[2] = -cy[0];
-    cx[3] = -cx[1]; cy[3] = -cy[1];
+    float orientation = 0.f;
+    {
+      double ax = (double)VX(nh - 1), ay = (double)VY(nh - 1);
+      for (int i = 0; i < nh; ++i) {
+        const double bx = (double)VX(i), by = (double)VY(i);
+        const double convexity = __dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx));
+        if (convexity != 0.0) { orientation = convexity > 0.0 ? 1.f : -1.f; break; }
+        ax = bx; ay = by;
+      }
+    }
+    float base_a = orientation, base_b = 0.f;
+    int seq[4] = {bottom, right, top, left};
+    float minarea = 3.402823466e+38f;
+    float bA = 1.f, bB = 0.f, bW = 0.f, bH = 0.f;
+    for (int k = 0; k < nh; ++k) {
+      // candidate edges rotated into the frame of caliper 0: identity, 90 CW, 180, 90 CCW
+      long long rx[4], ry[4];
+      rx[0] = (long long)VX(seq[0]);  ry[0] = (long long)VY(seq[0]);
+      rx[1] = (long long)VY(seq[1]);  ry[1] = -(long long)VX(seq[1]);
+      rx[2] = -(long long)VX(seq[2]); ry[2] = -(long long)VY(seq[2]);
+      rx[3] = -(long long)VY(seq[3]); ry[3] = (long long)VX(seq[3]);
+      int main_el = 0;
+      for (int i = 1; i < 4; ++i)
+        if (ry[i] * rx[main_el] - rx[i] * ry[main_el] < 0) main_el = i;     // rotate90CW(v_i) . v_main < 0
+      const int pindex = seq[main_el];
+      const float inv = INV(pindex);
+      const float lead_x = __fmul_rn(VX(pindex), inv), lead_y = __fmul_rn(VY(pindex), inv);
+      switch (main_el) {
+        case 0: base_a = lead_x;  base_b = lead_y;  break;
+        case 1: base_a = lead_y;  base_b = -lead_x; break;
+        case 2: base_a = -lead_x; base_b = -lead_y; break;
+        default: base_a = -lead_y; base_b = lead_x; break;
+      }
+      seq[main_el] = (seq[main_el] + 1 == nh) ? 0 : seq[main_el] + 1;
+      float dx = __fsub_rn(PX(seq[1]), PX(seq[3])), dy = __fsub_rn(PY(seq[1]), PY(seq[3]));
+      const float width = __fadd_rn(__fmul_rn(dx, base_a), __fmul_rn(dy, base_b));
+      dx = __fsub_rn(PX(seq[2]), PX(seq[0]));
+      dy = __fsub_rn(PY(seq[2]), PY(seq[0]));
+      const float height = __fadd_rn(__fmul_rn(-dx, base_b), __fmul_rn(dy, base_a));
+      const float area = __fmul_rn(width, height);
+      if (area <= minarea) { minarea = area; bA = base_a; bW = width; bB = base_b; bH = height; }
+    }
+    (void)bH;
+    // side vector out[1] = (A1 * width, B1 * width), turned by exact quarter turns into [-pi/2, 0)
     const double PI = 3.14159265358979323846;
-    float ang = -90.0f;
-    for (int q = 0; q < 4; ++q) {
-      const double a = atan2((double)cy[q], (double)cx[q]);
-      if (a >= -PI / 2 && a < 0.0) { ang = (float)(a * 180.0 / PI); break; }
-    }
+    double x = (double)__fmul_rn(bA, bW), y = (double)__fmul_rn(bB, bW);
+    double r = atan2(y, x);
+    for (int it = 0; it < 4 && r >= 0.0; ++it) { const double t = x; x = y; y = -t; r = atan2(y, x); }
+    for (int it = 0; it < 4 && r < -PI / 2; ++it) { const double t = x; x = -y; y = t; r = atan2(y, x); }
+    const float ang = (float)(r * 180.0 / PI);
     double angle = (double)ang;
     if (angle < -45.0) angle = -(90.0 + angle);
     else angle = -angle;

@@ -122,7 +122,7 @@ def test_small_deskew_golden(pp, image_small, name):
         assert np.isnan(ang)
         assert np.array_equal(pp.deskew(x)[0].cpu().numpy(), arr)
         return
-    assert abs(np.float32(ang) - np.float32(ref_ang)) <= 4 * np.spacing(np.float32(abs(ref_ang) + 90.0))
+    assert ang == ref_ang, "deskew angle must be bit-equal to cv2.minAreaRect's (golden, from the reference)"
     # warp is bit-exact given the reference's angle
     Mref = torch.from_numpy(R.rotation_matrix(arr.shape[1] // 2, arr.shape[0] // 2, ref_ang).reshape(1, 6))
     out = pp.warp_affine(x, Mref)[0].cpu().numpy()
@@ -140,19 +140,41 @@ def test_full_page_hashes(pp, synth, image_hashes, seed):
     for step in ["high_contrast", "binarize", "sharpen"]:
         assert sha(pp.apply_transform(x, step)[0].cpu().numpy()) == ent[step], step
     ang, M = pp.deskew_angle(x)
-    exact_angle = float(ang[0].cpu()) == ent["angle"]
+    assert float(ang[0].cpu()) == ent["angle"], "deskew angle must be bit-equal to the reference's"
     Mref = torch.from_numpy(R.rotation_matrix(ent["w"] // 2, ent["h"] // 2, ent["angle"]).reshape(1, 6))
     assert sha(pp.warp_affine(x, Mref)[0].cpu().numpy()) == ent["deskew"]
     for ch in CHAINS:
         out = pp.apply_strategy(x, ch.split("+"))
-        if "deskew" in ch and not exact_angle:
-            continue  # angle within 2 ulp but not bit-equal on this page: reported, not asserted
         assert sha(out[0].cpu().numpy()) == ent[ch], ch
         pv, (gh, gw) = pp.pixel_values(out, dtype=torch.float32)
         assert [1, gh, gw] == ent[f"grid:{ch}"][0]
         assert sha(pv.cpu().numpy()) == ent[f"pv:{ch}"], ch
     pv, (gh, gw) = pp.pixel_values(x, dtype=torch.float32)
     assert sha(pv.cpu().numpy()) == ent["pv:original"]
+
+
+def test_deskew_angle_vs_cv2_many_pages(pp, synth):
+    """The rotating-calipers restatement against the installed cv2 (the wheel the reference calls) on 120 pages,
+    both orientations, odd sizes and ruled paper: bit-equal angles (skipped where cv2 is not installed)."""
+    cv2 = pytest.importorskip("cv2")
+    pages = []
+    for seed in range(120):
+        if seed < 80:
+            pages.append(synth.page(500 + seed, 1024, 768) if seed % 2 == 0 else synth.page(500 + seed, 768, 1024))
+        else:
+            pages.append(synth.page(500 + seed, 504 + (seed % 7) * 13, 392 + (seed % 5) * 11, ruled=(seed % 3 == 0)))
+    bad = []
+    for i, page in enumerate(pages):
+        gray = cv2.cvtColor(page, cv2.COLOR_RGB2GRAY)
+        coords = np.column_stack(np.where(gray < 128))
+        if len(coords) <= 100:
+            continue
+        a = cv2.minAreaRect(coords)[-1]
+        want = float(-(90 + a) if a < -45 else -a)
+        ang, _ = pp.deskew_angle(pp.to_device(page))
+        if float(ang[0].cpu()) != want:
+            bad.append((i, want, float(ang[0].cpu())))
+    assert not bad, f"{len(bad)} of {len(pages)} angles differ from cv2: {bad[:3]}"
 
 
 def test_pixel_values_resize_paths(pp, synth, image_hashes):
