@@ -13,13 +13,17 @@
 //     so a 3584x3584 o_proj (28 tiles) fills the machine as evenly as the 152064-row lm_head.  A span that
 //     does not finish its tile publishes an fp32 partial; the CTA that finishes the tile adds the partials in
 //     k order (deterministic, independent of B => batch-invariant results);
-//   * activations: 4 producer warps write the X k-slices into the ring in the UMMA swizzled layout,
-//     optionally applying HF's RMSNorm on the fly (modeling_qwen2_5_vl.py:66-71: fp32 normalise -> bf16 ->
-//     bf16 multiply by the weight), so no separate norm kernel / launch sits in front of qkv, gate-up, lm_head;
-//   * epilogue warps: tcgen05.ld -> bias -> bf16 round -> residual / SwiGLU / GELU with HF's rounding points.
+//   * activations: TMA boxes of X itself ([BP rows x 64], rows >= B zero-filled by the hardware), issued after
+//     griddepcontrol.wait.  With an RMSNorm in front (qkv, gate/up, lm_head) the B rows are normalised ONCE by
+//     skinny_norm_rows_kernel (HF rounding, modeling_qwen2_5_vl.py:66-71) into a scratch buffer and read from there:
+//     fusing the norm into the GEMM (every CTA re-normalising the k-slices of every tile it streams, through producer
+//     warps writing the UMMA swizzled layout) was built and measured slower -- 3.58 vs 3.41 ms per decode step at B = 3,
+//     and 2.5x slower at B = 64 (profiles/r01_notes.md);
+//   * epilogue warps: tcgen05.ld (only the live accumulator columns, 16 at a time) -> bias -> bf16 round -> residual /
+//     SwiGLU / GELU with HF's rounding points.
 //
-// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue (TMEM lane
-// quadrant = warp % 4), 6..9 = activation producers.
+// Warp roles (192 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue (TMEM lane quadrant =
+// warp % 4).
 #include "tc_common.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -32,10 +36,10 @@ constexpr int SK_BK = 64;           // k-block: 64 bf16 = one 128-byte swizzle r
 #define SK_STAGES_N 5
 #endif
 constexpr int SK_STAGES = SK_STAGES_N;           // 5 x 18 KiB (BP=16): two CTAs of consecutive kernels fit one SM under PDL
-constexpr int SK_PF = 4;             // activation prefetch distance (units)
-constexpr int SK_THREADS = 320;
+constexpr int SK_THREADS = 192;
 constexpr int SK_MAX_GRID = 296;    // workspace slots (2 x 148)
 constexpr int SK_MAXBP = 64;
+constexpr int SK_MAX_NORM_K = 32768;  // widest row the B > 16 RMSNorm scratch holds
 constexpr uint32_t SK_W_BYTES = SK_BM * SK_BK * 2;   // 16 KiB
 
 struct SkinnyParams {
@@ -200,26 +204,51 @@ __device__ __forceinline__ void sk_row_rstd(const SkinnyParams &p, int w8, int l
   }
 }
 
+// RMSNorm of the B activation rows into a scratch buffer, for B > 16: above that the fused producers (every CTA
+// re-normalising the k-slices of every tile it streams) cost more than the weights' HBM time, so the rows are
+// normalised once and the GEMM reads them through TMA like any un-normed input.  Same statistics routine as the fused
+// path (sk_row_rstd: one warp per row, same summation order), so a row gets the same bits whatever B is.
+__global__ void __launch_bounds__(256)
+skinny_norm_rows_kernel(SkinnyParams p, bf16 *__restrict__ xn) {
+  __shared__ float s_rstd[SK_MAXBP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  sk_row_rstd(p, warp, lane, s_rstd);          // rows warp, warp + 8, ...
+  __syncthreads();
+  const int kvec = p.K >> 3;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.B * kvec; i += gridDim.x * 256) {
+    const int b = i / kvec, v = i - b * kvec;
+    float f[8], wf[8];
+    unpack8f(*reinterpret_cast<const uint4 *>(p.X + (size_t)b * p.ldx + v * 8), f);
+    unpack8f(*reinterpret_cast<const uint4 *>(p.norm_w + v * 8), wf);
+    const float rs = s_rstd[b];
+    uint4 o;
+    bf16 *oe = reinterpret_cast<bf16 *>(&o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) oe[e] = __float2bfloat16_rn(wf[e] * bf16_round(f[e] * rs));
+    *reinterpret_cast<uint4 *>(xn + (size_t)b * p.K + v * 8) = o;
+  }
+}
+
 // BP = MMA N (activation rows staged per k-block: 16/32/64); BC = accumulator columns the epilogue actually reads,
 // publishes and stores (4/8/16/32/64 >= B): with B = 3 sequences the fix-up moves 4 columns, not 16.
 template <int BP, int BC>
-__global__ void __launch_bounds__(SK_THREADS, (BP <= 16) ? 2 : 1)
+__global__ void __launch_bounds__(SK_THREADS, 2)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, SkinnyParams p) {
+  constexpr int ST = (BP >= 64) ? 4 : SK_STAGES;   // ring depth: 4 x 24 KiB at BP = 64 keeps two CTAs per SM
   constexpr uint32_t X_BYTES = BP * SK_BK * 2;
   constexpr uint32_t STAGE_BYTES = SK_W_BYTES + X_BYTES;
   constexpr int TMEM_COLS = (2 * BP < 32) ? 32 : 2 * BP;
   extern __shared__ uint8_t sk_smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sk_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t *full_w = reinterpret_cast<uint64_t *>(smem + SK_STAGES * STAGE_BYTES);
-  uint64_t *full_x = full_w + SK_STAGES;
-  uint64_t *empty = full_x + SK_STAGES;
-  uint64_t *tmem_full = empty + SK_STAGES;     // [2]
+  uint64_t *full_w = reinterpret_cast<uint64_t *>(smem + ST * STAGE_BYTES);
+  uint64_t *full_x = full_w + ST;
+  uint64_t *empty = full_x + ST;
+  uint64_t *tmem_full = empty + ST;     // [2]
   uint64_t *tmem_empty = tmem_full + 2;        // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-  float *s_rstd = reinterpret_cast<float *>(tmem_slot + 2);        // [BP]
-  float *s_part = s_rstd + SK_MAXBP;                               // [4 warps][BP]
-  float *s_up = s_part + 4 * SK_MAXBP;                             // [64][BP] SwiGLU exchange
-  volatile int *s_flag = reinterpret_cast<volatile int *>(s_up + 64 * BP);
+  float *s_up = reinterpret_cast<float *>(tmem_slot + 2);          // [64][CC] SwiGLU exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) sk_stamp(p, 0);            // CTA start
@@ -232,9 +261,9 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-    for (int s = 0; s < SK_STAGES; ++s) {
+    for (int s = 0; s < ST; ++s) {
       mbar_init(&full_w[s], 1);
-      mbar_init(&full_x[s], p.norm_w ? 4 : 1);   // norm: one arrival per producer warp; else the TMA transaction
+      mbar_init(&full_x[s], 1);                  // activation k-slice: one TMA transaction
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -263,17 +292,16 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     if (lane == 0) {
       uint64_t policy;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      const bool x_by_tma = (p.norm_w == nullptr);
       SkCursor cur, xc;
       cur.init(sp);
       xc = cur;
-      const int head = n_units < SK_STAGES ? n_units : SK_STAGES;
+      const int head = n_units < ST ? n_units : ST;
       for (int it = 0; it < head; ++it) {           // first pass over the ring: slots are free, weights only
         mbar_expect_tx(&full_w[it], SK_W_BYTES);
         tma_load_2d_hint(smem + it * STAGE_BYTES, &map_w, &full_w[it], cur.kb * SK_BK, cur.tile * SK_BM, policy);
         cur.advance(sp);
       }
-      if (x_by_tma) {
+      {
         pdl_wait();
         for (int it = 0; it < head; ++it) {
           mbar_expect_tx(&full_x[it], X_BYTES);
@@ -281,18 +309,18 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           xc.advance(sp);
         }
       }
-      int s = head == SK_STAGES ? 0 : head;
-      uint32_t ph = head == SK_STAGES ? 1 : 0;
+      int s = head == ST ? 0 : head;
+      uint32_t ph = head == ST ? 1 : 0;
       for (int it = head; it < n_units; ++it) {
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full_w[s], SK_W_BYTES);
         tma_load_2d_hint(smem + s * STAGE_BYTES, &map_w, &full_w[s], cur.kb * SK_BK, cur.tile * SK_BM, policy);
-        if (x_by_tma) {
+        {
           mbar_expect_tx(&full_x[s], X_BYTES);
           tma_load_2d(smem + s * STAGE_BYTES + SK_W_BYTES, &map_x, &full_x[s], cur.kb * SK_BK, 0);
         }
         cur.advance(sp);
-        if (++s == SK_STAGES) { s = 0; ph ^= 1; }
+        if (++s == ST) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -323,95 +351,13 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           for (int k = 0; k < SK_BK / UMMA_K; ++k)
             umma_bf16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty[s]);
-          if (++s == SK_STAGES) { s = 0; ph ^= 1; }
+          if (++s == ST) { s = 0; ph ^= 1; }
         }
         umma_commit(&tmem_full[acc]);
       }
     }
-  } else if (warp >= 6) {
-    // ───────────── activation producers (128 threads): only with a fused RMSNorm ─────────────
-    if (p.norm_w != nullptr) {
-    const int t = threadIdx.x - 192;
-    const int pw = t >> 5;
-    const bool norm = p.norm_w != nullptr;
-    if (norm) {
-      sk_row_rstd(p, warp - 2, lane, s_rstd);
-      named_bar_sync(2, 256);                    // rstd[] complete (warps 2..9)
-    }            // rstd[] written by warps 2..9 (sk_row_rstd)
-    // thread -> (row r, 16-byte chunk j) of the [BP x 64] k-slice; BP/16 rows per thread.
-    // The global (L2) loads run SK_PF units ahead of their use, so the ~1 us load latency is hidden.
-    const int j = t & 7;
-    const int r0 = t >> 3;                       // 0..15
-    constexpr int Q = BP / 16;
-    uint4 xq[SK_PF][Q];
-    uint4 wq[SK_PF];
-    SkCursor fc;                                 // fetch cursor, SK_PF units ahead of the consume position
-    fc.init(sp);
-    auto fetch = [&](uint4 *xv, uint4 &wv) {
-      const int k = fc.kb * SK_BK + j * 8;
-      const bool ok = fc.valid && (k < p.K);
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const int r = r0 + q * 16;
-        xv[q] = make_uint4(0, 0, 0, 0);
-        if (ok && r < p.B) xv[q] = *reinterpret_cast<const uint4 *>(p.X + (size_t)r * p.ldx + k);
-      }
-      wv = make_uint4(0, 0, 0, 0);
-      if (norm && ok) wv = *reinterpret_cast<const uint4 *>(p.norm_w + k);
-      if (fc.valid) fc.advance(sp);
-    };
-#pragma unroll
-    for (int i = 0; i < SK_PF; ++i) fetch(xq[i], wq[i]);
-    int s = 0;
-    uint32_t ph = 0;
-    for (int ib = 0; ib < n_units; ib += SK_PF) {
-#pragma unroll
-      for (int i = 0; i < SK_PF; ++i) {
-        const int it = ib + i;
-        if (it < n_units) {
-          uint4 xv[Q];
-#pragma unroll
-          for (int q = 0; q < Q; ++q) xv[q] = xq[i][q];
-          const uint4 wv = wq[i];
-          fetch(xq[i], wq[i]);                     // refill this slot for SK_PF units later
-          if (norm) {
-            float wf[8];
-            unpack8f(wv, wf);
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-              const int r = r0 + q * 16;
-              if (r < p.B) {
-                const float rs = s_rstd[r];
-                float f[8];
-                unpack8f(xv[q], f);
-                bf16 *oe = reinterpret_cast<bf16 *>(&xv[q]);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) oe[e] = __float2bfloat16_rn(wf[e] * bf16_round(f[e] * rs));
-              }
-            }
-          }
-          mbar_wait(&empty[s], ph ^ 1);
-          uint8_t *xs = smem + s * STAGE_BYTES + SK_W_BYTES;
-#pragma unroll
-          for (int q = 0; q < Q; ++q) {
-            const int r = r0 + q * 16;
-            *reinterpret_cast<uint4 *>(xs + r * 128 + ((j ^ (r & 7)) << 4)) = xv[q];
-          }
-          fence_proxy_async_smem();              // generic-proxy stores -> visible to the tensor core (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full_x[s]);  // 4 arrivals per stage, not 128: mbarrier arrives serialise
-          if (p.trace && t == 0 && it < 12) sk_stamp(p, 40 + it);
-          if (++s == SK_STAGES) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-    }
   } else {
     // ───────────── epilogue warps 2..5 ─────────────
-    if (p.norm_w != nullptr) {
-      sk_row_rstd(p, warp - 2, lane, s_rstd);
-      named_bar_sync(2, 256);
-    }
     const int quad = warp & 3;
     const int et = quad * 32 + lane;             // TMEM lane = weight row inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -423,27 +369,33 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       if (et == 0 && seg == 0) sk_stamp(p, 5);      // first segment accumulated
       if (et == 0 && seg == n_segs - 1) sk_stamp(p, 6);   // last segment accumulated
       tcgen05_fence_after();
-      float v[BC];
-      {
-        constexpr int LC = (BC < 16) ? BC : 16;
-#pragma unroll
-        for (int c = 0; c < BC; c += LC) {
-          uint32_t r[LC];
-          tmem_ld_cols<LC>(lane_addr + acc * BP + c, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < LC; ++i) v[c + i] = __uint_as_float(r[i]);
-        }
-      }
-      tcgen05_fence_before();
-      mbar_arrive(&tmem_empty[acc]);             // accumulator drained: the MMA warp may reuse it
-
+      // The BC live accumulator columns are processed in chunks of CC <= 16, so the register footprint (and with it
+      // the two-CTAs-per-SM co-residency PDL needs) is the same for 4 and for 64 sequences.
+      constexpr int CC = (BC < 16) ? BC : 16;
       const bool finishes = (kb0 + nkb == KB);
+      const int n = tile * SK_BM + et;
+      const bool n_ok = n < p.N;
+      auto load_chunk = [&](int c0, float (&v)[CC]) {
+        uint32_t r[CC];
+        tmem_ld_cols<CC>(lane_addr + acc * BP + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < CC; ++i) v[i] = __uint_as_float(r[i]);
+        if (c0 + CC >= BC) {                         // last TMEM read of this segment: the MMA warp may reuse the buffer
+          tcgen05_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+      };
       if (!finishes) {
         // partial span: publish fp32 partials, then the flag
         float *slot = p.partials + (size_t)blockIdx.x * BC * 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BC; c0 += CC) {
+          float v[CC];
+          load_chunk(c0, v);
 #pragma unroll
-        for (int b = 0; b < BC; ++b) __stcg(slot + b * 128 + et, v[b]);
+          for (int i = 0; i < CC; ++i) __stcg(slot + (c0 + i) * 128 + et, v[i]);
+        }
         __threadfence();
         named_bar_sync(1, 128);
         if (et == 0) {
@@ -451,21 +403,17 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           sk_stamp(p, 7);                           // partial published
         }
       } else {
+        int c_first = (int)blockIdx.x;               // first contributing CTA (== blockIdx.x: none)
         if (kb0 > 0) {
-          // this CTA finishes a tile that earlier CTAs started: add their partials in k order, then ours
+          // this CTA finishes a tile that earlier CTAs started: their partials are added in k order, then ours.
+          // First contributing CTA = the one whose span contains the tile's first unit.
           const int tile_first = tile * KB;
-          // first contributing CTA: the one whose span contains unit tile_first
           const int total = p.num_tiles * KB;
           const int per = total / (int)gridDim.x, rem = total % (int)gridDim.x;
           const int big = rem * (per + 1);
-          const int c0 = (tile_first < big) ? tile_first / (per + 1) : rem + (tile_first - big) / per;
-          float sum[BC];
-#pragma unroll
-          for (int b = 0; b < BC; ++b) sum[b] = 0.f;
-          constexpr int FX = (BC <= 4) ? 8 : ((BC <= 8) ? 4 : ((BC <= 16) ? 2 : 1));   // contributors fetched together
+          c_first = (tile_first < big) ? tile_first / (per + 1) : rem + (tile_first - big) / per;
           // all contributors' flags first (one polling thread per contributor), then stream their partials
-          const int n_contrib = (int)blockIdx.x - c0;
-          for (int cb = c0; cb < (int)blockIdx.x; cb += 128) {
+          for (int cb = c_first; cb < (int)blockIdx.x; cb += 128) {
             if (cb + et < (int)blockIdx.x) {
               const int c = cb + et;
               int f;
@@ -480,59 +428,69 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             }
           }
           named_bar_sync(1, 128);
-          for (int cb = c0; cb < (int)blockIdx.x; cb += FX) {
-            const int nc = min(FX, (int)blockIdx.x - cb);
-            float pv[FX][BC];
-#pragma unroll
-            for (int i = 0; i < FX; ++i) {
-              const float *slot = p.partials + (size_t)(cb + (i < nc ? i : 0)) * BC * 128;
-#pragma unroll
-              for (int b = 0; b < BC; ++b) pv[i][b] = __ldcg(slot + b * 128 + et);
-            }
-#pragma unroll
-            for (int i = 0; i < FX; ++i)
-              if (i < nc) {
-#pragma unroll
-                for (int b = 0; b < BC; ++b) sum[b] += pv[i][b];
-              }
-          }
-          named_bar_sync(1, 128);
-          for (int c = c0 + et; c < (int)blockIdx.x; c += 128) p.flags[c] = 0;   // consumed: ready for the next launch
-          (void)n_contrib;
-#pragma unroll
-          for (int b = 0; b < BC; ++b) v[b] = sum[b] + v[b];
-          if (et == 0) sk_stamp(p, 8);              // fix-up done
         }
-        // ───── epilogue math on the complete accumulator (HF rounding points) ─────
-        const int n = tile * SK_BM + et;
-        const bool n_ok = n < p.N;
-        float bv = (p.bias && n_ok) ? __bfloat162float(p.bias[n]) : 0.f;
+        const float bv = (p.bias && n_ok) ? __bfloat162float(p.bias[n]) : 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BC; c0 += CC) {
+          float v[CC];
+          load_chunk(c0, v);
+          if (c_first < (int)blockIdx.x) {
+            float sum[CC];
 #pragma unroll
-        for (int b = 0; b < BC; ++b) v[b] = bf16_round(v[b] + bv);
-        if (p.epilogue == OCRB_EPI_SWIGLU) {
-          // tile rows 0..63 = gate, 64..127 = up of output columns tile*64 + j
-          if (et >= 64) {
+            for (int i = 0; i < CC; ++i) sum[i] = 0.f;
+            constexpr int FX = (CC <= 4) ? 8 : ((CC <= 8) ? 4 : 2);   // contributors fetched together
+            for (int cb = c_first; cb < (int)blockIdx.x; cb += FX) {
+              const int nc = min(FX, (int)blockIdx.x - cb);
+              float pv[FX][CC];
 #pragma unroll
-            for (int b = 0; b < BC; ++b) s_up[(et - 64) * BC + b] = v[b];
+              for (int j = 0; j < FX; ++j) {
+                const float *slot = p.partials + (size_t)(cb + (j < nc ? j : 0)) * BC * 128;
+#pragma unroll
+                for (int i = 0; i < CC; ++i) pv[j][i] = __ldcg(slot + (c0 + i) * 128 + et);
+              }
+#pragma unroll
+              for (int j = 0; j < FX; ++j)
+                if (j < nc) {
+#pragma unroll
+                  for (int i = 0; i < CC; ++i) sum[i] += pv[j][i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < CC; ++i) v[i] = sum[i] + v[i];
           }
-          named_bar_sync(1, 128);
-          if (et < 64 && n_ok) {
-            const int oc = tile * 64 + et;
+          // ───── epilogue math on the complete accumulator (HF rounding points) ─────
 #pragma unroll
-            for (int b = 0; b < BC; ++b)
-              if (b < p.B) p.D[(size_t)b * p.ldd + oc] = __float2bfloat16_rn(sk_silu(v[b]) * s_up[et * BC + b]);
-          }
-          named_bar_sync(1, 128);
-        } else if (n_ok) {
+          for (int i = 0; i < CC; ++i) v[i] = bf16_round(v[i] + bv);
+          if (p.epilogue == OCRB_EPI_SWIGLU) {
+            // tile rows 0..63 = gate, 64..127 = up of output columns tile*64 + j
+            if (et >= 64) {
 #pragma unroll
-          for (int b = 0; b < BC; ++b) {
-            if (b < p.B) {
-              float o = v[b];
-              if (p.epilogue == OCRB_EPI_RESIDUAL) o += __bfloat162float(p.residual[(size_t)b * p.ldr + n]);
-              else if (p.epilogue == OCRB_EPI_GELU) o = sk_gelu(o);
-              p.D[(size_t)b * p.ldd + n] = __float2bfloat16_rn(o);
+              for (int i = 0; i < CC; ++i) s_up[(et - 64) * CC + i] = v[i];
+            }
+            named_bar_sync(1, 128);
+            if (et < 64 && n_ok) {
+              const int oc = tile * 64 + et;
+#pragma unroll
+              for (int i = 0; i < CC; ++i)
+                if (c0 + i < p.B) p.D[(size_t)(c0 + i) * p.ldd + oc] = __float2bfloat16_rn(sk_silu(v[i]) * s_up[et * CC + i]);
+            }
+            named_bar_sync(1, 128);
+          } else if (n_ok) {
+#pragma unroll
+            for (int i = 0; i < CC; ++i) {
+              if (c0 + i < p.B) {
+                float o = v[i];
+                if (p.epilogue == OCRB_EPI_RESIDUAL) o += __bfloat162float(p.residual[(size_t)(c0 + i) * p.ldr + n]);
+                else if (p.epilogue == OCRB_EPI_GELU) o = sk_gelu(o);
+                p.D[(size_t)(c0 + i) * p.ldd + n] = __float2bfloat16_rn(o);
+              }
             }
           }
+        }
+        if (c_first < (int)blockIdx.x) {
+          named_bar_sync(1, 128);                    // every thread is done reading the partials
+          for (int c = c_first + et; c < (int)blockIdx.x; c += 128) p.flags[c] = 0;   // consumed: ready for the next launch
+          if (et == 0) sk_stamp(p, 8);               // fix-up done
         }
       }
     }
@@ -548,8 +506,10 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 
 template <int BP, int BC>
 static int launch_skinny(const CUtensorMap &mw, const CUtensorMap &mx, const SkinnyParams &p, int grid, cudaStream_t st) {
-  constexpr size_t smem = (size_t)SK_STAGES * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 256 /*barriers*/ +
-                          (SK_MAXBP + 4 * SK_MAXBP + 64 * BP) * sizeof(float) + 64;
+  constexpr int ST = (BP >= 64) ? 4 : SK_STAGES;
+  constexpr int CC = (BC < 16) ? BC : 16;
+  constexpr size_t smem = (size_t)ST * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 256 /*barriers*/ +
+                          64 * CC * sizeof(float) + 64;
   static bool attr_set = false;
   if (!attr_set) {
     OCRB_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<BP, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -579,7 +539,8 @@ static unsigned long long *g_sk_trace = nullptr;
 extern "C" void ocrb_skinny_set_trace(void *buf) { g_sk_trace = (unsigned long long *)buf; }
 
 extern "C" int64_t ocrb_skinny_workspace_bytes(void) {
-  return (int64_t)SK_MAX_GRID * SK_MAXBP * 128 * sizeof(float) + (int64_t)SK_MAX_GRID * sizeof(int) + 256;
+  return (int64_t)SK_MAX_GRID * SK_MAXBP * 128 * sizeof(float) + (int64_t)SK_MAX_GRID * sizeof(int) + 256 +
+         (int64_t)SK_MAXBP * SK_MAX_NORM_K * sizeof(bf16);
 }
 
 extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, int64_t ldw, void *D, int64_t ldd, int32_t B,
@@ -628,11 +589,25 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int BPsel = B <= 16 ? 16 : (B <= 32 ? 32 : 64);
-  CUtensorMap mx = mw;                              // unused by the kernel when the RMSNorm producers run
-  if (!norm_w) {
-    rc = make_tensor_map_bf16(&mx, X, B, K, ldx, BPsel);
+  if (norm_w) {
+    // normalise the rows once (same rstd routine as the fused path), then treat them as a plain input
+    OCRB_REQUIRE(K <= SK_MAX_NORM_K, "skinny_gemm_bf16: the RMSNorm prologue supports K <= 32768");
+    bf16 *xn = (bf16 *)((char *)workspace + (size_t)SK_MAX_GRID * SK_MAXBP * 128 * sizeof(float) +
+                        (size_t)SK_MAX_GRID * sizeof(int) + 256);
+    const int nblk = cdiv((long long)B * (K >> 3), 256 * 4);
+    OCRB_CUDA(launch_pdl(skinny_norm_rows_kernel, dim3(nblk < 1 ? 1 : (nblk > 64 ? 64 : nblk)), dim3(256), 0, st, p, xn));
+    rc = check_launch("skinny_norm_rows_kernel");
     if (rc) return rc;
+    p.X = xn;
+    p.ldx = K;
+    p.norm_w = nullptr;
+    X = xn;
+    ldx = K;
+    norm_w = nullptr;
   }
+  CUtensorMap mx;
+  rc = make_tensor_map_bf16(&mx, X, B, K, ldx, BPsel);
+  if (rc) return rc;
   if (B <= 4) return launch_skinny<16, 4>(mw, mx, p, grid, st);
   if (B <= 8) return launch_skinny<16, 8>(mw, mx, p, grid, st);
   if (B <= 16) return launch_skinny<16, 16>(mw, mx, p, grid, st);
