@@ -177,57 +177,99 @@ struct SkCursor {
 // HF RMSNorm statistics (modeling_qwen2_5_vl.py:66-71): rstd[b] = rsqrt(mean(x[b]^2) + eps) in fp32.  Warps 2..9
 // (256 threads) share the rows; one warp per row, up to 16 independent 16-byte loads in flight per lane, fixed
 // summation order (lane-strided partial sums, xor-shuffle tree) so the result never depends on B.
-__device__ __forceinline__ void sk_row_rstd(const SkinnyParams &p, int w8, int lane, float *s_rstd) {
-  const int kvec = p.K >> 3;
-  for (int b = w8; b < p.B; b += 8) {
-    const bf16 *xr = p.X + (size_t)b * p.ldx;
-    float ss = 0.f;
-    for (int v0 = lane; v0 < kvec; v0 += 32 * 16) {
-      uint4 raw[16];
+__device__ __forceinline__ float sk_one_row_rstd(const bf16 *xr, int K, float eps, int lane) {
+  const int kvec = K >> 3;
+  float ss = 0.f;
+  for (int v0 = lane; v0 < kvec; v0 += 32 * 16) {
+    uint4 raw[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int v = v0 + i * 32;
-        raw[i] = make_uint4(0, 0, 0, 0);
-        if (v < kvec) raw[i] = *reinterpret_cast<const uint4 *>(xr + v * 8);
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float f[8];
-        unpack8f(raw[i], f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ss = fmaf(f[k], f[k], ss);
-      }
+    for (int i = 0; i < 16; ++i) {
+      const int v = v0 + i * 32;
+      raw[i] = make_uint4(0, 0, 0, 0);
+      if (v < kvec) raw[i] = __ldcg(reinterpret_cast<const uint4 *>(xr + v * 8));
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) s_rstd[b] = rsqrtf(ss / (float)p.K + p.eps);
+    for (int i = 0; i < 16; ++i) {
+      float f[8];
+      unpack8f(raw[i], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ss = fmaf(f[k], f[k], ss);
+    }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  return rsqrtf(ss / (float)K + eps);
 }
 
 // RMSNorm of the B activation rows into a scratch buffer, for B > 16: above that the fused producers (every CTA
 // re-normalising the k-slices of every tile it streams) cost more than the weights' HBM time, so the rows are
 // normalised once and the GEMM reads them through TMA like any un-normed input.  Same statistics routine as the fused
-// path (sk_row_rstd: one warp per row, same summation order), so a row gets the same bits whatever B is.
+// path (one warp per row, fixed summation order), so a row gets the same bits whatever B is.
 __global__ void __launch_bounds__(256)
 skinny_norm_rows_kernel(SkinnyParams p, bf16 *__restrict__ xn) {
-  __shared__ float s_rstd[SK_MAXBP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) pdl_launch_dependents();
-  pdl_wait();
-  sk_row_rstd(p, warp, lane, s_rstd);          // rows warp, warp + 8, ...
-  __syncthreads();
+  const int b = blockIdx.x * 8 + warp;             // one warp per row, no block-level synchronisation
   const int kvec = p.K >> 3;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.B * kvec; i += gridDim.x * 256) {
-    const int b = i / kvec, v = i - b * kvec;
-    float f[8], wf[8];
-    unpack8f(*reinterpret_cast<const uint4 *>(p.X + (size_t)b * p.ldx + v * 8), f);
-    unpack8f(*reinterpret_cast<const uint4 *>(p.norm_w + v * 8), wf);
-    const float rs = s_rstd[b];
-    uint4 o;
-    bf16 *oe = reinterpret_cast<bf16 *>(&o);
+  // the norm weights do not depend on the predecessor: fetch the first batch before the wait
+  uint4 wraw[16];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) oe[e] = __float2bfloat16_rn(wf[e] * bf16_round(f[e] * rs));
-    *reinterpret_cast<uint4 *>(xn + (size_t)b * p.K + v * 8) = o;
+  for (int i = 0; i < 16; ++i) {
+    const int v = lane + i * 32;
+    wraw[i] = make_uint4(0, 0, 0, 0);
+    if (v < kvec) wraw[i] = *reinterpret_cast<const uint4 *>(p.norm_w + v * 8);
+  }
+  pdl_wait();
+  if (b >= p.B) return;
+  const bf16 *xr = p.X + (size_t)b * p.ldx;
+  bf16 *yr = xn + (size_t)b * p.K;
+  if (kvec <= 512) {
+    // K <= 4096: the row stays in registers between the statistics and the scaling (one pass over memory).
+    // Same summation order as sk_one_row_rstd (lane-strided, 16 loads per batch, xor-shuffle tree).
+    uint4 raw[16];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int v = lane + i * 32;
+      raw[i] = make_uint4(0, 0, 0, 0);
+      if (v < kvec) raw[i] = __ldcg(reinterpret_cast<const uint4 *>(xr + v * 8));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float f[8];
+      unpack8f(raw[i], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ss = fmaf(f[k], f[k], ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rs = rsqrtf(ss / (float)p.K + p.eps);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int v = lane + i * 32;
+      if (v < kvec) {
+        float f[8], wf[8];
+        unpack8f(raw[i], f);
+        unpack8f(wraw[i], wf);
+        uint4 o;
+        bf16 *oe = reinterpret_cast<bf16 *>(&o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) oe[e] = __float2bfloat16_rn(wf[e] * bf16_round(f[e] * rs));
+        *reinterpret_cast<uint4 *>(yr + v * 8) = o;
+      }
+    }
+  } else {
+    const float rs = sk_one_row_rstd(xr, p.K, p.eps, lane);
+    for (int v = lane; v < kvec; v += 32) {
+      float f[8], wf[8];
+      unpack8f(__ldcg(reinterpret_cast<const uint4 *>(xr + v * 8)), f);
+      unpack8f(*reinterpret_cast<const uint4 *>(p.norm_w + v * 8), wf);
+      uint4 o;
+      bf16 *oe = reinterpret_cast<bf16 *>(&o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) oe[e] = __float2bfloat16_rn(wf[e] * bf16_round(f[e] * rs));
+      *reinterpret_cast<uint4 *>(yr + v * 8) = o;
+    }
   }
 }
 
@@ -594,8 +636,7 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
     OCRB_REQUIRE(K <= SK_MAX_NORM_K, "skinny_gemm_bf16: the RMSNorm prologue supports K <= 32768");
     bf16 *xn = (bf16 *)((char *)workspace + (size_t)SK_MAX_GRID * SK_MAXBP * 128 * sizeof(float) +
                         (size_t)SK_MAX_GRID * sizeof(int) + 256);
-    const int nblk = cdiv((long long)B * (K >> 3), 256 * 4);
-    OCRB_CUDA(launch_pdl(skinny_norm_rows_kernel, dim3(nblk < 1 ? 1 : (nblk > 64 ? 64 : nblk)), dim3(256), 0, st, p, xn));
+    OCRB_CUDA(launch_pdl(skinny_norm_rows_kernel, dim3(cdiv(B, 8)), dim3(256), 0, st, p, xn));
     rc = check_launch("skinny_norm_rows_kernel");
     if (rc) return rc;
     p.X = xn;
