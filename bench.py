@@ -244,9 +244,9 @@ def run_b200(args):
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "peak_source": peak_src,
                 # dram read+write of the weight-streaming launches of ONE decode step, from the `ncu --set full` capture
-                # profiles/r01b_summary.md (28 x (qkv 33.13 + o_proj 25.80 + gate/up 275.47 + down 139.01 MB) + lm_head):
-                # 1.014 x the algorithmic weight bytes (extra = stream-K partials and outputs); 7B config, B = 3 only
-                "traffic": (14_346_000_000 if (not args.tiny and B == 3) else None),
+                # profiles/r01c_summary.md (28 x (qkv 33.09 + o_proj 25.77 + gate/up 275.33 + down 139.97 MB) + lm_head):
+                # 1.016 x the algorithmic weight bytes (extra = stream-K partials and outputs); 7B config, B = 3 only
+                "traffic": (14_368_000_000 if (not args.tiny and B == 3) else None),
                 "traffic_unit": "bytes per decode step (same unit as algorithmic_bytes_per_decode_step)",
                 "algorithmic_bytes_per_decode_step": int(alg_bytes_step), "decode_step_ms": round(step_ms, 4),
                 "kernel_only": {"achieved": round(iso["gbs"], 1), "frac": round(iso["gbs"] / peak, 4),
