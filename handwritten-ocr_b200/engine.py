@@ -23,7 +23,7 @@ OCR_PROMPT = "Extract and return all the text from this handwritten document."
 class OcrEngine:
     def __init__(self, weights: VLMWeights, *, max_batch: int = 8, max_new_tokens: int = 2048,
                  max_prompt: int = 1600, page_size: int = 16, tokenizer=None, min_pixels: int = 256 * 256,
-                 max_pixels: int = 1024 * 1024, tp=None):
+                 max_pixels: int = 1024 * 1024, tp=None, prefill_chunk: int = 6):
         self.w = weights
         self.cfg: VLMConfig = weights.cfg
         self.dev = weights.device
@@ -33,6 +33,9 @@ class OcrEngine:
         self.pages_per_seq = math.ceil((max_prompt + max_new_tokens) / page_size)
         self.kv = PagedKV(self.cfg, max_batch * self.pages_per_seq, page_size, self.dev)
         self.tp = tp
+        # vision tower + prefill run over at most this many sequences at a time: their activation panels then stay in
+        # the 126 MB L2 between the GEMMs' tile waves (measured: 21 -> 13 ms of prefill per read at 48 sequences)
+        self.prefill_chunk = max(1, int(prefill_chunk))
         self.dec = Decoder(weights, self.kv, max_batch, self.pages_per_seq * page_size, tp=tp)
         self._plans = {}
         self._states = {}
@@ -73,27 +76,17 @@ class OcrEngine:
         t = self.cfg.text
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-        merged, plan = self.encode_images(pages_u8)
-        ev[1].record()
-        ids, pos3, delta = self.build_inputs(plan, prompt)
+        H_, W_ = pages_u8.shape[1:3]
+        rh, rw = preprocess.smart_resize(H_, W_, 28, self.min_pixels, self.max_pixels)
+        plan0 = self._plan((rh // 14, rw // 14), min(n, self.prefill_chunk))
+        ids, pos3, delta = self.build_inputs(plan0, prompt)
         T = len(ids)
         if T + max_new > self.pages_per_seq * self.page:
             raise ValueError("prompt + max_new_tokens exceeds the KV capacity this engine was built with")
-        ids_d = torch.from_numpy(np.tile(ids, n)).to(self.dev)
         h = torch.empty((n * T, t.hidden), dtype=BF, device=self.dev)
-        _lib.call("ocrb_embed_gather", self.w.embed.data_ptr(), ids_d.data_ptr(), h.data_ptr(), n * T, t.hidden,
-                  _lib.stream_ptr())
-        # scatter image embeddings: window-order row r of image i is source group plan.group_perm[r]
         img_pos = np.nonzero(ids == IMAGE_PAD)[0]                       # positions of the G image tokens
-        gp = plan.group_perm.cpu().numpy()                              # global group index (i*G + g)
-        dst = (gp // plan.G) * T + img_pos[gp % plan.G]
-        dst_d = torch.from_numpy(dst.astype(np.int32)).to(self.dev)
-        _lib.call("ocrb_rows_copy", merged.data_ptr(), merged.stride(0), None, h.data_ptr(), h.stride(0),
-                  dst_d.data_ptr(), merged.shape[0], t.hidden, _lib.stream_ptr())
         pos_d = torch.from_numpy(pos3).to(self.dev)
         cos1, sin1, inv_freq = text_rope_tables(self.cfg, pos_d)
-        cos, sin = cos1.repeat(n, 1).contiguous(), sin1.repeat(n, 1).contiguous()
-        cu = torch.arange(0, (n + 1) * T, T, dtype=torch.int32, device=self.dev)
         # paged KV: block table per sequence
         need = math.ceil((T + max_new) / self.page)
         pages = [self.kv.alloc(need) for _ in range(n)]
@@ -101,8 +94,29 @@ class OcrEngine:
         for i, pg in enumerate(pages):
             bt[i, :need] = torch.tensor(pg, dtype=torch.int32)
         bt = bt.to(self.dev)
+        vis_ev = []
+        merged = plan = None
         try:
-            self.dec.prefill(h, cos, sin, cu, n, T, bt)
+            for i0 in range(0, n, self.prefill_chunk):
+                c = min(self.prefill_chunk, n - i0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                merged, plan = self.encode_images(pages_u8[i0:i0 + c])
+                e1.record()
+                vis_ev.append((e0, e1))
+                hc = h[i0 * T:(i0 + c) * T]
+                ids_d = torch.from_numpy(np.tile(ids, c)).to(self.dev)
+                _lib.call("ocrb_embed_gather", self.w.embed.data_ptr(), ids_d.data_ptr(), hc.data_ptr(), c * T, t.hidden,
+                          _lib.stream_ptr())
+                # scatter image embeddings: window-order row r of image i is source group plan.group_perm[r]
+                gp = plan.group_perm.cpu().numpy()                          # group index inside the chunk (i*G + g)
+                dst = (gp // plan.G) * T + img_pos[gp % plan.G]
+                dst_d = torch.from_numpy(dst.astype(np.int32)).to(self.dev)
+                _lib.call("ocrb_rows_copy", merged.data_ptr(), merged.stride(0), None, hc.data_ptr(), hc.stride(0),
+                          dst_d.data_ptr(), merged.shape[0], t.hidden, _lib.stream_ptr())
+                cos, sin = cos1.repeat(c, 1).contiguous(), sin1.repeat(c, 1).contiguous()
+                cu = torch.arange(0, (c + 1) * T, T, dtype=torch.int32, device=self.dev)
+                self.dec.prefill(hc, cos, sin, cu, c, T, bt[i0:i0 + c])
             last = h[T - 1::T]                                          # [n, hidden] last prompt token of each sequence
             key = (n, max_new)
             st = self._states.get(key)
@@ -133,7 +147,8 @@ class OcrEngine:
             for pg in pages:
                 self.kv.release(pg)
         torch.cuda.synchronize()
-        self.timings = {"vision_ms": ev[0].elapsed_time(ev[1]), "prefill_ms": ev[1].elapsed_time(ev[2]),
+        vision_ms = sum(a.elapsed_time(b) for a, b in vis_ev)
+        self.timings = {"vision_ms": vision_ms, "prefill_ms": ev[0].elapsed_time(ev[2]) - vision_ms,
                         "decode_ms": ev[2].elapsed_time(ev[3]), "prompt_len": T, "steps": n_steps, "batch": n}
         # HF stops appending once every sequence is finished (finished rows are padded with eos until
         # then); the device loop only checks every 64 steps, so trim to HF's stopping point.
