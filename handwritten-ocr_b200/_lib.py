@@ -31,6 +31,7 @@ _SIGS = {
     "ocrb_clahe_u8": [_P, _P, _I, _I, _I, _P, _P],
     "ocrb_adaptive_gauss_thresh_u8": [_P, _P, _I, _I, _I, _P],
     "ocrb_sharpen3x3_u8": [_P, _P, _I, _I, _I, _I, _P],
+    "ocrb_remove_lines_mask_u8": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "ocrb_deskew_angle": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "ocrb_warp_affine_cubic_u8": [_P, _P, _I, _I, _I, _I, _P, _P],
     "ocrb_smart_resize_host": [_I, _I, _I, _L, _L, _P, _P],

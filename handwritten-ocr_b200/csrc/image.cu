@@ -380,6 +380,75 @@ deskew_angle_kernel(const int32_t *__restrict__ ext, int H, int W, double *__res
   }
 }
 
+// ───────────── remove_lines: ruled-line mask (tools.py:592-614) ─────────────
+// mask = dilate_1x3( open_{W/4 x 1}( adaptiveThreshold(255 - gray, MEAN_C, BINARY, 15, -2) ) ), all integer:
+//   mean  = rint(sum15x15(255 - gray, replicate border) / 225)   (cv::boxFilter normalised, round half even)
+//   th    = (255 - gray) - mean > 2 ? 255 : 0
+//   open  = horizontal erosion then dilation with a W/4-wide window, anchor W/8 (outside: 255 for the erosion, 0 for the
+//           dilation -- cv::morphologyDefaultBorderValue), done with per-row prefix counts
+//   mask  = max over rows y-1, y, y+1
+// The Telea inpaint that follows in the reference is not built; callers use the mask only to prove it is empty
+// (then cv2.inpaint returns its input) and refuse otherwise.
+__global__ void __launch_bounds__(256)
+rl_thresh_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ th, int H, int W, int C) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, img = blockIdx.z;
+  if (x >= W) return;
+  const uint8_t *im = src + (size_t)img * H * W * C;
+  auto inv_at = [&](int yy, int xx) {
+    yy = min(max(yy, 0), H - 1);
+    xx = min(max(xx, 0), W - 1);
+    const uint8_t *p = im + ((size_t)yy * W + xx) * C;
+    const int g = (C == 3) ? gray_px(p[0], p[1], p[2]) : p[0];
+    return 255 - g;
+  };
+  int sum = 0;
+  for (int dy = -7; dy <= 7; ++dy)
+    for (int dx = -7; dx <= 7; ++dx) sum += inv_at(y + dy, x + dx);
+  const int mean = __double2int_rn(__dmul_rn((double)sum, 1.0 / 225.0));
+  th[((size_t)img * H + y) * W + x] = (inv_at(y, x) - mean > 2) ? 255 : 0;
+}
+
+// one CTA per row: the row lives in shared memory, prefix counts by one thread (W <= 8192), window tests by all
+__global__ void __launch_bounds__(256)
+rl_open_row_kernel(const uint8_t *__restrict__ th, uint8_t *__restrict__ op, int W, int kw) {
+  extern __shared__ int rl_pre[];               // [W + 1] prefix counts, then [W] flags
+  int *flag = rl_pre + (W + 1);
+  const size_t row = blockIdx.x;
+  const uint8_t *r = th + row * W;
+  const int anchor = kw / 2;
+  for (int x = threadIdx.x; x < W; x += 256) flag[x] = (r[x] == 0);       // erosion: the window must hold no zero
+  __syncthreads();
+  for (int pass = 0; pass < 2; ++pass) {
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      rl_pre[0] = 0;
+      for (int x = 0; x < W; ++x) { acc += flag[x]; rl_pre[x + 1] = acc; }
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < W; x += 256) {
+      const int lo = max(0, x - anchor), hi = min(W, x - anchor + kw);
+      const int cnt = rl_pre[hi] - rl_pre[lo];
+      if (pass == 0) flag[x] = (cnt == 0);       // eroded pixel is 255; dilation: the window must hold one such pixel
+      else op[row * W + x] = (cnt > 0) ? 255 : 0;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rl_dilate_v_kernel(const uint8_t *__restrict__ op, uint8_t *__restrict__ mask, int32_t *__restrict__ nonzero, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, img = blockIdx.z;
+  if (x >= W) return;
+  const uint8_t *o = op + (size_t)img * H * W;
+  uint8_t v = o[(size_t)y * W + x];
+  if (y > 0) v = max(v, o[(size_t)(y - 1) * W + x]);
+  if (y + 1 < H) v = max(v, o[(size_t)(y + 1) * W + x]);
+  mask[((size_t)img * H + y) * W + x] = v;
+  if (v) atomicOr(nonzero + img, 1);
+}
+
 // OpenCV fixed-point bicubic table: int16 [1024][16], index (fy*32 + fx), built on the host.
 __device__ int16_t g_cubic_itab[1024 * 16];
 
@@ -548,6 +617,22 @@ extern "C" int ocrb_sharpen3x3_u8(const uint8_t *src, uint8_t *dst, int32_t n_im
   OCRB_REQUIRE(src && dst && n_img > 0 && H > 1 && W > 1 && (C == 1 || C == 3), "sharpen3x3_u8: bad arguments");
   sharpen_kernel<<<dim3(cdiv((long long)W * C, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, C);
   return check_launch("sharpen_kernel");
+}
+
+extern "C" int ocrb_remove_lines_mask_u8(const uint8_t *src, uint8_t *mask, int32_t *nonzero, uint8_t *tmp, int32_t n_img,
+                                         int32_t H, int32_t W, int32_t C, void *stream) {
+  OCRB_REQUIRE(src && mask && nonzero && tmp && n_img > 0 && H > 0 && W >= 4 && W <= 8192 && (C == 1 || C == 3),
+               "remove_lines_mask_u8: bad arguments (W must be in 4..8192)");
+  cudaStream_t st = (cudaStream_t)stream;
+  OCRB_CUDA(cudaMemsetAsync(nonzero, 0, sizeof(int32_t) * n_img, st));
+  rl_thresh_kernel<<<dim3(cdiv(W, 256), H, n_img), 256, 0, st>>>(src, mask, H, W, C);          // th -> mask buffer
+  int rc = check_launch("rl_thresh_kernel");
+  if (rc) return rc;
+  rl_open_row_kernel<<<n_img * H, 256, (2 * W + 1) * sizeof(int), st>>>(mask, tmp, W, W / 4);        // open -> tmp
+  rc = check_launch("rl_open_row_kernel");
+  if (rc) return rc;
+  rl_dilate_v_kernel<<<dim3(cdiv(W, 256), H, n_img), 256, 0, st>>>(tmp, mask, nonzero, H, W);     // mask
+  return check_launch("rl_dilate_v_kernel");
 }
 
 extern "C" int ocrb_deskew_angle(const uint8_t *src, int32_t n_img, int32_t H, int32_t W, int32_t C, double *out_angle,

@@ -13,7 +13,7 @@ from . import _lib
 
 # name -> implemented on the GPU?  (tools.py:623-630 registers these six)
 TRANSFORMS = ("high_contrast", "binarize", "sharpen", "deskew", "denoise", "remove_lines")
-_NOT_YET = {"denoise": "fastNlMeansDenoising", "remove_lines": "Telea inpaint"}
+_NOT_YET = {"denoise": "fastNlMeansDenoising"}
 
 
 def _check(x: torch.Tensor):
@@ -98,6 +98,31 @@ def deskew(x: torch.Tensor, M: torch.Tensor | None = None) -> torch.Tensor:
     return warp_affine(x, M)
 
 
+def remove_lines_mask(x: torch.Tensor):
+    """Ruled-line mask of tools._apply_remove_lines (tools.py:598-614), bit-exact: (mask uint8 [n,H,W], nonzero int32 [n])."""
+    _check(x)
+    n, H, W = x.shape[:3]
+    C = 3 if x.dim() == 4 else 1
+    mask = torch.empty((n, H, W), dtype=torch.uint8, device=x.device)
+    tmp = torch.empty_like(mask)
+    nz = torch.empty(n, dtype=torch.int32, device=x.device)
+    _lib.call("ocrb_remove_lines_mask_u8", _lib.ptr(x), _lib.ptr(mask), _lib.ptr(nz), _lib.ptr(tmp), n, H, W, C,
+              _lib.stream_ptr())
+    return mask, nz
+
+
+def remove_lines(x: torch.Tensor) -> torch.Tensor:
+    """tools._apply_remove_lines (tools.py:592-619).  The mask is computed on the GPU; when it is empty -- no ruled
+    line at least a quarter of the page wide -- cv2.inpaint returns its input and so does this.  A non-empty mask needs
+    the Telea fast-marching inpaint, which has no GPU kernel yet: that raises (there is no CPU fallback)."""
+    _, nz = remove_lines_mask(x)
+    if bool(nz.any()):
+        raise NotImplementedError(
+            "transform 'remove_lines': this page has ruled lines and the Telea inpaint (cv2.inpaint) has no GPU kernel yet "
+            "(SURVEY §8 f3); this package has no CPU fallback")
+    return x
+
+
 def apply_transform(x: torch.Tensor, name: str) -> torch.Tensor:
     if name == "high_contrast":
         return high_contrast(x)
@@ -107,6 +132,8 @@ def apply_transform(x: torch.Tensor, name: str) -> torch.Tensor:
         return sharpen(x)
     if name == "deskew":
         return deskew(x)
+    if name == "remove_lines":
+        return remove_lines(x)
     if name in _NOT_YET:
         raise NotImplementedError(
             f"transform '{name}' ({_NOT_YET[name]}) has no GPU kernel yet (SURVEY §8 f3) and this "

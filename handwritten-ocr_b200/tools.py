@@ -73,7 +73,7 @@ def _steps(strategy) -> list:
 
 
 def _gpu_supported(steps) -> bool:
-    return all(s == "original" or s not in ("denoise", "remove_lines") for s in steps)
+    return all(s == "original" or s != "denoise" for s in steps)
 
 
 def _open_array(image_path: str) -> np.ndarray:

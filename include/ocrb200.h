@@ -67,6 +67,14 @@ int ocrb_adaptive_gauss_thresh_u8(const uint8_t *src_gray, uint8_t *dst_gray, in
 int ocrb_sharpen3x3_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t H, int32_t W,
                        int32_t C, void *stream);
 
+/* tools.py:598-614 (_apply_remove_lines up to the inpaint): ruled-line mask = dilate_1x3(open_{W/4 x 1}(
+ * adaptiveThreshold(255 - gray, 255, MEAN_C, BINARY, 15, -2))), bit-exact.  mask: uint8[n_img*H*W]; nonzero:
+ * int32[n_img], set to 1 when the image's mask has any pixel; tmp: uint8[n_img*H*W].  The Telea inpaint that the
+ * reference runs on a non-empty mask is NOT implemented: callers return the page unchanged when the mask is empty
+ * (cv2.inpaint does) and refuse otherwise. */
+int ocrb_remove_lines_mask_u8(const uint8_t *src, uint8_t *mask, int32_t *nonzero, uint8_t *tmp, int32_t n_img,
+                              int32_t H, int32_t W, int32_t C, void *stream);
+
 /* tools.py:556-564: dark-pixel (<128) row extents -> convex hull -> min-area-rect angle ->
  * rotation matrix about (W//2, H//2).  src has C channels (gray computed on the fly for C=3).
  * out_angle: double[n_img] (NaN when <= 100 dark pixels: image must be left unchanged),

@@ -140,3 +140,8 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# remove_lines.json (ruled-line mask of tools._apply_remove_lines, tools.py:598-614) was generated in the same
+# container by the snippet recorded in tests/test_remove_lines.py::GOLDEN_RECIPE (reference function for the
+# unchanged-page cases, the reference's own cv2 call sequence for the masks of pages with drawn ruled lines).
