@@ -32,6 +32,8 @@ _SIGS = {
     "ocrb_adaptive_gauss_thresh_u8": [_P, _P, _I, _I, _I, _P],
     "ocrb_sharpen3x3_u8": [_P, _P, _I, _I, _I, _I, _P],
     "ocrb_remove_lines_mask_u8": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "ocrb_nlm_denoise_u8": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "ocrb_denoise_tables_host": [_P, _P, _P, _P, _P],
     "ocrb_deskew_angle": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "ocrb_warp_affine_cubic_u8": [_P, _P, _I, _I, _I, _I, _P, _P],
     "ocrb_smart_resize_host": [_I, _I, _I, _L, _L, _P, _P],

@@ -1,0 +1,348 @@
+// denoise strategy (tools.py:576-589): cv2.fastNlMeansDenoising(gray, None, 10, 7, 21) and
+// cv2.fastNlMeansDenoisingColored(rgb, None, 10, 10, 7, 21), bit-exact against OpenCV 4.13.0.92.
+// Everything is integer arithmetic (the weight table, the Lab cube-root table and the Lab coefficients are built
+// once on the host with the float / double steps OpenCV uses and uploaded).
+//
+//   nlm_kernel<CN>:   one warp per 26 x 32 output tile.  Lane l owns column l - 3 of the tile: for each of the
+//                     441 search displacements it walks 38 rows, keeps the running 7-row column sum of squared
+//                     differences in a register (ring of the last 7 values), gets the 7-column patch sum with three
+//                     warp shuffles, looks the weight up in a shared-memory table and accumulates weight and
+//                     weight * pixel in registers (32 rows x (1 + CN) accumulators).  The reflect-101 extended tile
+//                     lives in shared memory; the lane's own column of it is packed into registers once.
+//   lbgr2lab_kernel / lab2lbgr_kernel: the two 8-bit Lab conversions of the colored variant (the reference hands
+//                     an RGB array to a function that reads channel 0 as blue; restated as called).
+#include "common.cuh"
+#include <math.h>
+#include <string.h>
+
+namespace ocrb {
+
+constexpr int NLM_SH = 10;             // search half width (21 x 21)
+constexpr int NLM_B = 13;              // border = search half + template half
+constexpr int NLM_LUT = 2048;          // weights are zero from an index below this (host-checked)
+constexpr int NLM_ROWS = 32;           // output rows per warp tile
+constexpr int NLM_COLS = 26;           // output columns per warp: 32 lanes - 6 template halo lanes
+constexpr int NLM_DROWS = NLM_ROWS + 6;
+constexpr int NLM_ER = NLM_ROWS + 2 * NLM_B;
+constexpr int NLM_EC = 32 + 2 * NLM_SH;  // 52 columns of the extended tile
+constexpr int NLM_SHIFT = 6;           // 2^6 >= 7 * 7
+constexpr int NLM_FPM = 2147483647 / (21 * 21 * 255);
+
+__device__ __forceinline__ int reflect101_any(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+  return i;
+}
+
+template <int CN> struct NlmPix;
+template <> struct NlmPix<1> { typedef uint8_t T; };
+template <> struct NlmPix<2> { typedef uint16_t T; };
+
+template <int CN>
+__global__ void __launch_bounds__(32)
+nlm_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H, int W, const uint16_t *__restrict__ lut_g) {
+  typedef typename NlmPix<CN>::T T;
+  constexpr int PER = 4 / CN;                         // pixels of the lane's own column per 32-bit register
+  constexpr int NPACK = (NLM_DROWS + PER - 1) / PER;
+  __shared__ T ext[NLM_ER * NLM_EC];
+  __shared__ uint16_t lut[NLM_LUT];
+  const int lane = threadIdx.x;
+  const int tx0 = blockIdx.x * NLM_COLS, ty0 = blockIdx.y * NLM_ROWS;
+  const T *im = reinterpret_cast<const T *>(src) + (size_t)blockIdx.z * H * W;
+  T *om = reinterpret_cast<T *>(dst) + (size_t)blockIdx.z * H * W;
+  for (int i = lane; i < NLM_LUT; i += 32) lut[i] = lut_g[i];
+  for (int er = 0; er < NLM_ER; ++er) {
+    const int gy = reflect101_any(ty0 - NLM_B + er, H);
+    for (int ec = lane; ec < NLM_EC; ec += 32)
+      ext[er * NLM_EC + ec] = im[(size_t)gy * W + reflect101_any(tx0 - NLM_B + ec, W)];
+  }
+  __syncwarp();
+
+  uint32_t apack[NPACK];
+#pragma unroll
+  for (int k = 0; k < NPACK; ++k) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int r = k * PER + q;
+      if (r < NLM_DROWS) v |= (uint32_t)ext[(r + NLM_SH) * NLM_EC + lane + NLM_SH] << (q * 8 * CN);
+    }
+    apack[k] = v;
+  }
+
+  uint32_t wsum[NLM_ROWS], est0[NLM_ROWS], est1[CN == 2 ? NLM_ROWS : 1];
+#pragma unroll
+  for (int j = 0; j < NLM_ROWS; ++j) {
+    wsum[j] = 0;
+    est0[j] = 0;
+    if (CN == 2) est1[j] = 0;
+  }
+
+  for (int dy = -NLM_SH; dy <= NLM_SH; ++dy) {
+#pragma unroll 1
+    for (int dx = -NLM_SH; dx <= NLM_SH; ++dx) {
+      const T *bp = ext + (NLM_SH + dy) * NLM_EC + lane + NLM_SH + dx;
+      uint32_t col = 0, dring[7], bring[4];
+#pragma unroll
+      for (int r = 0; r < NLM_DROWS; ++r) {
+        const uint32_t a = (apack[r / PER] >> ((r % PER) * 8 * CN)) & (CN == 1 ? 0xffu : 0xffffu);
+        const uint32_t b = bp[r * NLM_EC];
+        const uint32_t ad = __vabsdiffu4(a, b);
+        const uint32_t dd = __dp4a(ad, ad, 0u);
+        col += dd;
+        if (r >= 7) col -= dring[r % 7];
+        dring[r % 7] = dd;
+        bring[r % 4] = b;
+        if (r >= 6) {
+          const int j = r - 6;
+          const uint32_t t2 = col + __shfl_down_sync(0xffffffffu, col, 1);
+          const uint32_t t4 = t2 + __shfl_down_sync(0xffffffffu, t2, 2);          // columns l .. l+3
+          const uint32_t s7 = __shfl_up_sync(0xffffffffu, t4, 3) + t4 - col;      // columns l-3 .. l+3
+          const uint32_t w = lut[min(s7 >> NLM_SHIFT, (uint32_t)(NLM_LUT - 1))];
+          const uint32_t bc = bring[(r - 3) % 4];
+          wsum[j] += w;
+          if (CN == 1) {
+            est0[j] += w * bc;
+          } else {
+            est0[j] += w * (bc & 0xffu);
+            est1[j] += w * (bc >> 8);
+          }
+        }
+      }
+    }
+  }
+
+  const int x = tx0 + lane - 3;
+  if (lane < 3 || lane >= 3 + NLM_COLS || x >= W) return;
+#pragma unroll
+  for (int j = 0; j < NLM_ROWS; ++j) {
+    const int y = ty0 + j;
+    if (y < H) {
+      const uint32_t ws = wsum[j];
+      uint32_t o = min((est0[j] + ws / 2) / ws, 255u);
+      if (CN == 2) o |= min((est1[j] + ws / 2) / ws, 255u) << 8;
+      om[(size_t)y * W + x] = (T)o;
+    }
+  }
+}
+
+// ───────────── 8-bit Lab conversions (cvtColor COLOR_LBGR2Lab / COLOR_Lab2LBGR) ─────────────
+struct LabCoef {
+  int fwd[9];   // RGB2Lab_b coefficients, 12 bits, columns already swapped for "channel 0 is blue"
+  int inv[9];   // Lab2RGBinteger coefficients, 12 bits
+};
+
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+__global__ void __launch_bounds__(256)
+lbgr2lab_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ Lp, uint8_t *__restrict__ abp, size_t npix,
+                const uint16_t *__restrict__ cbrt_tab, LabCoef cf) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const int c0 = src[3 * p] * 8, c1 = src[3 * p + 1] * 8, c2 = src[3 * p + 2] * 8;
+  const int fX = __ldg(cbrt_tab + descale(c0 * cf.fwd[0] + c1 * cf.fwd[1] + c2 * cf.fwd[2], 12));
+  const int fY = __ldg(cbrt_tab + descale(c0 * cf.fwd[3] + c1 * cf.fwd[4] + c2 * cf.fwd[5], 12));
+  const int fZ = __ldg(cbrt_tab + descale(c0 * cf.fwd[6] + c1 * cf.fwd[7] + c2 * cf.fwd[8], 12));
+  const int L = descale(296 * fY - 1336935, 15);              // (116*255+50)/100 and ((16*255*2^15+50)/100)
+  const int a = descale(500 * (fX - fY) + 128 * 32768, 15);
+  const int b = descale(200 * (fY - fZ) + 128 * 32768, 15);
+  Lp[p] = (uint8_t)min(max(L, 0), 255);
+  reinterpret_cast<uint16_t *>(abp)[p] = (uint16_t)(min(max(a, 0), 255) | (min(max(b, 0), 255) << 8));
+}
+
+__device__ __forceinline__ int ab_to_xz(int i) {
+  constexpr int B = 1 << 14;
+  if (i <= 3390) return i * 108 / 841 - (B * 16 / 116 * 108 / 841);       // C division truncates toward zero
+  return (int)((long long)(i * i / B) * i / B);
+}
+
+__global__ void __launch_bounds__(256)
+lab2lbgr_kernel(const uint8_t *__restrict__ Lp, const uint8_t *__restrict__ abp, uint8_t *__restrict__ dst, size_t npix,
+                const int2 *__restrict__ yf_tab, LabCoef cf) {
+  constexpr int B = 1 << 14;
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const int L = Lp[p];
+  const uint32_t ab = reinterpret_cast<const uint16_t *>(abp)[p];
+  const int aa = ab & 0xff, bb = ab >> 8;
+  const int2 yf = __ldg(yf_tab + L);
+  const int y = yf.x, ify = yf.y;
+  const int adiv = ((5 * aa * 53687 + 128) >> 13) - 128 * B / 500;
+  const int bdiv = ((bb * 41943 + 16) >> 9) - 128 * B / 200 + 1;
+  const int x = ab_to_xz(ify + adiv);
+  const int z = ab_to_xz(ify - bdiv);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int v = descale(cf.inv[3 * k] * x + cf.inv[3 * k + 1] * y + cf.inv[3 * k + 2] * z, 14);
+    v = min(max(v, 0), 4095);
+    dst[3 * p + k] = (uint8_t)((v * 255) >> 12);
+  }
+}
+
+// ───────────── host tables (built once; float / double steps as OpenCV's softfloat code takes them) ─────────────
+static float cv_cbrt(float x) {   // cv::cubeRoot: exponent in thirds, quartic rational on the fraction, mantissa truncated
+  if (x == 0.f) return 0.f;
+  uint32_t ix;
+  memcpy(&ix, &x, 4);
+  ix &= 0x7fffffffu;
+  const int ex = (int)(ix >> 23) - 127;
+  int shx = ex % 3;
+  shx -= shx >= 0 ? 3 : 0;
+  const int ex3 = (ex - shx) / 3;
+  const uint32_t fbits = (ix & ((1u << 23) - 1)) | ((uint32_t)(shx + 127) << 23);
+  float frf;
+  memcpy(&frf, &fbits, 4);
+  const double fr = frf;
+  const double num = ((((45.2548339756803022511987494 * fr + 192.2798368355061050458134625) * fr +
+                        119.1654824285581628956914143) * fr + 13.43250139086239872172837314) * fr +
+                      0.1636161226585754240958355063);
+  const double den = ((((14.80884093219134573786480845 * fr + 151.9714051044435648658557668) * fr +
+                        168.5254414101568283957668343) * fr + 33.9905941350215598754191872) * fr + 1.0);
+  const double q = num / den;
+  uint64_t qb;
+  memcpy(&qb, &q, 8);
+  // double -> float by truncating the mantissa to 23 bits, then add the exponent third
+  const uint32_t m = (uint32_t)((qb >> 29) & ((1u << 23) - 1));
+  const int e = (int)((qb >> 52) & 0x7ff) - 1023 + 127 + ex3;
+  const uint32_t ob = ((uint32_t)e << 23) | m;
+  float out;
+  memcpy(&out, &ob, 4);
+  return out;
+}
+
+struct DenoiseHostTables {
+  uint16_t cbrt_tab[3072];
+  int yf[512];
+  LabCoef cf;
+  uint16_t w[2][NLM_LUT];
+  bool ok;
+};
+
+static const DenoiseHostTables &host_tables() {
+  static DenoiseHostTables t;
+  static bool built = false;
+  if (built) return t;
+  t.ok = true;
+  const float thr = 216.0f / 24389.0f, sc = 841.0f / 108.0f, off = 16.0f / 116.0f;
+  for (int i = 0; i < 3072; ++i) {
+    const float x = (float)i / 2040.0f;
+    const float f = x < thr ? fmaf(x, sc, off) : cv_cbrt(x);
+    t.cbrt_tab[i] = (uint16_t)lrint((double)(32768.0f * f));
+  }
+  const int B = 1 << 14;
+  for (int i = 0; i < 256; ++i) {
+    float y, ify;
+    if (i <= 20) {
+      y = (float)(i * B * 20 * 9) / (float)(17 * 29 * 29 * 29);
+      ify = (float)B * (16.0f / 116.0f + (float)(i * 100) / (float)(255 * 116));
+    } else {
+      ify = (float)(i * 100 * B) / (float)(255 * 116) + (float)(16 * B) / 116.0f;
+      y = ify * ify * ify / (float)(B * B);
+    }
+    t.yf[2 * i] = (int)lrint((double)y);
+    t.yf[2 * i + 1] = (int)lrint((double)ify);
+  }
+  static const double wp[3] = {0.950456, 1.0, 1.088754};
+  static const double r2x[9] = {0.412453, 0.357580, 0.180423, 0.212671, 0.715160, 0.072169, 0.019334, 0.119193, 0.950227};
+  static const double x2r[9] = {3.240479, -1.53715, -0.498535, -0.969256, 1.875991, 0.041556, 0.055648, -0.204043, 1.057311};
+  for (int i = 0; i < 3; ++i) {
+    t.cf.fwd[i * 3 + 2] = (int)lrint(4096 * r2x[i * 3] / wp[i]);
+    t.cf.fwd[i * 3 + 1] = (int)lrint(4096 * r2x[i * 3 + 1] / wp[i]);
+    t.cf.fwd[i * 3 + 0] = (int)lrint(4096 * r2x[i * 3 + 2] / wp[i]);
+    t.cf.inv[i] = (int)lrint(4096 * x2r[i + 6] * wp[i]);
+    t.cf.inv[i + 3] = (int)lrint(4096 * x2r[i + 3] * wp[i]);
+    t.cf.inv[i + 6] = (int)lrint(4096 * x2r[i] * wp[i]);
+  }
+  const double mult = 64.0 / 49.0;
+  for (int cn = 1; cn <= 2; ++cn) {
+    const int n = (int)(255.0 * 255.0 * cn / mult + 1);
+    for (int d = 0; d < n; ++d) {
+      long wgt = lrint(NLM_FPM * exp(-(d * mult) / (10.0 * 10.0 * cn)));
+      if ((double)wgt < 0.001 * NLM_FPM) wgt = 0;
+      if (d < NLM_LUT) t.w[cn - 1][d] = (uint16_t)wgt;
+      else if (wgt != 0) t.ok = false;
+    }
+    if (t.w[cn - 1][NLM_LUT - 1] != 0) t.ok = false;
+  }
+  built = true;
+  return t;
+}
+
+struct DenoiseDevTables {
+  uint16_t *cbrt_tab;
+  int2 *yf;
+  uint16_t *w[2];
+};
+
+static int device_tables(const DenoiseDevTables **out) {
+  static DenoiseDevTables dev[64];
+  static bool done[64] = {false};
+  int d = 0;
+  OCRB_CUDA(cudaGetDevice(&d));
+  OCRB_REQUIRE(d >= 0 && d < 64, "denoise: device index out of range");
+  if (!done[d]) {
+    const DenoiseHostTables &h = host_tables();
+    OCRB_REQUIRE(h.ok, "denoise: weight table does not end inside the shared-memory table");
+    uint8_t *base = nullptr;
+    const size_t sz = sizeof(h.cbrt_tab) + sizeof(h.yf) + sizeof(h.w);
+    OCRB_CUDA(cudaMalloc(&base, sz));
+    OCRB_CUDA(cudaMemcpy(base, h.yf, sizeof(h.yf), cudaMemcpyHostToDevice));
+    OCRB_CUDA(cudaMemcpy(base + sizeof(h.yf), h.cbrt_tab, sizeof(h.cbrt_tab), cudaMemcpyHostToDevice));
+    OCRB_CUDA(cudaMemcpy(base + sizeof(h.yf) + sizeof(h.cbrt_tab), h.w, sizeof(h.w), cudaMemcpyHostToDevice));
+    dev[d].yf = reinterpret_cast<int2 *>(base);
+    dev[d].cbrt_tab = reinterpret_cast<uint16_t *>(base + sizeof(h.yf));
+    dev[d].w[0] = reinterpret_cast<uint16_t *>(base + sizeof(h.yf) + sizeof(h.cbrt_tab));
+    dev[d].w[1] = dev[d].w[0] + NLM_LUT;
+    done[d] = true;
+  }
+  *out = &dev[d];
+  return OCRB_OK;
+}
+
+}  // namespace ocrb
+
+using namespace ocrb;
+
+extern "C" int ocrb_denoise_tables_host(int32_t *cbrt_tab, int32_t *lab_yf, int32_t *coef, int32_t *w1, int32_t *w2) {
+  OCRB_REQUIRE(cbrt_tab && lab_yf && coef && w1 && w2, "denoise_tables_host: null pointer");
+  const DenoiseHostTables &h = host_tables();
+  for (int i = 0; i < 3072; ++i) cbrt_tab[i] = h.cbrt_tab[i];
+  for (int i = 0; i < 512; ++i) lab_yf[i] = h.yf[i];
+  for (int i = 0; i < 9; ++i) {
+    coef[i] = h.cf.fwd[i];
+    coef[9 + i] = h.cf.inv[i];
+  }
+  for (int i = 0; i < NLM_LUT; ++i) {
+    w1[i] = h.w[0][i];
+    w2[i] = h.w[1][i];
+  }
+  return h.ok ? OCRB_OK : OCRB_EINVAL;
+}
+
+extern "C" int ocrb_nlm_denoise_u8(const uint8_t *src, uint8_t *dst, uint8_t *ws, int32_t n_img, int32_t H, int32_t W,
+                                   int32_t C, void *stream) {
+  OCRB_REQUIRE(src && dst && n_img > 0 && H > 0 && W > 0 && (C == 1 || C == 3), "nlm_denoise_u8: bad arguments");
+  OCRB_REQUIRE(src != dst, "nlm_denoise_u8: in-place not supported");
+  OCRB_REQUIRE(C == 1 || ws, "nlm_denoise_u8: RGB pages need the 6-bytes-per-pixel workspace");
+  OCRB_REQUIRE(cdiv(H, NLM_ROWS) <= 65535 && n_img <= 65535, "nlm_denoise_u8: page too tall / batch too large");
+  const DenoiseDevTables *t = nullptr;
+  int rc = device_tables(&t);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(cdiv(W, NLM_COLS), cdiv(H, NLM_ROWS), n_img);
+  if (C == 1) {
+    nlm_kernel<1><<<grid, 32, 0, st>>>(src, dst, H, W, t->w[0]);
+    return check_launch("nlm_kernel<1>");
+  }
+  const size_t npix = (size_t)n_img * H * W;
+  uint8_t *ab0 = ws, *ab1 = ws + 2 * npix, *L0 = ws + 4 * npix, *L1 = ws + 5 * npix;   // (a, b) pairs first: 2-byte aligned
+  OCRB_REQUIRE(((uintptr_t)ws & 1) == 0, "nlm_denoise_u8: workspace must be 2-byte aligned");
+  lbgr2lab_kernel<<<cdiv((long long)npix, 256), 256, 0, st>>>(src, L0, ab0, npix, t->cbrt_tab, host_tables().cf);
+  if ((rc = check_launch("lbgr2lab_kernel"))) return rc;
+  nlm_kernel<1><<<grid, 32, 0, st>>>(L0, L1, H, W, t->w[0]);
+  if ((rc = check_launch("nlm_kernel<1>"))) return rc;
+  nlm_kernel<2><<<grid, 32, 0, st>>>(ab0, ab1, H, W, t->w[1]);
+  if ((rc = check_launch("nlm_kernel<2>"))) return rc;
+  lab2lbgr_kernel<<<cdiv((long long)npix, 256), 256, 0, st>>>(L1, ab1, dst, npix, t->yf, host_tables().cf);
+  return check_launch("lab2lbgr_kernel");
+}

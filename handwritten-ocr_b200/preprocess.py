@@ -13,7 +13,6 @@ from . import _lib
 
 # name -> implemented on the GPU?  (tools.py:623-630 registers these six)
 TRANSFORMS = ("high_contrast", "binarize", "sharpen", "deskew", "denoise", "remove_lines")
-_NOT_YET = {"denoise": "fastNlMeansDenoising"}
 
 
 def _check(x: torch.Tensor):
@@ -98,6 +97,18 @@ def deskew(x: torch.Tensor, M: torch.Tensor | None = None) -> torch.Tensor:
     return warp_affine(x, M)
 
 
+def denoise(x: torch.Tensor) -> torch.Tensor:
+    """tools._apply_denoise (tools.py:576-589): fastNlMeansDenoising(10, 7, 21) on gray pages,
+    fastNlMeansDenoisingColored(10, 10, 7, 21) on RGB pages; same mode/shape as the input, bit-exact."""
+    _check(x)
+    n, H, W = x.shape[:3]
+    C = 3 if x.dim() == 4 else 1
+    out = torch.empty_like(x)
+    ws = torch.empty((n * H * W * 6,), dtype=torch.uint8, device=x.device) if C == 3 else None
+    _lib.call("ocrb_nlm_denoise_u8", _lib.ptr(x), _lib.ptr(out), _lib.ptr(ws), n, H, W, C, _lib.stream_ptr())
+    return out
+
+
 def remove_lines_mask(x: torch.Tensor):
     """Ruled-line mask of tools._apply_remove_lines (tools.py:598-614), bit-exact: (mask uint8 [n,H,W], nonzero int32 [n])."""
     _check(x)
@@ -134,10 +145,8 @@ def apply_transform(x: torch.Tensor, name: str) -> torch.Tensor:
         return deskew(x)
     if name == "remove_lines":
         return remove_lines(x)
-    if name in _NOT_YET:
-        raise NotImplementedError(
-            f"transform '{name}' ({_NOT_YET[name]}) has no GPU kernel yet (SURVEY §8 f3) and this "
-            "package has no CPU fallback")
+    if name == "denoise":
+        return denoise(x)
     raise KeyError(name)
 
 

@@ -72,10 +72,6 @@ def _steps(strategy) -> list:
     return [strategy] if isinstance(strategy, str) else list(strategy)
 
 
-def _gpu_supported(steps) -> bool:
-    return all(s == "original" or s != "denoise" for s in steps)
-
-
 def _open_array(image_path: str) -> np.ndarray:
     img = Image.open(image_path)
     arr = np.array(img)
@@ -112,7 +108,7 @@ def preprocess_image(image_path: str, strategy) -> str:
     if _options["speculative"]:
         for s in getattr(config, "PREPROCESSING_STRATEGIES", []):
             s = _steps(s)
-            if _label(s) and _gpu_supported(s) and all(_label(s) != _label(w) for w in wanted):
+            if _label(s) and all(_label(s) != _label(w) for w in wanted):
                 wanted.append(s)
     result = None
     for s in wanted:

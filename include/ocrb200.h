@@ -75,6 +75,19 @@ int ocrb_sharpen3x3_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t 
 int ocrb_remove_lines_mask_u8(const uint8_t *src, uint8_t *mask, int32_t *nonzero, uint8_t *tmp, int32_t n_img,
                               int32_t H, int32_t W, int32_t C, void *stream);
 
+/* tools.py:582-587 (_apply_denoise), bit-exact against OpenCV 4.13:
+ *   C == 1: cv2.fastNlMeansDenoising(gray, None, 10, 7, 21) (PIL mode "L" pages);
+ *   C == 3: cv2.fastNlMeansDenoisingColored(rgb, None, 10, 10, 7, 21) -- 8-bit Lab (channel 0 read as blue, as the
+ *           reference's RGB array is), NLM on L and on the (a, b) pair, back.
+ * ws: uint8[n_img*H*W*6], 2-byte aligned, for C == 3 (ignored for C == 1).  src != dst. */
+int ocrb_nlm_denoise_u8(const uint8_t *src, uint8_t *dst, uint8_t *ws, int32_t n_img, int32_t H, int32_t W,
+                        int32_t C, void *stream);
+
+/* Host-only: the integer tables ocrb_nlm_denoise_u8 uploads (Lab cube-root table int32[3072], LabToYF int32[512],
+ * forward + inverse Lab coefficients int32[18], NLM weight prefixes for 1 and 2 channels int32[2048] each), so that
+ * they can be compared with the oracle on a machine without a GPU. */
+int ocrb_denoise_tables_host(int32_t *cbrt_tab, int32_t *lab_yf, int32_t *coef, int32_t *w1, int32_t *w2);
+
 /* tools.py:556-564: dark-pixel (<128) row extents -> convex hull -> min-area-rect angle ->
  * rotation matrix about (W//2, H//2).  src has C channels (gray computed on the fly for C=3).
  * out_angle: double[n_img] (NaN when <= 100 dark pixels: image must be left unchanged),
