@@ -121,3 +121,20 @@ def corrupt(s: str, seed: int, rate: float = 0.05) -> str:
         if r < rate:
             out.append(alphabet[int(rng.integers(0, len(alphabet)))])
     return "".join(out)
+
+
+def rule_lines(page: np.ndarray, *, first: int = 60, pitch: int = 57, margin: int = 30, color=(70, 70, 90),
+               thick: int = 2) -> np.ndarray:
+    """Copy of `page` with notebook ruling: dark `thick`-px lines every `pitch` rows from x = margin to W - margin, line i
+    dropping i % 3 pixels over its length (so the lines are not all perfectly horizontal).  Pure numpy."""
+    out = page.copy()
+    h, w = out.shape[:2]
+    x = np.arange(margin, w - margin)
+    for i, y0 in enumerate(range(first, h - 40, pitch)):
+        y = y0 + ((x - margin) * (i % 3) * 2 + (w - 2 * margin)) // (2 * (w - 2 * margin))
+        for k in range(thick):
+            if out.ndim == 3:
+                out[y + k, x] = np.asarray(color, out.dtype)
+            else:
+                out[y + k, x] = (int(color[0]) * 9798 + int(color[1]) * 19235 + int(color[2]) * 3735 + 16384) >> 15
+    return out
