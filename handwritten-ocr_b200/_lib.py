@@ -32,6 +32,7 @@ _SIGS = {
     "ocrb_adaptive_gauss_thresh_u8": [_P, _P, _I, _I, _I, _P],
     "ocrb_sharpen3x3_u8": [_P, _P, _I, _I, _I, _I, _P],
     "ocrb_remove_lines_mask_u8": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "ocrb_inpaint_telea_u8": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ocrb_nlm_denoise_u8": [_P, _P, _P, _I, _I, _I, _I, _P],
     "ocrb_denoise_tables_host": [_P, _P, _P, _P, _P],
     "ocrb_deskew_angle": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
@@ -59,7 +60,7 @@ _SIGS = {
 }
 
 EXPORTS = ["ocrb_version", "ocrb_last_error", "ocrb_launch_count", "ocrb_launch_count_reset",
-           "ocrb_skinny_workspace_bytes"] + list(_SIGS)
+           "ocrb_skinny_workspace_bytes", "ocrb_inpaint_workspace_bytes"] + list(_SIGS)
 
 
 def load():
@@ -77,6 +78,8 @@ def load():
     L.ocrb_launch_count.restype = c_uint64
     L.ocrb_launch_count_reset.restype = None
     L.ocrb_skinny_workspace_bytes.restype = c_int64
+    L.ocrb_inpaint_workspace_bytes.restype = c_int64
+    L.ocrb_inpaint_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
     for name, args in _SIGS.items():
         fn = getattr(L, name)
         fn.argtypes = args

@@ -122,16 +122,28 @@ def remove_lines_mask(x: torch.Tensor):
     return mask, nz
 
 
+def inpaint_telea(x: torch.Tensor, mask: torch.Tensor, radius: int = 3) -> torch.Tensor:
+    """cv2.inpaint(page, mask, radius, cv2.INPAINT_TELEA) per page (tools.py:617), bit-exact; mask uint8 [n,H,W]."""
+    _check(x)
+    n, H, W = x.shape[:3]
+    C = 3 if x.dim() == 4 else 1
+    if not (mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous() and tuple(mask.shape) == (n, H, W)):
+        raise ValueError("mask must be a contiguous CUDA uint8 tensor [n,H,W]")
+    out = torch.empty_like(x)
+    nbytes = _lib.load().ocrb_inpaint_workspace_bytes(n, H, W)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    _lib.call("ocrb_inpaint_telea_u8", _lib.ptr(x), _lib.ptr(mask), _lib.ptr(out), _lib.ptr(ws), n, H, W, C, radius,
+              _lib.stream_ptr())
+    return out
+
+
 def remove_lines(x: torch.Tensor) -> torch.Tensor:
-    """tools._apply_remove_lines (tools.py:592-619).  The mask is computed on the GPU; when it is empty -- no ruled
-    line at least a quarter of the page wide -- cv2.inpaint returns its input and so does this.  A non-empty mask needs
-    the Telea fast-marching inpaint, which has no GPU kernel yet: that raises (there is no CPU fallback)."""
-    _, nz = remove_lines_mask(x)
-    if bool(nz.any()):
-        raise NotImplementedError(
-            "transform 'remove_lines': this page has ruled lines and the Telea inpaint (cv2.inpaint) has no GPU kernel yet "
-            "(SURVEY §8 f3); this package has no CPU fallback")
-    return x
+    """tools._apply_remove_lines (tools.py:592-619): ruled-line mask, then Telea inpaint with radius 3.  A batch without
+    any ruled line comes back as is (cv2.inpaint copies its input when the mask is empty)."""
+    mask, nz = remove_lines_mask(x)
+    if not bool(nz.any()):
+        return x
+    return inpaint_telea(x, mask, 3)
 
 
 def apply_transform(x: torch.Tensor, name: str) -> torch.Tensor:

@@ -115,12 +115,7 @@ def preprocess_image(image_path: str, strategy) -> str:
         lab = _label(s)
         if lab in _by_original.get(image_path, {}):
             continue
-        try:
-            y = preprocess.apply_strategy(x, s)
-        except NotImplementedError:
-            if s is steps:
-                raise
-            continue
+        y = preprocess.apply_strategy(x, s)
         path = _save(y[0].cpu().numpy(), image_path, lab)
         _processed[path] = (y, image_path, lab)
         _by_original.setdefault(image_path, {})[lab] = path

@@ -69,11 +69,18 @@ int ocrb_sharpen3x3_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t 
 
 /* tools.py:598-614 (_apply_remove_lines up to the inpaint): ruled-line mask = dilate_1x3(open_{W/4 x 1}(
  * adaptiveThreshold(255 - gray, 255, MEAN_C, BINARY, 15, -2))), bit-exact.  mask: uint8[n_img*H*W]; nonzero:
- * int32[n_img], set to 1 when the image's mask has any pixel; tmp: uint8[n_img*H*W].  The Telea inpaint that the
- * reference runs on a non-empty mask is NOT implemented: callers return the page unchanged when the mask is empty
- * (cv2.inpaint does) and refuse otherwise. */
+ * int32[n_img], set to 1 when the image's mask has any pixel; tmp: uint8[n_img*H*W]. */
 int ocrb_remove_lines_mask_u8(const uint8_t *src, uint8_t *mask, int32_t *nonzero, uint8_t *tmp, int32_t n_img,
                               int32_t H, int32_t W, int32_t C, void *stream);
+
+/* tools.py:617 cv2.inpaint(img, mask, radius, cv2.INPAINT_TELEA), bit-exact against OpenCV 4.13 (the reference passes
+ * radius 3; 1..7 accepted).  src, dst: uint8[n_img*H*W*C], C = 1 or 3, src != dst; mask: uint8[n_img*H*W], non-zero =
+ * repaint; pages with an empty mask are copied.  H, W >= 2.  ws: ocrb_inpaint_workspace_bytes(n_img, H, W) bytes,
+ * 16-byte aligned, contents irrelevant.  Row segments of the mask separated by 2*radius+2 clean rows are marched
+ * concurrently (one warp each); within a segment the march order is OpenCV's. */
+int64_t ocrb_inpaint_workspace_bytes(int32_t n_img, int32_t H, int32_t W);
+int ocrb_inpaint_telea_u8(const uint8_t *src, const uint8_t *mask, uint8_t *dst, uint8_t *ws, int32_t n_img, int32_t H,
+                          int32_t W, int32_t C, int32_t radius, void *stream);
 
 /* tools.py:582-587 (_apply_denoise), bit-exact against OpenCV 4.13:
  *   C == 1: cv2.fastNlMeansDenoising(gray, None, 10, 7, 21) (PIL mode "L" pages);

@@ -36,8 +36,9 @@ def main():
     a = ap.parse_args()
     rgb = pp.to_device([synth.page(100 + i) for i in range(a.pages)])
     gray = pp.to_gray(rgb)
+    ruled = pp.to_device([synth.rule_lines(synth.page(100 + i)) for i in range(a.pages)])
     out = {}
-    cases = {"denoise_rgb": lambda: pp.denoise(rgb), "denoise_gray": lambda: pp.denoise(gray),
+    cases = {"remove_lines_ruled": lambda: pp.remove_lines(ruled),"denoise_rgb": lambda: pp.denoise(rgb), "denoise_gray": lambda: pp.denoise(gray),
              "high_contrast": lambda: pp.high_contrast(rgb), "binarize": lambda: pp.binarize(rgb),
              "sharpen": lambda: pp.sharpen(rgb), "deskew": lambda: pp.deskew(rgb),
              "remove_lines_mask": lambda: pp.remove_lines_mask(rgb)}

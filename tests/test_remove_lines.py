@@ -1,6 +1,9 @@
-"""remove_lines (tools.py:592-619): the ruled-line mask is bit-exact (oracle on CPU vs golden hashes produced with the
-reference's own cv2 calls; GPU kernel vs oracle); pages without ruled lines come back unchanged, as cv2.inpaint does with
-an empty mask; pages WITH ruled lines are refused (the Telea inpaint is not built, and there is no CPU fallback)."""
+"""remove_lines (tools.py:592-619): ruled-line mask + Telea inpaint (cv2.inpaint radius 3), bit-exact.
+
+CPU: the oracle (numpy mask, oracle/inpaint_ref.c march) against golden outputs of the unmodified reference
+(tests/golden/make_golden_f3.py: inpaint.json, inpaint_small.npz; remove_lines.json for the mask) and, where cv2 is
+importable, against cv2.inpaint on random masks, borders and degenerate masks.  GPU: mask and inpaint kernels against the
+oracle and the golden hashes; pages without ruled lines come back unchanged, as cv2.inpaint does with an empty mask."""
 import hashlib
 import json
 import os
@@ -48,8 +51,105 @@ def test_oracle_mask_golden(synth, name, seed, w, h):
     assert sha(page) == GOLDEN[name]["page_sha"]
     m = R.lines_mask(R.rgb2gray(page))
     assert int((m > 0).sum()) == GOLDEN[name]["mask_px"] > 0 and sha(m) == GOLDEN[name]["mask_sha"]
-    with pytest.raises(NotImplementedError):
-        R.remove_lines(page)
+
+
+INPAINT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "inpaint.json")))
+INPAINT_SMALL = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "inpaint_small.npz")))
+CHAIN = ["deskew", "remove_lines", "high_contrast"]
+
+
+def golden_page(synth, g):
+    return synth.rule_lines(synth.page(g["seed"], g["w"], g["h"], gray=g["gray"]))
+
+
+@pytest.mark.parametrize("name", sorted(INPAINT))
+def test_oracle_inpaint_golden(synth, name):
+    """The oracle's remove_lines equals the unmodified reference's _apply_remove_lines output."""
+    g = INPAINT[name]
+    page = golden_page(synth, g)
+    assert sha(page) == g["input"]
+    out = R.remove_lines(page)
+    assert sha(out) == g["remove_lines"]
+    assert int((out != page).reshape(g["h"], g["w"], -1).any(-1).sum()) == g["changed_px"] > 0
+    if f"{name}/remove_lines" in INPAINT_SMALL:
+        assert np.array_equal(out, INPAINT_SMALL[f"{name}/remove_lines"])
+
+
+def random_inpaint_cases(n, seed=7, max_h=50, max_w=60):
+    rng = np.random.default_rng(seed)
+    for it in range(n):
+        H, W = int(rng.integers(2, max_h)), int(rng.integers(2, max_w))
+        C = int(rng.choice([1, 3]))
+        img = rng.integers(0, 256, (H, W, 3) if C == 3 else (H, W), dtype=np.uint8)
+        if it % 3 == 1:
+            img = (img // 64 * 64 + 10).astype(np.uint8)             # flat regions: exact ties in the weights
+        if it % 7 == 2:
+            img[:] = 200                                             # constant page: the J terms are pure rounding residue
+        mask = (rng.random((H, W)) < rng.choice([0.02, 0.1, 0.3, 0.6, 0.95, 1.0])).astype(np.uint8)
+        mask *= np.uint8(rng.integers(1, 256))
+        if it % 5 == 0:                                              # horizontal bars, some touching the borders
+            mask[:] = 0
+            for _ in range(int(rng.integers(1, 4))):
+                y = int(rng.integers(0, H))
+                mask[y:y + int(rng.integers(1, 5)), int(rng.integers(0, W)):] = 255
+        yield img, mask
+
+
+def test_oracle_inpaint_vs_cv2():
+    cv2 = pytest.importorskip("cv2")
+    for i, (img, mask) in enumerate(random_inpaint_cases(150)):
+        assert np.array_equal(R.inpaint_telea(img, mask), cv2.inpaint(img, mask, 3, cv2.INPAINT_TELEA)), (i, img.shape)
+    img = np.random.default_rng(1).integers(0, 256, (20, 24), dtype=np.uint8)
+    for y in range(20):                                              # one pixel at every position: all border cases
+        for x in range(24):
+            mask = np.zeros((20, 24), np.uint8)
+            mask[y, x] = 1
+            assert np.array_equal(R.inpaint_telea(img, mask), cv2.inpaint(img, mask, 3, cv2.INPAINT_TELEA)), (y, x)
+    empty = np.zeros((20, 24), np.uint8)
+    assert np.array_equal(R.inpaint_telea(img, empty), img)
+
+
+@pytest.mark.gpu
+def test_gpu_inpaint_random(pkg):
+    """The march kernel against the oracle: random masks (one segment, many segments, everything masked), bars on the
+    borders, single pixels in the corners, batches; 1 and 3 channels."""
+    import torch
+    from handwritten_ocr_b200 import preprocess as pp
+    for i, (img, mask) in enumerate(random_inpaint_cases(60)):
+        out = pp.inpaint_telea(pp.to_device(img), torch.from_numpy(mask[None]).cuda())[0].cpu().numpy()
+        assert np.array_equal(out, R.inpaint_telea(img, mask)), (i, img.shape, int((mask > 0).sum()))
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, (64, 48, 3), dtype=np.uint8)
+    for (y, x) in [(0, 0), (0, 47), (63, 0), (63, 47), (1, 1), (0, 20), (30, 0), (63, 20), (30, 47), (31, 24)]:
+        mask = np.zeros((64, 48), np.uint8)
+        mask[y, x] = 255
+        out = pp.inpaint_telea(pp.to_device(img), torch.from_numpy(mask[None]).cuda())[0].cpu().numpy()
+        assert np.array_equal(out, R.inpaint_telea(img, mask)), (y, x)
+    # segments exactly at / just under the independence gap (8 clean rows for radius 3), and a batch of different masks
+    imgs = rng.integers(0, 256, (4, 80, 70), dtype=np.uint8)
+    masks = np.zeros((4, 80, 70), np.uint8)
+    masks[0, 10:12, 5:60] = 1; masks[0, 20:22, 0:70] = 1            # 8 clean rows: two segments
+    masks[1, 10:12, 5:60] = 1; masks[1, 19:22, 3:66] = 1            # 7 clean rows: merged into one
+    masks[2, 0:3, :] = 1; masks[2, 77:80, :] = 1; masks[2, 40, 35] = 1
+    out = pp.inpaint_telea(pp.to_device(list(imgs)), torch.from_numpy(masks).cuda()).cpu().numpy()
+    for k in range(4):
+        assert np.array_equal(out[k], R.inpaint_telea(imgs[k], masks[k])), k
+    # other radii accepted by the C ABI
+    for r in (1, 5):
+        m = (rng.random((40, 50)) < 0.1).astype(np.uint8)
+        im = rng.integers(0, 256, (40, 50, 3), dtype=np.uint8)
+        out = pp.inpaint_telea(pp.to_device(im), torch.from_numpy(m[None]).cuda(), r)[0].cpu().numpy()
+        assert np.array_equal(out, R.inpaint_telea(im, m, r)), r
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(INPAINT))
+def test_gpu_remove_lines_golden(pkg, synth, name):
+    from handwritten_ocr_b200 import preprocess as pp
+    g = INPAINT[name]
+    x = pp.to_device(golden_page(synth, g))
+    assert sha(pp.remove_lines(x)[0].cpu().numpy()) == g["remove_lines"]
+    assert sha(pp.apply_strategy(x, CHAIN)[0].cpu().numpy()) == g["+".join(CHAIN)]
 
 
 @pytest.mark.gpu
@@ -71,5 +171,7 @@ def test_gpu_mask_and_strategy(pkg, synth):
     one = pp.to_device(synth.page(21))
     out = pp.apply_strategy(one, ["deskew", "remove_lines", "high_contrast"])
     assert torch.equal(out, pp.apply_strategy(one, ["deskew", "high_contrast"]))
-    with pytest.raises(NotImplementedError):
-        pp.apply_strategy(pp.to_device(pages[1]), ["remove_lines"])
+    # a mixed batch: the ruled page is repainted, the plain ones are copied
+    got = pp.remove_lines(x).cpu().numpy()
+    assert np.array_equal(got[0], pages[0]) and np.array_equal(got[2], pages[2])
+    assert np.array_equal(got[1], R.remove_lines(pages[1]))
