@@ -12,7 +12,10 @@
 //     the <= 49 disc positions of a painted pixel are evaluated by the lanes in parallel; only the float sums are then
 //     accumulated in OpenCV's raster order (one lane per running sum), because float addition does not reassociate.
 // The queue is a binary heap on the key (float bits of T) << 32 | insertion number, equal in order to OpenCV's sorted
-// list; it lives in global memory (L1-resident: one warp works on it) and only lane 0 touches it.
+// list; only lane 0 touches it.  A segment's window of the distance field, the flags and the page rows is staged in
+// shared memory together with the heap (freshly written global data would come back from L2 at ~600 cycles a load,
+// and the march is one long dependent chain); segments too tall for that run from global memory through the same
+// generic pointers, and a heap that outgrows its shared part spills into the segment's global slice.
 #include "common.cuh"
 #include <math.h>
 
@@ -116,53 +119,77 @@ inp_segment_kernel(InpWs w, int H, int maxseg, int gap) {
 }
 
 // ───────────── the queue (lane 0 only) ─────────────
+// A 32-ary heap handled by the whole warp: a pop loads the 32 children of a node with one access per lane and finds the
+// smallest (T bits, insertion number) with two warp min-reductions, so a queue of a few thousand entries is 2-3 levels
+// deep.  The first `cap` entries live in shared memory, the rest (pathological masks only) in the segment's global slice.
+// Every lane keeps n / seq; only lane 0 writes entries.
 struct Heap {
-  uint64_t *key;
-  int32_t *pos;
+  uint32_t *sT, *sS;
+  int32_t *sP;
+  uint32_t *gT, *gS;
+  int32_t *gP;
+  int cap;
   int n;
   uint32_t seq;
+  __device__ __forceinline__ uint32_t T(int i) const { return i < cap ? sT[i] : gT[i]; }
+  __device__ __forceinline__ uint32_t S(int i) const { return i < cap ? sS[i] : gS[i]; }
+  __device__ __forceinline__ int P(int i) const { return i < cap ? sP[i] : gP[i]; }
+  __device__ __forceinline__ void set(int i, uint32_t t, uint32_t q, int p) {
+    if (i < cap) {
+      sT[i] = t;
+      sS[i] = q;
+      sP[i] = p;
+    } else {
+      gT[i] = t;
+      gS[i] = q;
+      gP[i] = p;
+    }
+  }
 };
 
-__device__ __forceinline__ void heap_push(Heap &h, int p, float T) {
-  const uint64_t k = ((uint64_t)(T == 0.f ? 0u : __float_as_uint(T)) << 32) | h.seq++;
+// all lanes call with the same arguments
+__device__ __forceinline__ void heap_push(Heap &h, int p, float Tv, int lane) {
+  const uint32_t kt = Tv == 0.f ? 0u : __float_as_uint(Tv), ks = h.seq++;
   int i = h.n++;
-  while (i > 0) {
-    const int par = (i - 1) >> 1;
-    const uint64_t kp = h.key[par];
-    if (kp <= k) break;
-    h.key[i] = kp;
-    h.pos[i] = h.pos[par];
-    i = par;
+  if (lane == 0) {
+    while (i > 0) {
+      const int par = (i - 1) >> 5;
+      const uint32_t pt = h.T(par), ps = h.S(par);
+      if (pt < kt || (pt == kt && ps <= ks)) break;
+      h.set(i, pt, ps, h.P(par));
+      i = par;
+    }
+    h.set(i, kt, ks, p);
   }
-  h.key[i] = k;
-  h.pos[i] = p;
+  __syncwarp();
 }
 
-__device__ __forceinline__ int heap_pop(Heap &h) {
+// all lanes call; every lane gets the popped pixel (or -1)
+__device__ __forceinline__ int heap_pop(Heap &h, int lane) {
   if (h.n == 0) return -1;
-  const int top = h.pos[0];
+  const int top = h.P(0);
   const int n = --h.n;
-  const uint64_t k = h.key[n];
-  const int pv = h.pos[n];
+  if (n == 0) return top;
+  const uint32_t kt = h.T(n), ks = h.S(n);
+  const int kp = h.P(n);
+  __syncwarp();
   int i = 0;
   for (;;) {
-    int c = 2 * i + 1;
-    if (c >= n) break;
-    uint64_t kc = h.key[c];
-    if (c + 1 < n) {
-      const uint64_t kr = h.key[c + 1];
-      if (kr < kc) {
-        kc = kr;
-        ++c;
-      }
-    }
-    if (kc >= k) break;
-    h.key[i] = kc;
-    h.pos[i] = h.pos[c];
-    i = c;
+    const int c0 = 32 * i + 1;
+    if (c0 >= n) break;
+    const int idx = c0 + lane;
+    const bool valid = idx < n;
+    const uint32_t ct = valid ? h.T(idx) : 0xffffffffu, cs = valid ? h.S(idx) : 0xffffffffu;
+    const uint32_t mt = __reduce_min_sync(0xffffffffu, ct);
+    const uint32_t cand = ct == mt ? cs : 0xffffffffu;
+    const uint32_t ms = __reduce_min_sync(0xffffffffu, cand);
+    if (mt > kt || (mt == kt && ms >= ks)) break;
+    const int widx = c0 + __ffs(__ballot_sync(0xffffffffu, ct == mt && cand == ms)) - 1;
+    if (lane == 0) h.set(i, mt, ms, h.P(widx));
+    i = widx;
   }
-  h.key[i] = k;
-  h.pos[i] = pv;
+  if (lane == 0) h.set(i, kt, ks, kp);
+  __syncwarp();
   return top;
 }
 
@@ -177,8 +204,7 @@ __device__ int heap_seed(Heap &h, const uint8_t *rg, uint8_t marker, int row0, i
     const unsigned b = __ballot_sync(0xffffffffu, is);
     if (is) {
       const int idx = n + __popc(b & ((1u << lane) - 1));
-      h.key[idx] = (uint64_t)idx;
-      h.pos[idx] = row0 * ec + q;
+      h.set(idx, 0u, (uint32_t)idx, row0 * ec + q);
     }
     n += __popc(b);
   }
@@ -260,21 +286,18 @@ __device__ void paint_pixel(const uint8_t *f, const float *t, uint8_t *out, int 
         const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ec - 2);
         const bool fr = f[kl + 1] != F_INSIDE, fl = f[kl - 1] != F_INSIDE;
         const bool fd = f[kl + ec] != F_INSIDE, fu = f[kl - ec] != F_INSIDE;
+        // the two pixels of each difference and its factor (central differences are doubled, not halved, in OpenCV)
+        const int xa = (km * W + (fr ? lp + 1 : lp)) * C, xb = (km * W + (fl ? lm - 1 : lm)) * C;
+        const int ya = ((fd ? kp + 1 : kp) * W + lm) * C, yb = ((fu ? km - 1 : km) * W + lm) * C;
+        const float sx = fr ? (fl ? 2.0f : 1.0f) : (fl ? 1.0f : 0.f), sy = fd ? (fu ? 2.0f : 1.0f) : (fu ? 1.0f : 0.f);
+        const int ctr = ((k - 1) * W + (l - 1)) * C;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          auto PX = [&](int y, int x) { return (int)out[((size_t)y * W + x) * C + c]; };
-          float gix, giy;
-          if (fr)
-            gix = fl ? (float)(PX(km, lp + 1) - PX(km, lm - 1)) * 2.0f : (float)(PX(km, lp + 1) - PX(km, lm));
-          else
-            gix = fl ? (float)(PX(km, lp) - PX(km, lm - 1)) : 0.f;
-          if (fd)
-            giy = fu ? (float)(PX(kp + 1, lm) - PX(km - 1, lm)) * 2.0f : (float)(PX(kp + 1, lm) - PX(km, lm));
-          else
-            giy = fu ? (float)(PX(kp, lm) - PX(km - 1, lm)) : 0.f;
-          tr[c] = w * (float)PX(k - 1, l - 1);
-          tr[3 + c] = w * (gix * rx);
-          tr[6 + c] = w * (giy * ry);
+          const float gix = (float)((int)out[xa + c] - (int)out[xb + c]) * sx;
+          const float giy = (float)((int)out[ya + c] - (int)out[yb + c]) * sy;
+          tr[c] = w * (float)out[ctr + c];
+          tr[3 + c] = -(w * (gix * rx));       // Jx -= v  ==  Jx += -v
+          tr[6 + c] = -(w * (giy * ry));
         }
         tr[9] = w;
       }
@@ -285,30 +308,30 @@ __device__ void paint_pixel(const uint8_t *f, const float *t, uint8_t *out, int 
   __syncwarp();
   // running sums in raster order: lane c < 3 -> Ia[c], 3..5 -> Jx, 6..8 -> Jy, 9 -> s
   float acc = lane == 9 ? 1.0e-20f : 0.f;
-  if (lane < INP_CHAINS) {
-    if (lane < 3 || lane == 9) {
-      for (int q = 0; q < D * D; ++q) acc += terms[q * INP_CHAINS + lane];
-    } else {
-      for (int q = 0; q < D * D; ++q) acc -= terms[q * INP_CHAINS + lane];
-    }
-  }
+  if (lane < INP_CHAINS)
+    for (int q = 0; q < D * D; ++q) acc += terms[q * INP_CHAINS + lane];
   const int c = lane < C ? lane : 0;
   const float Ia = __shfl_sync(0xffffffffu, acc, c), Jx = __shfl_sync(0xffffffffu, acc, 3 + c);
   const float Jy = __shfl_sync(0xffffffffu, acc, 6 + c), s = __shfl_sync(0xffffffffu, acc, 9);
   if (lane < C) {
     const float sat = (float)(Ia / s + (Jx + Jy) / (sqrt((double)(Jx * Jx + Jy * Jy)) + (double)1.0e-20f));
     const int v = __float2int_rn(sat + 0.5f);
-    out[((size_t)(i - 1) * W + (j - 1)) * C + lane] = (uint8_t)min(max(v, 0), 255);
+    out[((i - 1) * W + (j - 1)) * C + lane] = (uint8_t)min(max(v, 0), 255);
   }
   __syncwarp();
 }
 
 // ───────────── one warp per (segment, page) ─────────────
+// Dynamic shared memory: [terms | dst_tab | window of t, f, rg, page rows (when it fits) | heap].
+constexpr int INP_FIXED_SMEM = ((2 * INP_MAX_RANGE + 1) * (2 * INP_MAX_RANGE + 1) * (INP_CHAINS + 1) * 4 + 15) & ~15;
+constexpr int INP_MIN_HEAP = 1024;    // entries kept in shared memory at the very least
+
 template <int C>
-__global__ void __launch_bounds__(32)
-inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, int maxseg) {
-  __shared__ float terms[(2 * INP_MAX_RANGE + 1) * (2 * INP_MAX_RANGE + 1) * INP_CHAINS];
-  __shared__ float dst_tab[(2 * INP_MAX_RANGE + 1) * (2 * INP_MAX_RANGE + 1)];
+__global__ void __launch_bounds__(32, 1)
+inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, int maxseg, int smem_bytes) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  float *terms = reinterpret_cast<float *>(smem);
+  float *dst_tab = terms + (2 * INP_MAX_RANGE + 1) * (2 * INP_MAX_RANGE + 1) * INP_CHAINS;
   const int lane = threadIdx.x, img = blockIdx.y;
   const int32_t *seg = w.seg + (size_t)img * (1 + 2 * maxseg);
   if ((int)blockIdx.x >= seg[0]) return;
@@ -319,9 +342,45 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
   float *t = w.t + img * ne;
   uint8_t *out = dst + (size_t)img * H * W * C;
   const int lo = max(r0 - range, 0), hi = min(r1 + range, er - 1);
+  // everything the march reads or writes lies in extended rows wlo..whi and page rows olo..ohi
+  const int wlo = max(r0 - range - 1, 0), whi = min(r1 + range + 1, er - 1);
+  const int olo = max(wlo - 1, 0), ohi = min(whi - 1, H - 1);
+  const size_t wpx = (size_t)(whi - wlo + 1) * ec, obytes = (size_t)(ohi - olo + 1) * W * C;
+  const size_t win_bytes = ((wpx * 4 + 15) & ~(size_t)15) + 2 * ((wpx + 15) & ~(size_t)15) + ((obytes + 15) & ~(size_t)15);
+  const bool staged = INP_FIXED_SMEM + win_bytes + (size_t)INP_MIN_HEAP * 12 <= (size_t)smem_bytes;
+  uint8_t *sp = smem + INP_FIXED_SMEM;
+  uint8_t *out_s = nullptr;
+  if (staged) {
+    float *t_s = reinterpret_cast<float *>(sp);
+    sp += (wpx * 4 + 15) & ~(size_t)15;
+    uint8_t *f_s = sp;
+    sp += (wpx + 15) & ~(size_t)15;
+    uint8_t *rg_s = sp;
+    sp += (wpx + 15) & ~(size_t)15;
+    out_s = sp;
+    sp += (obytes + 15) & ~(size_t)15;
+    const size_t w0 = (size_t)wlo * ec;
+    for (size_t q = lane; q < wpx; q += 32) {
+      t_s[q] = t[w0 + q];
+      f_s[q] = f[w0 + q];
+      rg_s[q] = rg[w0 + q];
+    }
+    const uint8_t *og = out + (size_t)olo * W * C;
+    for (size_t q = lane; q < obytes; q += 32) out_s[q] = og[q];
+    t = t_s - w0;            // generic pointers biased so that extended / page coordinates index them unchanged
+    f = f_s - w0;
+    rg = rg_s - w0;
+    out = out_s - (size_t)olo * W * C;
+  }
   Heap h;
-  h.key = w.key + img * ne + (size_t)lo * ec;
-  h.pos = w.pos + img * ne + (size_t)lo * ec;
+  h.cap = (int)((smem + smem_bytes - sp) / 12);
+  h.sT = reinterpret_cast<uint32_t *>(sp);
+  h.sS = h.sT + h.cap;
+  h.sP = reinterpret_cast<int32_t *>(h.sS + h.cap);
+  const size_t slice = (size_t)(hi - lo + 1) * ec;          // the segment's part of the global spill arrays
+  h.gT = reinterpret_cast<uint32_t *>(w.key + img * ne + (size_t)lo * ec);
+  h.gS = h.gT + slice;
+  h.gP = w.pos + img * ne + (size_t)lo * ec;
   const int D = 2 * range + 1;
   for (int q = lane; q < D * D; q += 32) {
     const int dk = q / D - range, dl = q % D - range;
@@ -333,13 +392,9 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
   __syncwarp();
   heap_seed(h, rg, F_SEED, r0 - 1, r1 + 1, ec, lane);
   for (;;) {
-    int p = -1;
-    if (lane == 0) {
-      p = heap_pop(h);
-      if (p >= 0) rg[p] = rg[p] == F_SEED ? F_SEED_DONE : F_CHANGE;
-    }
-    p = __shfl_sync(0xffffffffu, p, 0);
+    const int p = heap_pop(h, lane);
     if (p < 0) break;
+    if (lane == 0) rg[p] = rg[p] == F_SEED ? F_SEED_DONE : F_CHANGE;
     __syncwarp();
     int nb;
     float d;
@@ -350,13 +405,14 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
       const bool vq = __shfl_sync(0xffffffffu, (int)valid, 4 * q) != 0;
       const float dq = __shfl_sync(0xffffffffu, d, 4 * q);
       const int nq = __shfl_sync(0xffffffffu, nb, 4 * q);
-      if (vq && lane == 0) {
-        t[nq] = dq;
-        rg[nq] = F_BAND;
-        heap_push(h, nq, dq);
+      if (vq) {
+        if (lane == 0) {
+          t[nq] = dq;
+          rg[nq] = F_BAND;
+        }
+        heap_push(h, nq, dq, lane);
       }
     }
-    __syncwarp();
   }
   for (int q = lo * ec + lane; q < (hi + 1) * ec; q += 32)
     if (rg[q] == F_CHANGE || rg[q] == F_SEED_DONE) t[q] = -t[q];
@@ -365,13 +421,9 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
   // march inwards, painting every pixel when the front reaches it
   heap_seed(h, rg, F_SEED_DONE, r0 - 1, r1 + 1, ec, lane);
   for (;;) {
-    int p = -1;
-    if (lane == 0) {
-      p = heap_pop(h);
-      if (p >= 0) f[p] = F_KNOWN;
-    }
-    p = __shfl_sync(0xffffffffu, p, 0);
+    const int p = heap_pop(h, lane);
     if (p < 0) break;
+    if (lane == 0) f[p] = F_KNOWN;
     __syncwarp();
     int nb;
     float d;
@@ -385,12 +437,14 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
       if (lane == 0) t[nq] = dq;
       __syncwarp();
       paint_pixel<C>(f, t, out, er, ec, range, nq, lane, dst_tab, terms);
-      if (lane == 0) {
-        f[nq] = F_BAND;
-        heap_push(h, nq, dq);
-      }
-      __syncwarp();
+      if (lane == 0) f[nq] = F_BAND;
+      heap_push(h, nq, dq, lane);
     }
+  }
+  if (staged) {                                  // painted rows back to the page
+    uint8_t *og = dst + (size_t)img * H * W * C;
+    const size_t b0 = (size_t)(r0 - 1) * W * C, b1 = (size_t)r1 * W * C;
+    for (size_t q = b0 + lane; q < b1; q += 32) og[q] = out[q];
   }
 }
 
@@ -410,7 +464,7 @@ extern "C" int ocrb_inpaint_telea_u8(const uint8_t *src, const uint8_t *mask, ui
   OCRB_REQUIRE(H >= 2 && W >= 2, "inpaint_telea_u8: pages one pixel high or wide are not supported (OpenCV reads outside them)");
   OCRB_REQUIRE(radius >= 1 && radius <= INP_MAX_RANGE, "inpaint_telea_u8: radius must be in 1..7");
   OCRB_REQUIRE(src != dst && ((uintptr_t)ws & 15) == 0, "inpaint_telea_u8: in-place not supported; workspace must be 16-byte aligned");
-  OCRB_REQUIRE((size_t)(H + 2) * (W + 2) < ((size_t)1 << 31) && H + 2 <= 65535 && n_img <= 65535, "inpaint_telea_u8: page too large");
+  OCRB_REQUIRE((size_t)(H + 2) * (W + 2) * 3 < ((size_t)1 << 31) && H + 2 <= 65535 && n_img <= 65535, "inpaint_telea_u8: page too large");
   cudaStream_t st = (cudaStream_t)stream;
   InpWs w;
   inp_layout(&w, ws, n_img, H, W);
@@ -422,9 +476,19 @@ extern "C" int ocrb_inpaint_telea_u8(const uint8_t *src, const uint8_t *mask, ui
   if (rc) return rc;
   inp_segment_kernel<<<n_img, 32, 0, st>>>(w, H, maxseg, inp_gap(radius));
   if ((rc = check_launch("inp_segment_kernel"))) return rc;
+  static int smem_bytes = 0;
+  if (!smem_bytes) {
+    int dev = 0, optin = 0;
+    OCRB_CUDA(cudaGetDevice(&dev));
+    OCRB_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    OCRB_REQUIRE(optin >= INP_FIXED_SMEM + INP_MIN_HEAP * 12, "inpaint_telea_u8: not enough shared memory per block");
+    OCRB_CUDA(cudaFuncSetAttribute(inp_march_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    OCRB_CUDA(cudaFuncSetAttribute(inp_march_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    smem_bytes = optin;
+  }
   if (C == 1)
-    inp_march_kernel<1><<<dim3(maxseg, n_img), 32, 0, st>>>(dst, w, H, W, radius, maxseg);
+    inp_march_kernel<1><<<dim3(maxseg, n_img), 32, smem_bytes, st>>>(dst, w, H, W, radius, maxseg, smem_bytes);
   else
-    inp_march_kernel<3><<<dim3(maxseg, n_img), 32, 0, st>>>(dst, w, H, W, radius, maxseg);
+    inp_march_kernel<3><<<dim3(maxseg, n_img), 32, smem_bytes, st>>>(dst, w, H, W, radius, maxseg, smem_bytes);
   return check_launch("inp_march_kernel");
 }

@@ -134,6 +134,11 @@ def test_gpu_inpaint_random(pkg):
     out = pp.inpaint_telea(pp.to_device(list(imgs)), torch.from_numpy(masks).cuda()).cpu().numpy()
     for k in range(4):
         assert np.array_equal(out[k], R.inpaint_telea(imgs[k], masks[k])), k
+    # a segment too tall for shared memory (runs from global memory) whose queue outgrows its shared part
+    big = rng.integers(0, 256, (300, 400, 3), dtype=np.uint8)
+    bm = (rng.random((300, 400)) < 0.3).astype(np.uint8)
+    out = pp.inpaint_telea(pp.to_device(big), torch.from_numpy(bm[None]).cuda())[0].cpu().numpy()
+    assert np.array_equal(out, R.inpaint_telea(big, bm))
     # other radii accepted by the C ABI
     for r in (1, 5):
         m = (rng.random((40, 50)) < 0.1).astype(np.uint8)
