@@ -101,3 +101,56 @@ def test_original_unknown_and_denoise_transforms(rig, capsys):
     assert os.path.isfile(p3) and os.path.basename(p3).startswith("ocr_deskew+denoise+high_contrast_")
     with pytest.raises(Exception):
         tools.preprocess_image("/nonexistent/page.png", S[1])
+
+
+def test_complete_reocr_sweep_config4(pkg, synth, tmp_path):
+    """BASELINE configs[3]: every distinct configured strategy of a page (config.py:29-36, all five -- denoise and
+    remove_lines included) preprocessed on the GPU, read in ONE paged-KV batch, each transcription scored against a
+    synthetic ground truth.  The page is ruled, so remove_lines really inpaints.  Checks: preprocessed temp files equal
+    the oracle's arrays bit for bit, one batched read of 5, evaluate() equal to the oracle's."""
+    from handwritten_ocr_b200 import tools, vlm, engine
+    from handwritten_ocr_b200.vlm_config import VLMConfig
+    from oracle import image_ref
+    strategies = [["deskew", "high_contrast", "binarize"], ["high_contrast", "binarize"],       # config.py:29-36:
+                  ["deskew", "high_contrast", "sharpen"], ["deskew", "denoise", "high_contrast"],  # six entries,
+                  ["deskew", "remove_lines", "high_contrast"], ["deskew", "high_contrast", "binarize"]]  # five distinct
+    distinct = []
+    for s in strategies:
+        if s not in distinct:
+            distinct.append(s)
+    assert len(distinct) == 5
+    cfg = VLMConfig.tiny()
+    w = vlm.VLMWeights.random(cfg, torch.device("cuda"), seed=0)
+    eng = engine.OcrEngine(w, max_batch=8, max_new_tokens=24, max_prompt=400)
+    saved = (tools._ocr_engine, dict(tools._options), tools.config.OCR_MAX_NEW_TOKENS, tools.config.PREPROCESSING_STRATEGIES)
+    tools._ocr_engine = eng
+    tools.configure(speculative=True, max_batch=8)
+    tools.config.OCR_MAX_NEW_TOKENS = 24
+    tools.config.PREPROCESSING_STRATEGIES = strategies
+    page = synth.rule_lines(synth.page(410, 504, 392))
+    img = str(tmp_path / "ruled.png")
+    Image.fromarray(page).save(img)
+    calls = []
+    orig = eng.read_batch
+
+    def counting(pages, **kw):
+        calls.append(pages.shape[0])
+        return orig(pages, **kw)
+
+    eng.read_batch = counting
+    try:
+        texts = [tools.run_ocr(tools.preprocess_image(img, s)) for s in strategies]
+        assert calls == [5], calls
+        assert texts[0] == texts[5]                               # the repeated strategy is served from the cache
+        for s in distinct:
+            got = np.array(Image.open(tools.preprocess_image(img, s)))
+            assert np.array_equal(got, image_ref.apply_strategy(page, s)), s
+        assert (image_ref.remove_lines(page) != page).any()
+        gt = synth.corrupt(texts[0], 3, 0.05)
+        for t in texts:
+            assert tools.evaluate(t, gt) == text_ref.evaluate(t, gt)
+    finally:
+        eng.read_batch = orig
+        tools.forget(img)
+        tools._ocr_engine, opts, tools.config.OCR_MAX_NEW_TOKENS, tools.config.PREPROCESSING_STRATEGIES = saved
+        tools._options.update(opts)
