@@ -253,6 +253,9 @@ def run_b200(args):
                                 "launches": iso["launches"], "avg_launch_us": round(iso["avg_us"], 2),
                                 "bytes": iso["bytes"]}}
 
+    # ---- the preprocessing transforms one by one (all six of tools.py:623-630), device-resident page, warm ----
+    pre_table = preprocess_table(torch, preprocess, synth, host_pages[0][0], peak) if rank == 0 else None
+
     if rank == 0:
         reads = args.steps * B * world
         value = reads / (total_ms_max * 1e-3)
@@ -272,6 +275,7 @@ def run_b200(args):
             "e2e": {"value": round(e2e_steps * B * world / e2e_s_max, 4), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "api": "tools.preprocess_image/run_ocr/compare_versions/merge_versions on PNG files"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "preprocess_kernels": pre_table,
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(cfg, host_pages[0][0], P)
@@ -279,6 +283,39 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def preprocess_table(torch, preprocess, synth, page, peak_gbs):
+    """Each transform of tools.py:623-630 timed alone on one device-resident 1024x768 RGB page (CUDA events on the
+    current stream, median of 7 after 3 warm-up calls; the page + outputs are far below L2 size, so these are
+    L2-warm figures).  bytes = page read once + result written once.  remove_lines runs on the ruled
+    version of the page (an unruled page returns after the 0.2 ms mask)."""
+    x = preprocess.to_device(page)
+    ruled = preprocess.to_device(synth.rule_lines(page))
+    H, W = page.shape[:2]
+    cases = {"high_contrast": (lambda: preprocess.high_contrast(x), 4 * H * W, "hbm"),
+             "binarize": (lambda: preprocess.binarize(x), 4 * H * W, "hbm"),
+             "sharpen": (lambda: preprocess.sharpen(x), 6 * H * W, "hbm"),
+             "deskew": (lambda: preprocess.deskew(x), 6 * H * W, "hbm"),
+             "denoise": (lambda: preprocess.denoise(x), 6 * H * W, "integer ALU / shared memory (441 x 49 comparisons per pixel)"),
+             "remove_lines": (lambda: preprocess.remove_lines(ruled), 6 * H * W, "latency (ordered fast march, one warp per ruled line)")}
+    out = {}
+    for name, (fn, nbytes, bound) in cases.items():
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(7):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = sorted(ts)[len(ts) // 2]
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 4), "algorithmic_gbs": round(gbs, 1), "frac_hbm_peak": round(gbs / peak_gbs, 4),
+                     "bound": bound}
+    return out
 
 
 # ─────────────────────────────── CPU baseline / reference arm ───────────────────────────────
@@ -310,7 +347,9 @@ def cpu_sample(cfg, page, P=1):
     texts = [synth.text(11 + i, NEW_TOKENS) for i in range(3)]
     t_text, text_detail = cpu_path.text_ops_cpu(texts)
     est_step = P * (t_pre + 3 * (t_ip + rd["est_read_s"]) + t_text)
+    tt = cpu_path.transform_times_cpu(page, synth.rule_lines(page))
     detail = {"preprocess_s": round(t_pre, 4), "preprocess_backend": kind, "image_processor_s": round(t_ip, 4),
+              "transform_ms_cv2": {k: round(v * 1e3, 2) for k, v in tt.items()},
               "hf_read": {k: (round(v, 5) if isinstance(v, float) else v) for k, v in rd.items()},
               "text_ops_s": round(t_text, 3), "text": {k: (round(v, 3) if isinstance(v, float) else v) for k, v in text_detail.items()}}
     return est_step, detail, _READER.threads

@@ -57,13 +57,43 @@ def _cv_transforms():
         M = cv2.getRotationMatrix2D((w // 2, h // 2), ang, 1.0)
         return cv2.warpAffine(a, M, (w, h), flags=cv2.INTER_CUBIC, borderMode=cv2.BORDER_REPLICATE)
 
-    return {"high_contrast": high_contrast, "binarize": binarize, "sharpen": sharpen, "deskew": deskew}, "cv2"
+    def denoise(a):                                     # tools.py:582-587
+        if a.ndim == 3:
+            return cv2.fastNlMeansDenoisingColored(a, None, 10, 10, 7, 21)
+        return cv2.fastNlMeansDenoising(a, None, 10, 7, 21)
+
+    def remove_lines(a):                                # tools.py:598-617
+        g = gray_of(a)
+        hk = cv2.getStructuringElement(cv2.MORPH_RECT, (g.shape[1] // 4, 1))
+        m = cv2.morphologyEx(cv2.adaptiveThreshold(cv2.bitwise_not(g), 255, cv2.ADAPTIVE_THRESH_MEAN_C,
+                                                   cv2.THRESH_BINARY, 15, -2), cv2.MORPH_OPEN, hk, iterations=1)
+        m = cv2.dilate(m, cv2.getStructuringElement(cv2.MORPH_RECT, (1, 3)))
+        return cv2.inpaint(a, m, 3, cv2.INPAINT_TELEA)
+
+    return {"high_contrast": high_contrast, "binarize": binarize, "sharpen": sharpen, "deskew": deskew,
+            "denoise": denoise, "remove_lines": remove_lines}, "cv2"
 
 
 def _np_transforms():
     from . import image_ref as R
-    return {"high_contrast": lambda a: R.clahe(R.rgb2gray(a)), "binarize": lambda a: R.adaptive_threshold(R.rgb2gray(a)),
-            "sharpen": R.sharpen, "deskew": R.deskew}, "numpy-port"
+    return dict(R.TRANSFORMS), "numpy-port"
+
+
+def transform_times_cpu(page: np.ndarray, ruled: np.ndarray) -> dict:
+    """Seconds of each single transform of tools.py:623-630 on one page with the reference's own cv2 calls (second of two
+    runs; remove_lines on the ruled page).  Empty when cv2 is missing: the numpy port of NLM takes minutes per page."""
+    try:
+        tf, _ = _cv_transforms()
+    except ImportError:
+        return {}
+    out = {}
+    for name, fn in tf.items():
+        a = ruled if name == "remove_lines" else page
+        fn(a)
+        t0 = time.perf_counter()
+        fn(a)
+        out[name] = time.perf_counter() - t0
+    return out
 
 
 def preprocess_cpu(page: np.ndarray, strategies=STRATEGIES):
