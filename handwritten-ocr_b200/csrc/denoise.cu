@@ -3,8 +3,9 @@
 // Everything is integer arithmetic (the weight table, the Lab cube-root table and the Lab coefficients are built
 // once on the host with the float / double steps OpenCV uses and uploaded).
 //
-//   nlm_kernel<CN>:   one warp per 26 x 32 output tile.  Lane l owns column l - 3 of the tile: for each of the
-//                     441 search displacements it walks 38 rows, keeps the running 7-row column sum of squared
+//   nlm_kernel<CN>:   one CTA of 4 warps per 26 x 32 output tile, each warp taking a quarter of the 441 search
+//                     displacements (integer partial sums meet in shared memory: order-free, so still exact).
+//                     Lane l owns column l - 3 of the tile: for each displacement it walks 38 rows, keeps the running 7-row column sum of squared
 //                     differences in a register (ring of the last 7 values), gets the 7-column patch sum with three
 //                     warp shuffles, looks the weight up in a shared-memory table and accumulates weight and
 //                     weight * pixel in registers (32 rows x (1 + CN) accumulators).  The reflect-101 extended tile
@@ -38,25 +39,30 @@ template <int CN> struct NlmPix;
 template <> struct NlmPix<1> { typedef uint8_t T; };
 template <> struct NlmPix<2> { typedef uint16_t T; };
 
+constexpr int NLM_NW = 4;              // warps per tile: each takes a quarter of the 441 displacements
+
 template <int CN>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32 * NLM_NW)
 nlm_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H, int W, const uint16_t *__restrict__ lut_g) {
   typedef typename NlmPix<CN>::T T;
   constexpr int PER = 4 / CN;                         // pixels of the lane's own column per 32-bit register
   constexpr int NPACK = (NLM_DROWS + PER - 1) / PER;
+  constexpr int NSEARCH = (2 * NLM_SH + 1) * (2 * NLM_SH + 1);
   __shared__ T ext[NLM_ER * NLM_EC];
   __shared__ uint16_t lut[NLM_LUT];
-  const int lane = threadIdx.x;
+  __shared__ uint32_t acc[(1 + CN) * NLM_ROWS * 32];  // the warps' partial sums meet here (integer: order-free)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tx0 = blockIdx.x * NLM_COLS, ty0 = blockIdx.y * NLM_ROWS;
   const T *im = reinterpret_cast<const T *>(src) + (size_t)blockIdx.z * H * W;
   T *om = reinterpret_cast<T *>(dst) + (size_t)blockIdx.z * H * W;
-  for (int i = lane; i < NLM_LUT; i += 32) lut[i] = lut_g[i];
-  for (int er = 0; er < NLM_ER; ++er) {
+  for (int i = threadIdx.x; i < NLM_LUT; i += 32 * NLM_NW) lut[i] = lut_g[i];
+  for (int i = threadIdx.x; i < (1 + CN) * NLM_ROWS * 32; i += 32 * NLM_NW) acc[i] = 0;
+  for (int er = warp; er < NLM_ER; er += NLM_NW) {
     const int gy = reflect101_any(ty0 - NLM_B + er, H);
     for (int ec = lane; ec < NLM_EC; ec += 32)
       ext[er * NLM_EC + ec] = im[(size_t)gy * W + reflect101_any(tx0 - NLM_B + ec, W)];
   }
-  __syncwarp();
+  __syncthreads();
 
   uint32_t apack[NPACK];
 #pragma unroll
@@ -78,49 +84,55 @@ nlm_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H, in
     if (CN == 2) est1[j] = 0;
   }
 
-  for (int dy = -NLM_SH; dy <= NLM_SH; ++dy) {
+  const int d_end = (warp + 1) * NSEARCH / NLM_NW;
 #pragma unroll 1
-    for (int dx = -NLM_SH; dx <= NLM_SH; ++dx) {
-      const T *bp = ext + (NLM_SH + dy) * NLM_EC + lane + NLM_SH + dx;
-      uint32_t col = 0, dring[7], bring[4];
+  for (int d = warp * NSEARCH / NLM_NW; d < d_end; ++d) {
+    const int dy = d / (2 * NLM_SH + 1) - NLM_SH, dx = d % (2 * NLM_SH + 1) - NLM_SH;
+    const T *bp = ext + (NLM_SH + dy) * NLM_EC + lane + NLM_SH + dx;
+    uint32_t col = 0, dring[7], bring[4];
 #pragma unroll
-      for (int r = 0; r < NLM_DROWS; ++r) {
-        const uint32_t a = (apack[r / PER] >> ((r % PER) * 8 * CN)) & (CN == 1 ? 0xffu : 0xffffu);
-        const uint32_t b = bp[r * NLM_EC];
-        const uint32_t ad = __vabsdiffu4(a, b);
-        const uint32_t dd = __dp4a(ad, ad, 0u);
-        col += dd;
-        if (r >= 7) col -= dring[r % 7];
-        dring[r % 7] = dd;
-        bring[r % 4] = b;
-        if (r >= 6) {
-          const int j = r - 6;
-          const uint32_t t2 = col + __shfl_down_sync(0xffffffffu, col, 1);
-          const uint32_t t4 = t2 + __shfl_down_sync(0xffffffffu, t2, 2);          // columns l .. l+3
-          const uint32_t s7 = __shfl_up_sync(0xffffffffu, t4, 3) + t4 - col;      // columns l-3 .. l+3
-          const uint32_t w = lut[min(s7 >> NLM_SHIFT, (uint32_t)(NLM_LUT - 1))];
-          const uint32_t bc = bring[(r - 3) % 4];
-          wsum[j] += w;
-          if (CN == 1) {
-            est0[j] += w * bc;
-          } else {
-            est0[j] += w * (bc & 0xffu);
-            est1[j] += w * (bc >> 8);
-          }
+    for (int r = 0; r < NLM_DROWS; ++r) {
+      const uint32_t a = (apack[r / PER] >> ((r % PER) * 8 * CN)) & (CN == 1 ? 0xffu : 0xffffu);
+      const uint32_t b = bp[r * NLM_EC];
+      const uint32_t ad = __vabsdiffu4(a, b);
+      const uint32_t dd = __dp4a(ad, ad, 0u);
+      col += dd;
+      if (r >= 7) col -= dring[r % 7];
+      dring[r % 7] = dd;
+      bring[r % 4] = b;
+      if (r >= 6) {
+        const int j = r - 6;
+        const uint32_t t2 = col + __shfl_down_sync(0xffffffffu, col, 1);
+        const uint32_t t4 = t2 + __shfl_down_sync(0xffffffffu, t2, 2);          // columns l .. l+3
+        const uint32_t s7 = __shfl_up_sync(0xffffffffu, t4, 3) + t4 - col;      // columns l-3 .. l+3
+        const uint32_t w = lut[min(s7 >> NLM_SHIFT, (uint32_t)(NLM_LUT - 1))];
+        const uint32_t bc = bring[(r - 3) % 4];
+        wsum[j] += w;
+        if (CN == 1) {
+          est0[j] += w * bc;
+        } else {
+          est0[j] += w * (bc & 0xffu);
+          est1[j] += w * (bc >> 8);
         }
       }
     }
   }
 
-  const int x = tx0 + lane - 3;
-  if (lane < 3 || lane >= 3 + NLM_COLS || x >= W) return;
 #pragma unroll
   for (int j = 0; j < NLM_ROWS; ++j) {
+    atomicAdd(&acc[j * 32 + lane], wsum[j]);
+    atomicAdd(&acc[(NLM_ROWS + j) * 32 + lane], est0[j]);
+    if (CN == 2) atomicAdd(&acc[(2 * NLM_ROWS + j) * 32 + lane], est1[j]);
+  }
+  __syncthreads();
+  const int x = tx0 + lane - 3;
+  if (lane < 3 || lane >= 3 + NLM_COLS || x >= W) return;
+  for (int j = warp; j < NLM_ROWS; j += NLM_NW) {
     const int y = ty0 + j;
     if (y < H) {
-      const uint32_t ws = wsum[j];
-      uint32_t o = min((est0[j] + ws / 2) / ws, 255u);
-      if (CN == 2) o |= min((est1[j] + ws / 2) / ws, 255u) << 8;
+      const uint32_t ws = acc[j * 32 + lane];
+      uint32_t o = min((acc[(NLM_ROWS + j) * 32 + lane] + ws / 2) / ws, 255u);
+      if (CN == 2) o |= min((acc[(2 * NLM_ROWS + j) * 32 + lane] + ws / 2) / ws, 255u) << 8;
       om[(size_t)y * W + x] = (T)o;
     }
   }
@@ -331,7 +343,7 @@ extern "C" int ocrb_nlm_denoise_u8(const uint8_t *src, uint8_t *dst, uint8_t *ws
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid(cdiv(W, NLM_COLS), cdiv(H, NLM_ROWS), n_img);
   if (C == 1) {
-    nlm_kernel<1><<<grid, 32, 0, st>>>(src, dst, H, W, t->w[0]);
+    nlm_kernel<1><<<grid, 32 * NLM_NW, 0, st>>>(src, dst, H, W, t->w[0]);
     return check_launch("nlm_kernel<1>");
   }
   const size_t npix = (size_t)n_img * H * W;
@@ -339,9 +351,9 @@ extern "C" int ocrb_nlm_denoise_u8(const uint8_t *src, uint8_t *dst, uint8_t *ws
   OCRB_REQUIRE(((uintptr_t)ws & 1) == 0, "nlm_denoise_u8: workspace must be 2-byte aligned");
   lbgr2lab_kernel<<<cdiv((long long)npix, 256), 256, 0, st>>>(src, L0, ab0, npix, t->cbrt_tab, host_tables().cf);
   if ((rc = check_launch("lbgr2lab_kernel"))) return rc;
-  nlm_kernel<1><<<grid, 32, 0, st>>>(L0, L1, H, W, t->w[0]);
+  nlm_kernel<1><<<grid, 32 * NLM_NW, 0, st>>>(L0, L1, H, W, t->w[0]);
   if ((rc = check_launch("nlm_kernel<1>"))) return rc;
-  nlm_kernel<2><<<grid, 32, 0, st>>>(ab0, ab1, H, W, t->w[1]);
+  nlm_kernel<2><<<grid, 32 * NLM_NW, 0, st>>>(ab0, ab1, H, W, t->w[1]);
   if ((rc = check_launch("nlm_kernel<2>"))) return rc;
   lab2lbgr_kernel<<<cdiv((long long)npix, 256), 256, 0, st>>>(L1, ab1, dst, npix, t->yf, host_tables().cf);
   return check_launch("lab2lbgr_kernel");

@@ -10,7 +10,15 @@
 //     has one segment per ruled line;
 //   * inside a segment, the four distance solves of each of the four neighbours of a popped pixel run on 16 lanes, and
 //     the <= 49 disc positions of a painted pixel are evaluated by the lanes in parallel; only the float sums are then
-//     accumulated in OpenCV's raster order (one lane per running sum), because float addition does not reassociate.
+//     accumulated in OpenCV's raster order (one lane per running sum), because float addition does not reassociate;
+//   * the two marches and the painting are decoupled (one CTA of 4 warps per segment).  The outward march (negative
+//     distances in the ring) and the inward march (arrival times of the mask pixels) read disjoint data -- the eikonal
+//     solve of a ring pixel never touches a mask pixel and vice versa, the band between them is T = 0 in both -- so they
+//     run concurrently on two warps with two queues.  The inward march does not depend on pixel VALUES at all: it only
+//     emits the list of pixels in the order OpenCV would paint them, stamping each with its position in that order.
+//     Two painter warps consume the list: "known when pixel n is painted" is stamp < n, so a painter can evaluate
+//     flags, distances and weights of job n while job n - 1 is still being painted by the other warp, and only the
+//     part that reads pixel values waits for its predecessor (a counter in shared memory).
 // The queue is a binary heap on the key (float bits of T) << 32 | insertion number, equal in order to OpenCV's sorted
 // list; only lane 0 touches it.  A segment's window of the distance field, the flags and the page rows is staged in
 // shared memory together with the heap (freshly written global data would come back from L2 at ~600 cycles a load,
@@ -18,6 +26,7 @@
 // generic pointers, and a heap that outgrows its shared part spills into the segment's global slice.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace ocrb {
 
@@ -27,6 +36,13 @@ constexpr int INP_MAX_RANGE = 7;
 // range rows away, so 2 * range + 1 clean rows already separate two segments; one more for margin
 static inline __host__ __device__ int inp_gap(int range) { return 2 * range + 2; }
 constexpr int INP_CHAINS = 10;        // Ia[3], Jx[3], Jy[3], s
+constexpr int INP_NOTYET = 0x7fffffff;
+constexpr int INP_PAINTERS = 2;
+constexpr int INP_WARPS = 2 + INP_PAINTERS;   // outward march, inward march, painters
+// a waiting warp traps instead of hanging if its partner never arrives (2^36 cycles: half a minute)
+__device__ __forceinline__ void inp_spin_check(int it, long long t0) {
+  if ((it & 1023) == 1023 && clock64() - t0 > (1ll << 36)) __trap();
+}
 
 struct InpWs {
   uint64_t *key;   // [n * ne] heap keys
@@ -36,6 +52,10 @@ struct InpWs {
   uint8_t *f;      // [n * ne] KNOWN / BAND / INSIDE of the inward march
   uint8_t *rg;     // [n * ne] ring flags of the outward march (INSIDE = ring, SEED = boundary band)
   uint8_t *rowflag;  // [n * H] image row has mask pixels
+  uint64_t *key2;  // second queue (the two marches run concurrently)
+  int32_t *pos2;
+  int32_t *stamp;  // [n * ne] paint order of a mask pixel (NOTYET until the inward march reaches it), -1 elsewhere
+  int32_t *job;    // [n * ne] pixels in paint order, per segment at the offset of its first mask row
 };
 
 static inline int inp_maxseg(int H) { return (H + inp_gap(1)) / (inp_gap(1) + 1) + 1; }   // bound for every radius
@@ -55,6 +75,10 @@ static size_t inp_layout(InpWs *w, uint8_t *base, int n, int H, int W) {
   w->f = take(ne);
   w->rg = take(ne);
   w->rowflag = take((size_t)n * H);
+  w->key2 = (uint64_t *)take(ne * 8);
+  w->pos2 = (int32_t *)take(ne * 4);
+  w->stamp = (int32_t *)take(ne * 4);
+  w->job = (int32_t *)take(ne * 4);
   return off;
 }
 
@@ -83,6 +107,7 @@ inp_init_kernel(const uint8_t *__restrict__ mask, InpWs w, int H, int W, int ran
   w.f[p] = in ? F_INSIDE : F_KNOWN;
   w.rg[p] = band ? F_SEED : ring ? F_INSIDE : F_KNOWN;
   w.t[p] = band ? 0.f : 1.0e6f;
+  w.stamp[p] = in ? INP_NOTYET : -1;
   if (in) w.rowflag[(size_t)img * H + i - 1] = 1;
 }
 
@@ -195,12 +220,13 @@ __device__ __forceinline__ int heap_pop(Heap &h, int lane) {
 
 // Boundary-band pixels of the segment, in raster order, as the initial queue content: equal keys T = 0 with rising
 // insertion numbers form a sorted array, which is a valid heap.  All lanes take part (ballot compaction).
-__device__ int heap_seed(Heap &h, const uint8_t *rg, uint8_t marker, int row0, int row1, int ec, int lane) {
+__device__ int heap_seed(Heap &h, const uint8_t *rg, int row0, int row1, int ec, int lane) {
   int n = 0;
   const int total = (row1 - row0 + 1) * ec;
   for (int base = 0; base < total; base += 32) {
     const int q = base + lane;
-    const bool is = q < total && rg[row0 * ec + q] == marker;
+    const uint8_t v = q < total ? rg[row0 * ec + q] : (uint8_t)F_KNOWN;
+    const bool is = v == F_SEED || v == F_SEED_DONE;      // the outward march flips SEED -> SEED_DONE while it runs
     const unsigned b = __ballot_sync(0xffffffffu, is);
     if (is) {
       const int idx = n + __popc(b & ((1u << lane) - 1));
@@ -251,200 +277,314 @@ __device__ __forceinline__ bool neighbour_dist(const uint8_t *f, const float *t,
   return valid;
 }
 
-// ───────────── one painted pixel ─────────────
-template <int C>
-__device__ void paint_pixel(const uint8_t *f, const float *t, uint8_t *out, int er, int ec, int range, int p, int lane,
-                            const float *dst_tab, float *terms) {
-  const int W = ec - 2, D = 2 * range + 1;
-  const int i = p / ec, j = p - i * ec;
-  const float tij = t[p];
-  float gx, gy;
-  if (f[p + 1] != F_INSIDE)
-    gx = f[p - 1] != F_INSIDE ? (t[p + 1] - t[p - 1]) * 0.5f : t[p + 1] - tij;
-  else
-    gx = f[p - 1] != F_INSIDE ? tij - t[p - 1] : 0.f;
-  if (f[p + ec] != F_INSIDE)
-    gy = f[p - ec] != F_INSIDE ? (t[p + ec] - t[p - ec]) * 0.5f : t[p + ec] - tij;
-  else
-    gy = f[p - ec] != F_INSIDE ? tij - t[p - ec] : 0.f;
+// ───────────── one painted pixel, in two parts ─────────────
+struct InpSync {        // shared-memory mailbox of a segment's four warps
+  int jobs_ready;       // pixels emitted by the inward march so far
+  int queue_total;      // -1 while the inward march runs, then the number of pixels
+  int outside_done;     // ring distances final (negated)
+  int painted_upto;     // pixels 0 .. painted_upto-1 carry their final value
+};
 
-  for (int q = lane; q < D * D; q += 32) {
-    const int dk = q / D - range, dl = q - (q / D) * D - range;
-    const int k = i + dk, l = j + dl;
-    float tr[INP_CHAINS];
-#pragma unroll
-    for (int c = 0; c < INP_CHAINS; ++c) tr[c] = 0.f;
-    if (k > 0 && l > 0 && k < er - 1 && l < ec - 1 && dk * dk + dl * dl <= range * range) {
-      const int kl = k * ec + l;
-      if (f[kl] != F_INSIDE) {
-        const float ry = (float)(-dk), rx = (float)(-dl);
-        const float lev = (float)(1. / (1 + fabs((double)(t[kl] - tij))));
-        float dir = rx * gx + ry * gy;
-        if ((double)fabsf(dir) <= 0.01) dir = 0.000001f;
-        const float w = fabsf(dst_tab[q] * lev * dir);
-        const int km = k - 1 + (k == 1), kp = k - 1 - (k == er - 2);
-        const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ec - 2);
-        const bool fr = f[kl + 1] != F_INSIDE, fl = f[kl - 1] != F_INSIDE;
-        const bool fd = f[kl + ec] != F_INSIDE, fu = f[kl - ec] != F_INSIDE;
-        // the two pixels of each difference and its factor (central differences are doubled, not halved, in OpenCV)
-        const int xa = (km * W + (fr ? lp + 1 : lp)) * C, xb = (km * W + (fl ? lm - 1 : lm)) * C;
-        const int ya = ((fd ? kp + 1 : kp) * W + lm) * C, yb = ((fu ? km - 1 : km) * W + lm) * C;
-        const float sx = fr ? (fl ? 2.0f : 1.0f) : (fl ? 1.0f : 0.f), sy = fd ? (fu ? 2.0f : 1.0f) : (fu ? 1.0f : 0.f);
-        const int ctr = ((k - 1) * W + (l - 1)) * C;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float gix = (float)((int)out[xa + c] - (int)out[xb + c]) * sx;
-          const float giy = (float)((int)out[ya + c] - (int)out[yb + c]) * sy;
-          tr[c] = w * (float)out[ctr + c];
-          tr[3 + c] = -(w * (gix * rx));       // Jx -= v  ==  Jx += -v
-          tr[6 + c] = -(w * (giy * ry));
-        }
-        tr[9] = w;
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < INP_CHAINS; ++c) terms[q * INP_CHAINS + c] = tr[c];
-  }
-  __syncwarp();
-  // running sums in raster order: lane c < 3 -> Ia[c], 3..5 -> Jx, 6..8 -> Jy, 9 -> s
-  float acc = lane == 9 ? 1.0e-20f : 0.f;
-  if (lane < INP_CHAINS)
-    for (int q = 0; q < D * D; ++q) acc += terms[q * INP_CHAINS + lane];
-  const int c = lane < C ? lane : 0;
-  const float Ia = __shfl_sync(0xffffffffu, acc, c), Jx = __shfl_sync(0xffffffffu, acc, 3 + c);
-  const float Jy = __shfl_sync(0xffffffffu, acc, 6 + c), s = __shfl_sync(0xffffffffu, acc, 9);
-  if (lane < C) {
-    const float sat = (float)(Ia / s + (Jx + Jy) / (sqrt((double)(Jx * Jx + Jy * Jy)) + (double)1.0e-20f));
-    const int v = __float2int_rn(sat + 0.5f);
-    out[((i - 1) * W + (j - 1)) * C + lane] = (uint8_t)min(max(v, 0), 255);
-  }
-  __syncwarp();
+struct PosState {       // what one disc position contributes, everything that does not depend on pixel values
+  float w, sx, sy;
+  int xa, xb, ya, yb, ctr;   // ctr < 0: position contributes nothing
+};
+
+__device__ __forceinline__ bool inp_known(const int32_t *stamp, int m0, int m1, int q, int n) {
+  return q < m0 || q >= m1 || stamp[q] < n;
 }
 
-// ───────────── one warp per (segment, page) ─────────────
-// Dynamic shared memory: [terms | dst_tab | window of t, f, rg, page rows (when it fits) | heap].
-constexpr int INP_FIXED_SMEM = ((2 * INP_MAX_RANGE + 1) * (2 * INP_MAX_RANGE + 1) * (INP_CHAINS + 1) * 4 + 15) & ~15;
-constexpr int INP_MIN_HEAP = 1024;    // entries kept in shared memory at the very least
+template <int C>
+__device__ __forceinline__ void paint_position(PosState &st, int q, int i, int j, int n, float tij, float gx, float gy,
+                                               const float *t, const int32_t *stamp, int m0, int m1, int er, int ec,
+                                               int range, const float *dst_tab) {
+  const int W = ec - 2, D = 2 * range + 1;
+  st.ctr = -1;
+  if (q >= D * D) return;
+  const int dk = q / D - range, dl = q - (q / D) * D - range;
+  const int k = i + dk, l = j + dl;
+  if (!(k > 0 && l > 0 && k < er - 1 && l < ec - 1 && dk * dk + dl * dl <= range * range)) return;
+  const int kl = k * ec + l;
+  if (!inp_known(stamp, m0, m1, kl, n)) return;
+  const float ry = (float)(-dk), rx = (float)(-dl);
+  const float lev = (float)(1. / (1 + fabs((double)(t[kl] - tij))));
+  float dir = rx * gx + ry * gy;
+  if ((double)fabsf(dir) <= 0.01) dir = 0.000001f;
+  st.w = fabsf(dst_tab[q] * lev * dir);
+  const int km = k - 1 + (k == 1), kp = k - 1 - (k == er - 2);
+  const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ec - 2);
+  const bool fr = inp_known(stamp, m0, m1, kl + 1, n), fl = inp_known(stamp, m0, m1, kl - 1, n);
+  const bool fd = inp_known(stamp, m0, m1, kl + ec, n), fu = inp_known(stamp, m0, m1, kl - ec, n);
+  // the two pixels of each difference and its factor (central differences are doubled, not halved, in OpenCV)
+  st.xa = (km * W + (fr ? lp + 1 : lp)) * C;
+  st.xb = (km * W + (fl ? lm - 1 : lm)) * C;
+  st.ya = ((fd ? kp + 1 : kp) * W + lm) * C;
+  st.yb = ((fu ? km - 1 : km) * W + lm) * C;
+  st.sx = fr ? (fl ? 2.0f : 1.0f) : (fl ? 1.0f : 0.f);
+  st.sy = fd ? (fu ? 2.0f : 1.0f) : (fu ? 1.0f : 0.f);
+  st.ctr = ((k - 1) * W + (l - 1)) * C;
+}
 
 template <int C>
-__global__ void __launch_bounds__(32, 1)
-inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, int maxseg, int smem_bytes) {
+__device__ __forceinline__ void paint_terms(const PosState &st, int q, int range, const uint8_t *out, float *terms) {
+  const int D = 2 * range + 1;
+  if (q >= D * D) return;
+  float tr[INP_CHAINS];
+#pragma unroll
+  for (int c = 0; c < INP_CHAINS; ++c) tr[c] = 0.f;
+  if (st.ctr >= 0) {
+    const float ry = (float)(range - q / D), rx = (float)(range - (q - (q / D) * D));
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float gix = (float)((int)out[st.xa + c] - (int)out[st.xb + c]) * st.sx;
+      const float giy = (float)((int)out[st.ya + c] - (int)out[st.yb + c]) * st.sy;
+      tr[c] = st.w * (float)out[st.ctr + c];
+      tr[3 + c] = -(st.w * (gix * rx));       // Jx -= v  ==  Jx += -v
+      tr[6 + c] = -(st.w * (giy * ry));
+    }
+    tr[9] = st.w;
+  }
+#pragma unroll
+  for (int c = 0; c < INP_CHAINS; ++c) terms[q * INP_CHAINS + c] = tr[c];
+}
+
+// A painter warp: jobs k, k + INP_PAINTERS, ...
+template <int C>
+__device__ void painter_loop(int k, int lane, volatile InpSync *sy, const int32_t *job, const int32_t *stamp, int m0, int m1,
+                             const float *t, uint8_t *out, int er, int ec, int range, const float *dst_tab, float *terms) {
+  const int W = ec - 2, D = 2 * range + 1, DD = D * D;
+  bool outside_seen = false;
+  for (int n = k;; n += INP_PAINTERS) {
+    int ok = 1;
+    if (lane == 0) {
+      const long long t0 = clock64();
+      for (int it = 0;; ++it) {
+        if (sy->jobs_ready > n) break;
+        const int tot = sy->queue_total;
+        if (tot >= 0 && n >= tot) {
+          ok = 0;
+          break;
+        }
+        inp_spin_check(it, t0);
+      }
+      if (ok && !outside_seen)
+        for (int it = 0; !sy->outside_done; ++it) inp_spin_check(it, t0);
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) break;
+    outside_seen = true;
+    __threadfence_block();
+    const int p = job[n];
+    const int i = p / ec, j = p - i * ec;
+    const float tij = t[p];
+    float gx, gy;
+    {
+      const bool r = inp_known(stamp, m0, m1, p + 1, n), l = inp_known(stamp, m0, m1, p - 1, n);
+      const bool d = inp_known(stamp, m0, m1, p + ec, n), u = inp_known(stamp, m0, m1, p - ec, n);
+      gx = r ? (l ? (t[p + 1] - t[p - 1]) * 0.5f : t[p + 1] - tij) : (l ? tij - t[p - 1] : 0.f);
+      gy = d ? (u ? (t[p + ec] - t[p - ec]) * 0.5f : t[p + ec] - tij) : (u ? tij - t[p - ec] : 0.f);
+    }
+    // everything that does not read pixel values: the first two rounds of disc positions (all of them for radius <= 3)
+    PosState s0, s1;
+    paint_position<C>(s0, lane, i, j, n, tij, gx, gy, t, stamp, m0, m1, er, ec, range, dst_tab);
+    paint_position<C>(s1, lane + 32, i, j, n, tij, gx, gy, t, stamp, m0, m1, er, ec, range, dst_tab);
+    if (lane == 0) {
+      const long long t0 = clock64();
+      for (int it = 0; sy->painted_upto != n; ++it) inp_spin_check(it, t0);
+    }
+    __syncwarp();
+    __threadfence_block();
+    paint_terms<C>(s0, lane, range, out, terms);
+    paint_terms<C>(s1, lane + 32, range, out, terms);
+    for (int q = lane + 64; q < DD; q += 32) {          // radius > 3 only
+      PosState sx_;
+      paint_position<C>(sx_, q, i, j, n, tij, gx, gy, t, stamp, m0, m1, er, ec, range, dst_tab);
+      paint_terms<C>(sx_, q, range, out, terms);
+    }
+    __syncwarp();
+    // running sums in raster order: lane c < 3 -> Ia[c], 3..5 -> Jx, 6..8 -> Jy, 9 -> s
+    float acc = lane == 9 ? 1.0e-20f : 0.f;
+    if (lane < INP_CHAINS)
+      for (int q = 0; q < DD; ++q) acc += terms[q * INP_CHAINS + lane];
+    const int c = lane < C ? lane : 0;
+    const float Ia = __shfl_sync(0xffffffffu, acc, c), Jx = __shfl_sync(0xffffffffu, acc, 3 + c);
+    const float Jy = __shfl_sync(0xffffffffu, acc, 6 + c), s = __shfl_sync(0xffffffffu, acc, 9);
+    if (lane < C) {
+      const float sat = (float)(Ia / s + (Jx + Jy) / (sqrt((double)(Jx * Jx + Jy * Jy)) + (double)1.0e-20f));
+      const int v = __float2int_rn(sat + 0.5f);
+      out[((i - 1) * W + (j - 1)) * C + lane] = (uint8_t)min(max(v, 0), 255);
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) sy->painted_upto = n + 1;
+  }
+}
+
+// ───────────── one CTA (4 warps) per (segment, page) ─────────────
+// Dynamic shared memory: [mailbox | dst_tab | painters' terms | window of t, f, rg, page rows, stamps, jobs (when it
+// fits) | two heaps].
+constexpr int INP_DD_MAX = (2 * INP_MAX_RANGE + 1) * (2 * INP_MAX_RANGE + 1);
+constexpr int INP_MIN_HEAP = 512;     // entries each queue keeps in shared memory at the very least
+__host__ __device__ inline size_t inp_a16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+template <int C>
+__global__ void __launch_bounds__(32 * INP_WARPS, 1)
+inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, int maxseg, int smem_bytes, int stage_ok) {
   extern __shared__ __align__(16) uint8_t smem[];
-  float *terms = reinterpret_cast<float *>(smem);
-  float *dst_tab = terms + (2 * INP_MAX_RANGE + 1) * (2 * INP_MAX_RANGE + 1) * INP_CHAINS;
-  const int lane = threadIdx.x, img = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, img = blockIdx.y;
   const int32_t *seg = w.seg + (size_t)img * (1 + 2 * maxseg);
   if ((int)blockIdx.x >= seg[0]) return;
-  const int er = H + 2, ec = W + 2;
+  const int er = H + 2, ec = W + 2, D = 2 * range + 1, DD = D * D;
   const int r0 = seg[1 + 2 * blockIdx.x], r1 = seg[2 + 2 * blockIdx.x];      // extended rows holding mask pixels
   const size_t ne = (size_t)er * ec;
+  volatile InpSync *sy = reinterpret_cast<volatile InpSync *>(smem);
+  float *dst_tab = reinterpret_cast<float *>(smem + 32);
+  float *terms_all = dst_tab + INP_DD_MAX;
+  uint8_t *sp = smem + inp_a16(32 + INP_DD_MAX * 4 + (size_t)INP_PAINTERS * DD * INP_CHAINS * 4);
   uint8_t *f = w.f + img * ne, *rg = w.rg + img * ne;
   float *t = w.t + img * ne;
+  int32_t *stamp = w.stamp + img * ne;
   uint8_t *out = dst + (size_t)img * H * W * C;
   const int lo = max(r0 - range, 0), hi = min(r1 + range, er - 1);
-  // everything the march reads or writes lies in extended rows wlo..whi and page rows olo..ohi
+  // everything the marches read or write lies in extended rows wlo..whi and page rows olo..ohi
   const int wlo = max(r0 - range - 1, 0), whi = min(r1 + range + 1, er - 1);
   const int olo = max(wlo - 1, 0), ohi = min(whi - 1, H - 1);
-  const size_t wpx = (size_t)(whi - wlo + 1) * ec, obytes = (size_t)(ohi - olo + 1) * W * C;
-  const size_t win_bytes = ((wpx * 4 + 15) & ~(size_t)15) + 2 * ((wpx + 15) & ~(size_t)15) + ((obytes + 15) & ~(size_t)15);
-  const bool staged = INP_FIXED_SMEM + win_bytes + (size_t)INP_MIN_HEAP * 12 <= (size_t)smem_bytes;
-  uint8_t *sp = smem + INP_FIXED_SMEM;
-  uint8_t *out_s = nullptr;
+  const int m0 = r0 * ec, m1 = (r1 + 1) * ec;                 // the mask rows: stamps and jobs exist only there
+  int32_t *job = w.job + img * ne + m0;
+  const size_t wpx = (size_t)(whi - wlo + 1) * ec, obytes = (size_t)(ohi - olo + 1) * W * C, mpx = (size_t)(m1 - m0);
+  const size_t win_bytes = inp_a16(wpx * 4) + 2 * inp_a16(wpx) + inp_a16(obytes) + 2 * inp_a16(mpx * 4);
+  const bool staged = stage_ok && (size_t)(sp - smem) + win_bytes + 2 * (size_t)INP_MIN_HEAP * 12 <= (size_t)smem_bytes;
   if (staged) {
     float *t_s = reinterpret_cast<float *>(sp);
-    sp += (wpx * 4 + 15) & ~(size_t)15;
+    sp += inp_a16(wpx * 4);
     uint8_t *f_s = sp;
-    sp += (wpx + 15) & ~(size_t)15;
+    sp += inp_a16(wpx);
     uint8_t *rg_s = sp;
-    sp += (wpx + 15) & ~(size_t)15;
-    out_s = sp;
-    sp += (obytes + 15) & ~(size_t)15;
+    sp += inp_a16(wpx);
+    uint8_t *out_s = sp;
+    sp += inp_a16(obytes);
+    int32_t *stamp_s = reinterpret_cast<int32_t *>(sp);
+    sp += inp_a16(mpx * 4);
+    int32_t *job_s = reinterpret_cast<int32_t *>(sp);
+    sp += inp_a16(mpx * 4);
     const size_t w0 = (size_t)wlo * ec;
-    for (size_t q = lane; q < wpx; q += 32) {
+    for (size_t q = threadIdx.x; q < wpx; q += 32 * INP_WARPS) {
       t_s[q] = t[w0 + q];
       f_s[q] = f[w0 + q];
       rg_s[q] = rg[w0 + q];
     }
+    for (size_t q = threadIdx.x; q < mpx; q += 32 * INP_WARPS) stamp_s[q] = stamp[m0 + q];
     const uint8_t *og = out + (size_t)olo * W * C;
-    for (size_t q = lane; q < obytes; q += 32) out_s[q] = og[q];
+    for (size_t q = threadIdx.x; q < obytes; q += 32 * INP_WARPS) out_s[q] = og[q];
     t = t_s - w0;            // generic pointers biased so that extended / page coordinates index them unchanged
     f = f_s - w0;
     rg = rg_s - w0;
     out = out_s - (size_t)olo * W * C;
+    stamp = stamp_s - m0;
+    job = job_s;
   }
-  Heap h;
-  h.cap = (int)((smem + smem_bytes - sp) / 12);
-  h.sT = reinterpret_cast<uint32_t *>(sp);
-  h.sS = h.sT + h.cap;
-  h.sP = reinterpret_cast<int32_t *>(h.sS + h.cap);
-  const size_t slice = (size_t)(hi - lo + 1) * ec;          // the segment's part of the global spill arrays
-  h.gT = reinterpret_cast<uint32_t *>(w.key + img * ne + (size_t)lo * ec);
-  h.gS = h.gT + slice;
-  h.gP = w.pos + img * ne + (size_t)lo * ec;
-  const int D = 2 * range + 1;
-  for (int q = lane; q < D * D; q += 32) {
+  for (int q = threadIdx.x; q < DD; q += 32 * INP_WARPS) {
     const int dk = q / D - range, dl = q % D - range;
     const float len2 = (float)(dk * dk + dl * dl);
     dst_tab[q] = len2 > 0.f ? (float)(1. / (len2 * sqrt((double)len2))) : 0.f;
   }
+  if (threadIdx.x == 0) {
+    sy->jobs_ready = 0;
+    sy->queue_total = -1;
+    sy->outside_done = 0;
+    sy->painted_upto = 0;
+  }
+  __syncthreads();
 
-  // march outwards through the ring: distances there, negated afterwards
-  __syncwarp();
-  heap_seed(h, rg, F_SEED, r0 - 1, r1 + 1, ec, lane);
-  for (;;) {
-    const int p = heap_pop(h, lane);
-    if (p < 0) break;
-    if (lane == 0) rg[p] = rg[p] == F_SEED ? F_SEED_DONE : F_CHANGE;
-    __syncwarp();
-    int nb;
-    float d;
-    const bool valid = neighbour_dist(rg, t, p, er, ec, lane, nb, d);
-    __syncwarp();
+  if (warp < 2) {
+    // the two queues split what is left of the shared memory; each spills into its own global slice
+    Heap h;
+    const int cap = (int)((smem + smem_bytes - sp) / 24);
+    uint8_t *hp = sp + (size_t)warp * cap * 12;
+    h.cap = cap;
+    h.sT = reinterpret_cast<uint32_t *>(hp);
+    h.sS = h.sT + cap;
+    h.sP = reinterpret_cast<int32_t *>(h.sS + cap);
+    const size_t slice = (size_t)(hi - lo + 1) * ec;
+    uint64_t *gk = (warp == 0 ? w.key : w.key2) + img * ne + (size_t)lo * ec;
+    h.gT = reinterpret_cast<uint32_t *>(gk);
+    h.gS = h.gT + slice;
+    h.gP = (warp == 0 ? w.pos : w.pos2) + img * ne + (size_t)lo * ec;
+    heap_seed(h, rg, r0 - 1, r1 + 1, ec, lane);
+    if (warp == 0) {
+      // march outwards through the ring: distances there, negated afterwards
+      for (;;) {
+        const int p = heap_pop(h, lane);
+        if (p < 0) break;
+        if (lane == 0) rg[p] = rg[p] == F_SEED ? F_SEED_DONE : F_CHANGE;
+        __syncwarp();
+        int nb;
+        float d;
+        const bool valid = neighbour_dist(rg, t, p, er, ec, lane, nb, d);
+        __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const bool vq = __shfl_sync(0xffffffffu, (int)valid, 4 * q) != 0;
-      const float dq = __shfl_sync(0xffffffffu, d, 4 * q);
-      const int nq = __shfl_sync(0xffffffffu, nb, 4 * q);
-      if (vq) {
-        if (lane == 0) {
-          t[nq] = dq;
-          rg[nq] = F_BAND;
+        for (int q = 0; q < 4; ++q) {
+          const bool vq = __shfl_sync(0xffffffffu, (int)valid, 4 * q) != 0;
+          const float dq = __shfl_sync(0xffffffffu, d, 4 * q);
+          const int nq = __shfl_sync(0xffffffffu, nb, 4 * q);
+          if (vq) {
+            if (lane == 0) {
+              t[nq] = dq;
+              rg[nq] = F_BAND;
+            }
+            heap_push(h, nq, dq, lane);
+          }
         }
-        heap_push(h, nq, dq, lane);
       }
-    }
-  }
-  for (int q = lo * ec + lane; q < (hi + 1) * ec; q += 32)
-    if (rg[q] == F_CHANGE || rg[q] == F_SEED_DONE) t[q] = -t[q];
-  __syncwarp();
-
-  // march inwards, painting every pixel when the front reaches it
-  heap_seed(h, rg, F_SEED_DONE, r0 - 1, r1 + 1, ec, lane);
-  for (;;) {
-    const int p = heap_pop(h, lane);
-    if (p < 0) break;
-    if (lane == 0) f[p] = F_KNOWN;
-    __syncwarp();
-    int nb;
-    float d;
-    const bool valid = neighbour_dist(f, t, p, er, ec, lane, nb, d);
-    __syncwarp();
-    for (int q = 0; q < 4; ++q) {
-      const bool vq = __shfl_sync(0xffffffffu, (int)valid, 4 * q) != 0;
-      const float dq = __shfl_sync(0xffffffffu, d, 4 * q);
-      const int nq = __shfl_sync(0xffffffffu, nb, 4 * q);
-      if (!vq) continue;
-      if (lane == 0) t[nq] = dq;
+      for (int q = lo * ec + lane; q < (hi + 1) * ec; q += 32)
+        if (rg[q] == F_CHANGE || rg[q] == F_SEED_DONE) t[q] = -t[q];
+      __threadfence_block();
       __syncwarp();
-      paint_pixel<C>(f, t, out, er, ec, range, nq, lane, dst_tab, terms);
-      if (lane == 0) f[nq] = F_BAND;
-      heap_push(h, nq, dq, lane);
+      if (lane == 0) sy->outside_done = 1;
+    } else {
+      // march inwards: arrival times of the mask pixels and the order in which they are painted
+      int n = 0;
+      for (;;) {
+        const int p = heap_pop(h, lane);
+        if (p < 0) break;
+        if (lane == 0) f[p] = F_KNOWN;
+        __syncwarp();
+        int nb;
+        float d;
+        const bool valid = neighbour_dist(f, t, p, er, ec, lane, nb, d);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool vq = __shfl_sync(0xffffffffu, (int)valid, 4 * q) != 0;
+          const float dq = __shfl_sync(0xffffffffu, d, 4 * q);
+          const int nq = __shfl_sync(0xffffffffu, nb, 4 * q);
+          if (vq) {
+            if (lane == 0) {
+              t[nq] = dq;
+              f[nq] = F_BAND;
+              stamp[nq] = n;
+              job[n] = nq;
+              __threadfence_block();
+              sy->jobs_ready = n + 1;
+            }
+            ++n;
+            heap_push(h, nq, dq, lane);
+          }
+        }
+      }
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) sy->queue_total = n;
     }
+  } else {
+    painter_loop<C>(warp - 2, lane, sy, job, stamp, m0, m1, t, out, er, ec, range, dst_tab,
+                    terms_all + (size_t)(warp - 2) * DD * INP_CHAINS);
   }
+  __syncthreads();
   if (staged) {                                  // painted rows back to the page
     uint8_t *og = dst + (size_t)img * H * W * C;
     const size_t b0 = (size_t)(r0 - 1) * W * C, b1 = (size_t)r1 * W * C;
-    for (size_t q = b0 + lane; q < b1; q += 32) og[q] = out[q];
+    for (size_t q = b0 + threadIdx.x; q < b1; q += 32 * INP_WARPS) og[q] = out[q];
   }
 }
 
@@ -481,14 +621,19 @@ extern "C" int ocrb_inpaint_telea_u8(const uint8_t *src, const uint8_t *mask, ui
     int dev = 0, optin = 0;
     OCRB_CUDA(cudaGetDevice(&dev));
     OCRB_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    OCRB_REQUIRE(optin >= INP_FIXED_SMEM + INP_MIN_HEAP * 12, "inpaint_telea_u8: not enough shared memory per block");
+    OCRB_REQUIRE(optin >= 64 * 1024, "inpaint_telea_u8: not enough shared memory per block");
     OCRB_CUDA(cudaFuncSetAttribute(inp_march_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     OCRB_CUDA(cudaFuncSetAttribute(inp_march_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     smem_bytes = optin;
   }
+  static int stage_ok = -1;               // OCRB_INPAINT_STAGE=0 forces the global-memory path (tests, measurements)
+  if (stage_ok < 0) {
+    const char *e = getenv("OCRB_INPAINT_STAGE");
+    stage_ok = e ? atoi(e) != 0 : 1;
+  }
   if (C == 1)
-    inp_march_kernel<1><<<dim3(maxseg, n_img), 32, smem_bytes, st>>>(dst, w, H, W, radius, maxseg, smem_bytes);
+    inp_march_kernel<1><<<dim3(maxseg, n_img), 32 * INP_WARPS, smem_bytes, st>>>(dst, w, H, W, radius, maxseg, smem_bytes, stage_ok);
   else
-    inp_march_kernel<3><<<dim3(maxseg, n_img), 32, smem_bytes, st>>>(dst, w, H, W, radius, maxseg, smem_bytes);
+    inp_march_kernel<3><<<dim3(maxseg, n_img), 32 * INP_WARPS, smem_bytes, st>>>(dst, w, H, W, radius, maxseg, smem_bytes, stage_ok);
   return check_launch("inp_march_kernel");
 }
