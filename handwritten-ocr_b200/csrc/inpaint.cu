@@ -37,7 +37,7 @@ constexpr int INP_MAX_RANGE = 7;
 static inline __host__ __device__ int inp_gap(int range) { return 2 * range + 2; }
 constexpr int INP_CHAINS = 10;        // Ia[3], Jx[3], Jy[3], s
 constexpr int INP_NOTYET = 0x7fffffff;
-constexpr int INP_PAINTERS = 2;
+constexpr int INP_PAINTERS = 3;
 constexpr int INP_WARPS = 2 + INP_PAINTERS;   // outward march, inward march, painters
 // a waiting warp traps instead of hanging if its partner never arrives (2^36 cycles: half a minute)
 __device__ __forceinline__ void inp_spin_check(int it, long long t0) {
@@ -283,10 +283,11 @@ struct InpSync {        // shared-memory mailbox of a segment's four warps
   int queue_total;      // -1 while the inward march runs, then the number of pixels
   int outside_done;     // ring distances final (negated)
   int painted_upto;     // pixels 0 .. painted_upto-1 carry their final value
+  long long ts[6];      // OCRB_INPAINT_DEBUG=1: clock64 at start / outward done / inward done / painters done / first paint
 };
 
 struct PosState {       // what one disc position contributes, everything that does not depend on pixel values
-  float w, sx, sy;
+  float w, sx, sy, rx, ry;
   int xa, xb, ya, yb, ctr;   // ctr < 0: position contributes nothing
 };
 
@@ -294,23 +295,25 @@ __device__ __forceinline__ bool inp_known(const int32_t *stamp, int m0, int m1, 
   return q < m0 || q >= m1 || stamp[q] < n;
 }
 
+// disc entry e = (dk, dl) packed by the kernel prologue, raster order, centre left out
 template <int C>
-__device__ __forceinline__ void paint_position(PosState &st, int q, int i, int j, int n, float tij, float gx, float gy,
+__device__ __forceinline__ void paint_position(PosState &st, int e, int nd, int i, int j, int n, float tij, float gx, float gy,
                                                const float *t, const int32_t *stamp, int m0, int m1, int er, int ec,
-                                               int range, const float *dst_tab) {
-  const int W = ec - 2, D = 2 * range + 1;
+                                               const int *disc, const float *dst_tab) {
+  const int W = ec - 2;
   st.ctr = -1;
-  if (q >= D * D) return;
-  const int dk = q / D - range, dl = q - (q / D) * D - range;
+  if (e >= nd) return;
+  const int dkl = disc[e], dk = dkl >> 8, dl = (int)(int8_t)(dkl & 0xff);
   const int k = i + dk, l = j + dl;
-  if (!(k > 0 && l > 0 && k < er - 1 && l < ec - 1 && dk * dk + dl * dl <= range * range)) return;
+  if (!(k > 0 && l > 0 && k < er - 1 && l < ec - 1)) return;
   const int kl = k * ec + l;
   if (!inp_known(stamp, m0, m1, kl, n)) return;
-  const float ry = (float)(-dk), rx = (float)(-dl);
+  st.ry = (float)(-dk);
+  st.rx = (float)(-dl);
   const float lev = (float)(1. / (1 + fabs((double)(t[kl] - tij))));
-  float dir = rx * gx + ry * gy;
+  float dir = st.rx * gx + st.ry * gy;
   if ((double)fabsf(dir) <= 0.01) dir = 0.000001f;
-  st.w = fabsf(dst_tab[q] * lev * dir);
+  st.w = fabsf(dst_tab[e] * lev * dir);
   const int km = k - 1 + (k == 1), kp = k - 1 - (k == er - 2);
   const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ec - 2);
   const bool fr = inp_known(stamp, m0, m1, kl + 1, n), fl = inp_known(stamp, m0, m1, kl - 1, n);
@@ -325,34 +328,35 @@ __device__ __forceinline__ void paint_position(PosState &st, int q, int i, int j
   st.ctr = ((k - 1) * W + (l - 1)) * C;
 }
 
+// terms[chain * ndp + e]: chain-major, so that the lane owning a running sum walks consecutive words
 template <int C>
-__device__ __forceinline__ void paint_terms(const PosState &st, int q, int range, const uint8_t *out, float *terms) {
-  const int D = 2 * range + 1;
-  if (q >= D * D) return;
+__device__ __forceinline__ void paint_terms(const PosState &st, int e, int nd, int ndp, const uint8_t *out, float *terms) {
+  if (e >= nd) return;
   float tr[INP_CHAINS];
 #pragma unroll
   for (int c = 0; c < INP_CHAINS; ++c) tr[c] = 0.f;
   if (st.ctr >= 0) {
-    const float ry = (float)(range - q / D), rx = (float)(range - (q - (q / D) * D));
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const float gix = (float)((int)out[st.xa + c] - (int)out[st.xb + c]) * st.sx;
       const float giy = (float)((int)out[st.ya + c] - (int)out[st.yb + c]) * st.sy;
       tr[c] = st.w * (float)out[st.ctr + c];
-      tr[3 + c] = -(st.w * (gix * rx));       // Jx -= v  ==  Jx += -v
-      tr[6 + c] = -(st.w * (giy * ry));
+      tr[3 + c] = -(st.w * (gix * st.rx));       // Jx -= v  ==  Jx += -v
+      tr[6 + c] = -(st.w * (giy * st.ry));
     }
     tr[9] = st.w;
   }
 #pragma unroll
-  for (int c = 0; c < INP_CHAINS; ++c) terms[q * INP_CHAINS + c] = tr[c];
+  for (int c = 0; c < INP_CHAINS; ++c)
+    if (c < C || (c >= 3 && c < 3 + C) || (c >= 6 && c < 6 + C) || c == 9) terms[c * ndp + e] = tr[c];
 }
 
 // A painter warp: jobs k, k + INP_PAINTERS, ...
 template <int C>
 __device__ void painter_loop(int k, int lane, volatile InpSync *sy, const int32_t *job, const int32_t *stamp, int m0, int m1,
-                             const float *t, uint8_t *out, int er, int ec, int range, const float *dst_tab, float *terms) {
-  const int W = ec - 2, D = 2 * range + 1, DD = D * D;
+                             const float *t, uint8_t *out, int er, int ec, int nd, int ndp, const int *disc,
+                             const float *dst_tab, float *terms) {
+  const int W = ec - 2;
   bool outside_seen = false;
   for (int n = k;; n += INP_PAINTERS) {
     int ok = 1;
@@ -384,33 +388,43 @@ __device__ void painter_loop(int k, int lane, volatile InpSync *sy, const int32_
       gx = r ? (l ? (t[p + 1] - t[p - 1]) * 0.5f : t[p + 1] - tij) : (l ? tij - t[p - 1] : 0.f);
       gy = d ? (u ? (t[p + ec] - t[p - ec]) * 0.5f : t[p + ec] - tij) : (u ? tij - t[p - ec] : 0.f);
     }
-    // everything that does not read pixel values: the first two rounds of disc positions (all of them for radius <= 3)
+    // everything that does not read pixel values: the first two rounds of disc positions (all of them for radius <= 4)
     PosState s0, s1;
-    paint_position<C>(s0, lane, i, j, n, tij, gx, gy, t, stamp, m0, m1, er, ec, range, dst_tab);
-    paint_position<C>(s1, lane + 32, i, j, n, tij, gx, gy, t, stamp, m0, m1, er, ec, range, dst_tab);
+    paint_position<C>(s0, lane, nd, i, j, n, tij, gx, gy, t, stamp, m0, m1, er, ec, disc, dst_tab);
+    paint_position<C>(s1, lane + 32, nd, i, j, n, tij, gx, gy, t, stamp, m0, m1, er, ec, disc, dst_tab);
     if (lane == 0) {
       const long long t0 = clock64();
       for (int it = 0; sy->painted_upto != n; ++it) inp_spin_check(it, t0);
     }
     __syncwarp();
     __threadfence_block();
-    paint_terms<C>(s0, lane, range, out, terms);
-    paint_terms<C>(s1, lane + 32, range, out, terms);
-    for (int q = lane + 64; q < DD; q += 32) {          // radius > 3 only
+    paint_terms<C>(s0, lane, nd, ndp, out, terms);
+    paint_terms<C>(s1, lane + 32, nd, ndp, out, terms);
+    for (int e = lane + 64; e < nd; e += 32) {          // radius > 4 only
       PosState sx_;
-      paint_position<C>(sx_, q, i, j, n, tij, gx, gy, t, stamp, m0, m1, er, ec, range, dst_tab);
-      paint_terms<C>(sx_, q, range, out, terms);
+      paint_position<C>(sx_, e, nd, i, j, n, tij, gx, gy, t, stamp, m0, m1, er, ec, disc, dst_tab);
+      paint_terms<C>(sx_, e, nd, ndp, out, terms);
     }
     __syncwarp();
     // running sums in raster order: lane c < 3 -> Ia[c], 3..5 -> Jx, 6..8 -> Jy, 9 -> s
     float acc = lane == 9 ? 1.0e-20f : 0.f;
-    if (lane < INP_CHAINS)
-      for (int q = 0; q < DD; ++q) acc += terms[q * INP_CHAINS + lane];
+    if (lane < INP_CHAINS && (lane == 9 || lane % 3 < C)) {
+      const float *tp = terms + lane * ndp;
+#pragma unroll 4
+      for (int e = 0; e < nd; ++e) acc += tp[e];
+    }
     const int c = lane < C ? lane : 0;
     const float Ia = __shfl_sync(0xffffffffu, acc, c), Jx = __shfl_sync(0xffffffffu, acc, 3 + c);
     const float Jy = __shfl_sync(0xffffffffu, acc, 6 + c), s = __shfl_sync(0xffffffffu, acc, 9);
     if (lane < C) {
-      const float sat = (float)(Ia / s + (Jx + Jy) / (sqrt((double)(Jx * Jx + Jy * Jy)) + (double)1.0e-20f));
+      // sat = Ia/s + (Jx+Jy)/(sqrt(Jx^2+Jy^2) + 1e-20) with the second term in double, then round(sat + 0.5).  The
+      // result only changes where sat crosses an integer, so an all-float estimate (error < 1e-4: the term is at most
+      // sqrt 2, |sat| < ~300) settles every case that is not within 1/64 of one; the rest take OpenCV's exact steps.
+      const float q1 = Ia / s, ss = Jx * Jx + Jy * Jy;
+      float sat = q1 + (Jx + Jy) / (sqrtf(ss) + 1.0e-20f);
+      const float fr = sat - floorf(sat);
+      if (!(fr > 0.015625f && fr < 0.984375f) || !(fabsf(sat) < 1.0e6f))
+        sat = (float)(q1 + (Jx + Jy) / (sqrt((double)ss) + (double)1.0e-20f));
       const int v = __float2int_rn(sat + 0.5f);
       out[((i - 1) * W + (j - 1)) * C + lane] = (uint8_t)min(max(v, 0), 255);
     }
@@ -420,7 +434,7 @@ __device__ void painter_loop(int k, int lane, volatile InpSync *sy, const int32_
   }
 }
 
-// ───────────── one CTA (4 warps) per (segment, page) ─────────────
+// ───────────── one CTA (2 march warps + painters) per (segment, page) ─────────────
 // Dynamic shared memory: [mailbox | dst_tab | painters' terms | window of t, f, rg, page rows, stamps, jobs (when it
 // fits) | two heaps].
 constexpr int INP_DD_MAX = (2 * INP_MAX_RANGE + 1) * (2 * INP_MAX_RANGE + 1);
@@ -438,9 +452,18 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
   const int r0 = seg[1 + 2 * blockIdx.x], r1 = seg[2 + 2 * blockIdx.x];      // extended rows holding mask pixels
   const size_t ne = (size_t)er * ec;
   volatile InpSync *sy = reinterpret_cast<volatile InpSync *>(smem);
-  float *dst_tab = reinterpret_cast<float *>(smem + 32);
-  float *terms_all = dst_tab + INP_DD_MAX;
-  uint8_t *sp = smem + inp_a16(32 + INP_DD_MAX * 4 + (size_t)INP_PAINTERS * DD * INP_CHAINS * 4);
+  // disc positions (dk, dl) with dk^2 + dl^2 <= range^2 in raster order, centre left out (the pixel being painted is
+  // never known to itself); same count on every thread
+  int nd = 0;
+  for (int q = 0; q < DD; ++q) {
+    const int dk = q / D - range, dl = q % D - range;
+    nd += (dk * dk + dl * dl <= range * range && (dk | dl) != 0);
+  }
+  const int ndp = (nd + 3) & ~3;
+  float *dst_tab = reinterpret_cast<float *>(smem + 96);
+  int *disc = reinterpret_cast<int *>(dst_tab + INP_DD_MAX);
+  float *terms_all = reinterpret_cast<float *>(disc + INP_DD_MAX);
+  uint8_t *sp = smem + inp_a16(96 + 2 * INP_DD_MAX * 4 + (size_t)INP_PAINTERS * ndp * INP_CHAINS * 4);
   uint8_t *f = w.f + img * ne, *rg = w.rg + img * ne;
   float *t = w.t + img * ne;
   int32_t *stamp = w.stamp + img * ne;
@@ -483,16 +506,22 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
     stamp = stamp_s - m0;
     job = job_s;
   }
-  for (int q = threadIdx.x; q < DD; q += 32 * INP_WARPS) {
-    const int dk = q / D - range, dl = q % D - range;
-    const float len2 = (float)(dk * dk + dl * dl);
-    dst_tab[q] = len2 > 0.f ? (float)(1. / (len2 * sqrt((double)len2))) : 0.f;
+  if (threadIdx.x == 0) {
+    int e = 0;
+    for (int q = 0; q < DD; ++q) {
+      const int dk = q / D - range, dl = q % D - range;
+      if (dk * dk + dl * dl > range * range || (dk | dl) == 0) continue;
+      const float len2 = (float)(dk * dk + dl * dl);
+      dst_tab[e] = (float)(1. / (len2 * sqrt((double)len2)));
+      disc[e++] = (dk << 8) | (dl & 0xff);
+    }
   }
   if (threadIdx.x == 0) {
     sy->jobs_ready = 0;
     sy->queue_total = -1;
     sy->outside_done = 0;
     sy->painted_upto = 0;
+    sy->ts[0] = clock64();
   }
   __syncthreads();
 
@@ -540,7 +569,10 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
         if (rg[q] == F_CHANGE || rg[q] == F_SEED_DONE) t[q] = -t[q];
       __threadfence_block();
       __syncwarp();
-      if (lane == 0) sy->outside_done = 1;
+      if (lane == 0) {
+        sy->ts[1] = clock64();
+        sy->outside_done = 1;
+      }
     } else {
       // march inwards: arrival times of the mask pixels and the order in which they are painted
       int n = 0;
@@ -574,13 +606,20 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
       }
       __threadfence_block();
       __syncwarp();
-      if (lane == 0) sy->queue_total = n;
+      if (lane == 0) {
+        sy->ts[2] = clock64();
+        sy->queue_total = n;
+      }
     }
   } else {
-    painter_loop<C>(warp - 2, lane, sy, job, stamp, m0, m1, t, out, er, ec, range, dst_tab,
-                    terms_all + (size_t)(warp - 2) * DD * INP_CHAINS);
+    painter_loop<C>(warp - 2, lane, sy, job, stamp, m0, m1, t, out, er, ec, nd, ndp, disc, dst_tab,
+                    terms_all + (size_t)(warp - 2) * ndp * INP_CHAINS);
+    if (lane == 0 && warp == 2) sy->ts[3] = clock64();
   }
   __syncthreads();
+  if (stage_ok > 1 && threadIdx.x == 0 && blockIdx.x < 2 && img == 0)
+    printf("inpaint segment %d rows %d..%d staged %d jobs %d: outward %lld inward %lld painters %lld cycles\n", (int)blockIdx.x,
+           r0, r1, (int)staged, sy->queue_total, sy->ts[1] - sy->ts[0], sy->ts[2] - sy->ts[0], sy->ts[3] - sy->ts[0]);
   if (staged) {                                  // painted rows back to the page
     uint8_t *og = dst + (size_t)img * H * W * C;
     const size_t b0 = (size_t)(r0 - 1) * W * C, b1 = (size_t)r1 * W * C;
@@ -629,7 +668,7 @@ extern "C" int ocrb_inpaint_telea_u8(const uint8_t *src, const uint8_t *mask, ui
   static int stage_ok = -1;               // OCRB_INPAINT_STAGE=0 forces the global-memory path (tests, measurements)
   if (stage_ok < 0) {
     const char *e = getenv("OCRB_INPAINT_STAGE");
-    stage_ok = e ? atoi(e) != 0 : 1;
+    stage_ok = e ? atoi(e) : 1;           // 2: staged + one timing line per segment (device printf)
   }
   if (C == 1)
     inp_march_kernel<1><<<dim3(maxseg, n_img), 32 * INP_WARPS, smem_bytes, st>>>(dst, w, H, W, radius, maxseg, smem_bytes, stage_ok);

@@ -30,7 +30,7 @@ def main():
         if m:
             cur = int(m.group(1))
             continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
             lines.append(cur)
     assert len(lines) == len(rows), (len(lines), len(rows))
     cnt, smp = collections.Counter(), collections.Counter()
