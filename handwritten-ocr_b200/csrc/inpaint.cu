@@ -37,10 +37,14 @@ constexpr int INP_MAX_RANGE = 7;
 static inline __host__ __device__ int inp_gap(int range) { return 2 * range + 2; }
 constexpr int INP_CHAINS = 10;        // Ia[3], Jx[3], Jy[3], s
 constexpr int INP_NOTYET = 0x7fffffff;
+#ifndef INP_SPIN_SLEEP
+#define INP_SPIN_SLEEP 0
+#endif
 constexpr int INP_PAINTERS = 3;
 constexpr int INP_WARPS = 2 + INP_PAINTERS;   // outward march, inward march, painters
 // a waiting warp traps instead of hanging if its partner never arrives (2^36 cycles: half a minute)
 __device__ __forceinline__ void inp_spin_check(int it, long long t0) {
+  if (INP_SPIN_SLEEP) __nanosleep(INP_SPIN_SLEEP);
   if ((it & 1023) == 1023 && clock64() - t0 > (1ll << 36)) __trap();
 }
 
@@ -172,20 +176,20 @@ struct Heap {
   }
 };
 
-// all lanes call with the same arguments
+// all lanes call with the same arguments and walk the same path (loads are broadcasts, only lane 0 stores): a lane-0-only
+// loop would leave the warp diverged, and every later shuffle / ballot / redux would take the slow collective path
 __device__ __forceinline__ void heap_push(Heap &h, int p, float Tv, int lane) {
   const uint32_t kt = Tv == 0.f ? 0u : __float_as_uint(Tv), ks = h.seq++;
   int i = h.n++;
-  if (lane == 0) {
-    while (i > 0) {
-      const int par = (i - 1) >> 5;
-      const uint32_t pt = h.T(par), ps = h.S(par);
-      if (pt < kt || (pt == kt && ps <= ks)) break;
-      h.set(i, pt, ps, h.P(par));
-      i = par;
-    }
-    h.set(i, kt, ks, p);
+  while (i > 0) {
+    const int par = (i - 1) >> 5;
+    const uint32_t pt = h.T(par), ps = h.S(par);
+    if (pt < kt || (pt == kt && ps <= ks)) break;
+    const int pp = h.P(par);
+    if (lane == 0) h.set(i, pt, ps, pp);
+    i = par;
   }
+  if (lane == 0) h.set(i, kt, ks, p);
   __syncwarp();
 }
 
@@ -301,7 +305,10 @@ __device__ __forceinline__ void paint_position(PosState &st, int e, int nd, int 
                                                const float *t, const int32_t *stamp, int m0, int m1, int er, int ec,
                                                const int *disc, const float *dst_tab) {
   const int W = ec - 2;
-  st.ctr = -1;
+  // a position that contributes nothing gets weight 0 and reads the pixel being painted: no branch in the dependent part
+  st.w = 0.f;
+  st.sx = st.sy = st.rx = st.ry = 0.f;
+  st.xa = st.xb = st.ya = st.yb = st.ctr = ((i - 1) * W + (j - 1)) * C;
   if (e >= nd) return;
   const int dkl = disc[e], dk = dkl >> 8, dl = (int)(int8_t)(dkl & 0xff);
   const int k = i + dk, l = j + dl;
@@ -332,41 +339,41 @@ __device__ __forceinline__ void paint_position(PosState &st, int e, int nd, int 
 template <int C>
 __device__ __forceinline__ void paint_terms(const PosState &st, int e, int nd, int ndp, const uint8_t *out, float *terms) {
   if (e >= nd) return;
-  float tr[INP_CHAINS];
 #pragma unroll
-  for (int c = 0; c < INP_CHAINS; ++c) tr[c] = 0.f;
-  if (st.ctr >= 0) {
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float gix = (float)((int)out[st.xa + c] - (int)out[st.xb + c]) * st.sx;
-      const float giy = (float)((int)out[st.ya + c] - (int)out[st.yb + c]) * st.sy;
-      tr[c] = st.w * (float)out[st.ctr + c];
-      tr[3 + c] = -(st.w * (gix * st.rx));       // Jx -= v  ==  Jx += -v
-      tr[6 + c] = -(st.w * (giy * st.ry));
-    }
-    tr[9] = st.w;
+  for (int c = 0; c < C; ++c) {
+    const float gix = (float)((int)out[st.xa + c] - (int)out[st.xb + c]) * st.sx;
+    const float giy = (float)((int)out[st.ya + c] - (int)out[st.yb + c]) * st.sy;
+    terms[c * ndp + e] = st.w * (float)out[st.ctr + c];
+    terms[(3 + c) * ndp + e] = -(st.w * (gix * st.rx));       // Jx -= v  ==  Jx += -v
+    terms[(6 + c) * ndp + e] = -(st.w * (giy * st.ry));
   }
-#pragma unroll
-  for (int c = 0; c < INP_CHAINS; ++c)
-    if (c < C || (c >= 3 && c < 3 + C) || (c >= 6 && c < 6 + C) || c == 9) terms[c * ndp + e] = tr[c];
+  terms[9 * ndp + e] = st.w;
 }
 
 // A painter warp: jobs k, k + INP_PAINTERS, ...
 template <int C>
 __device__ void painter_loop(int k, int lane, volatile InpSync *sy, const int32_t *job, const int32_t *stamp, int m0, int m1,
                              const float *t, uint8_t *out, int er, int ec, int nd, int ndp, const int *disc,
-                             const float *dst_tab, float *terms) {
+                             const float *dst_tab, float *terms, int debug) {
   const int W = ec - 2;
   bool outside_seen = false;
+  long long ph[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();   // debug: cycles per phase of this painter
+#define INP_PHASE(x)                      \
+  if (debug) {                            \
+    const long long now_ = clock64();     \
+    ph[x] += now_ - tc;                   \
+    tc = now_;                            \
+  }
   for (int n = k;; n += INP_PAINTERS) {
-    int ok = 1;
-    if (lane == 0) {
+    // every lane polls (one broadcast load per poll): the warp stays converged, so the collectives below are cheap
+    bool ok = true;
+    {
       const long long t0 = clock64();
       for (int it = 0;; ++it) {
         if (sy->jobs_ready > n) break;
         const int tot = sy->queue_total;
         if (tot >= 0 && n >= tot) {
-          ok = 0;
+          ok = false;
           break;
         }
         inp_spin_check(it, t0);
@@ -374,8 +381,12 @@ __device__ void painter_loop(int k, int lane, volatile InpSync *sy, const int32_
       if (ok && !outside_seen)
         for (int it = 0; !sy->outside_done; ++it) inp_spin_check(it, t0);
     }
-    ok = __shfl_sync(0xffffffffu, ok, 0);
     if (!ok) break;
+    if (outside_seen) {
+      INP_PHASE(0)                                             // 0: waiting for a job (after the outward march is done)
+    } else {
+      tc = clock64();
+    }
     outside_seen = true;
     __threadfence_block();
     const int p = job[n];
@@ -392,12 +403,14 @@ __device__ void painter_loop(int k, int lane, volatile InpSync *sy, const int32_
     PosState s0, s1;
     paint_position<C>(s0, lane, nd, i, j, n, tij, gx, gy, t, stamp, m0, m1, er, ec, disc, dst_tab);
     paint_position<C>(s1, lane + 32, nd, i, j, n, tij, gx, gy, t, stamp, m0, m1, er, ec, disc, dst_tab);
-    if (lane == 0) {
+    INP_PHASE(1)                                               // 1: prologue
+    {
       const long long t0 = clock64();
       for (int it = 0; sy->painted_upto != n; ++it) inp_spin_check(it, t0);
     }
     __syncwarp();
     __threadfence_block();
+    INP_PHASE(2)                                               // 2: waiting for the predecessor
     paint_terms<C>(s0, lane, nd, ndp, out, terms);
     paint_terms<C>(s1, lane + 32, nd, ndp, out, terms);
     for (int e = lane + 64; e < nd; e += 32) {          // radius > 4 only
@@ -406,16 +419,19 @@ __device__ void painter_loop(int k, int lane, volatile InpSync *sy, const int32_
       paint_terms<C>(sx_, e, nd, ndp, out, terms);
     }
     __syncwarp();
+    INP_PHASE(3)                                               // 3: terms
     // running sums in raster order: lane c < 3 -> Ia[c], 3..5 -> Jx, 6..8 -> Jy, 9 -> s
     float acc = lane == 9 ? 1.0e-20f : 0.f;
-    if (lane < INP_CHAINS && (lane == 9 || lane % 3 < C)) {
-      const float *tp = terms + lane * ndp;
+    {
+      const int ch = lane < INP_CHAINS && (lane == 9 || lane % 3 < C) ? lane : 9;
+      const float *tp = terms + ch * ndp;
 #pragma unroll 4
       for (int e = 0; e < nd; ++e) acc += tp[e];
     }
     const int c = lane < C ? lane : 0;
     const float Ia = __shfl_sync(0xffffffffu, acc, c), Jx = __shfl_sync(0xffffffffu, acc, 3 + c);
     const float Jy = __shfl_sync(0xffffffffu, acc, 6 + c), s = __shfl_sync(0xffffffffu, acc, 9);
+    INP_PHASE(4)                                               // 4: ordered sums
     if (lane < C) {
       // sat = Ia/s + (Jx+Jy)/(sqrt(Jx^2+Jy^2) + 1e-20) with the second term in double, then round(sat + 0.5).  The
       // result only changes where sat crosses an integer, so an all-float estimate (error < 1e-4: the term is at most
@@ -431,7 +447,12 @@ __device__ void painter_loop(int k, int lane, volatile InpSync *sy, const int32_
     __threadfence_block();
     __syncwarp();
     if (lane == 0) sy->painted_upto = n + 1;
+    INP_PHASE(5)                                               // 5: final quotient, store, publish
   }
+  if (debug && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+    printf("painter %d: wait-job %lld prologue %lld wait-pred %lld terms %lld sums %lld finish %lld cycles\n", k, ph[0], ph[1],
+           ph[2], ph[3], ph[4], ph[5]);
+#undef INP_PHASE
 }
 
 // ───────────── one CTA (2 march warps + painters) per (segment, page) ─────────────
@@ -596,9 +617,9 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
               f[nq] = F_BAND;
               stamp[nq] = n;
               job[n] = nq;
-              __threadfence_block();
-              sy->jobs_ready = n + 1;
             }
+            __threadfence_block();
+            if (lane == 0) sy->jobs_ready = n + 1;
             ++n;
             heap_push(h, nq, dq, lane);
           }
@@ -613,7 +634,7 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
     }
   } else {
     painter_loop<C>(warp - 2, lane, sy, job, stamp, m0, m1, t, out, er, ec, nd, ndp, disc, dst_tab,
-                    terms_all + (size_t)(warp - 2) * ndp * INP_CHAINS);
+                    terms_all + (size_t)(warp - 2) * ndp * INP_CHAINS, stage_ok > 1);
     if (lane == 0 && warp == 2) sy->ts[3] = clock64();
   }
   __syncthreads();
