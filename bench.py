@@ -294,7 +294,7 @@ def preprocess_table(torch, preprocess, synth, page, peak_gbs):
     ruled = preprocess.to_device(synth.rule_lines(page))
     H, W = page.shape[:2]
     cases = {"high_contrast": (lambda: preprocess.high_contrast(x), 4 * H * W, "hbm"),
-             "binarize": (lambda: preprocess.binarize(x), 4 * H * W, "hbm"),
+             "binarize": (lambda: preprocess.binarize(x), 4 * H * W, "hbm (rgb2gray) + fp32 FMA (2 x 21-tap stencil)"),
              "sharpen": (lambda: preprocess.sharpen(x), 6 * H * W, "hbm"),
              "deskew": (lambda: preprocess.deskew(x), 6 * H * W, "hbm"),
              "denoise": (lambda: preprocess.denoise(x), 6 * H * W, "integer ALU / shared memory (441 x 49 comparisons per pixel)"),

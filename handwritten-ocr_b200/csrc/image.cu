@@ -126,6 +126,49 @@ clahe_apply_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, c
   dst[p] = (uint8_t)q;
 }
 
+// Same arithmetic, four pixels per thread (one 32-bit load and store): used when W % 4 == 0.
+__global__ void __launch_bounds__(256)
+clahe_apply4_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const uint8_t *__restrict__ lut,
+                    int H, int W, float inv_tw, float inv_th) {
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const int img = blockIdx.z;
+  if (x0 >= W) return;
+  const float yf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+  int ty1 = (int)floorf(yf);
+  int ty2 = ty1 + 1;
+  const float ya = __fsub_rn(yf, (float)ty1);
+  const float ya1 = __fsub_rn(1.0f, ya);
+  ty1 = max(ty1, 0);
+  ty2 = min(ty2, 7);
+  const size_t p = ((size_t)img * H + y) * W + x0;
+  const uint32_t v4 = *reinterpret_cast<const uint32_t *>(src + p);
+  const uint8_t *L = lut + (size_t)img * 64 * 256;
+  uint32_t o = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float xf = __fsub_rn(__fmul_rn((float)(x0 + k), inv_tw), 0.5f);
+    int tx1 = (int)floorf(xf);
+    int tx2 = tx1 + 1;
+    const float xa = __fsub_rn(xf, (float)tx1);
+    const float xa1 = __fsub_rn(1.0f, xa);
+    tx1 = max(tx1, 0);
+    tx2 = min(tx2, 7);
+    const int v = (v4 >> (8 * k)) & 0xff;
+    const float l11 = (float)L[(ty1 * 8 + tx1) * 256 + v];
+    const float l12 = (float)L[(ty1 * 8 + tx2) * 256 + v];
+    const float l21 = (float)L[(ty2 * 8 + tx1) * 256 + v];
+    const float l22 = (float)L[(ty2 * 8 + tx2) * 256 + v];
+    const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+    const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+    const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+    int q = __float2int_rn(res);
+    q = min(max(q, 0), 255);
+    o |= (uint32_t)q << (8 * k);
+  }
+  *reinterpret_cast<uint32_t *>(dst + p) = o;
+}
+
 // ───────────────────────── A.3 adaptive Gaussian threshold ─────────────────────────
 // cv2.getGaussianKernel(21, 0, CV_32F) bit patterns (sigma = 3.5).
 __constant__ uint32_t c_gauss21[21] = {
@@ -142,7 +185,7 @@ constexpr int AT_SH = AT_TH + 2 * AT_R;  // 52
 // (symmetric FMA), then round-half-even and compare: one HBM read + one HBM write per pixel.
 __global__ void __launch_bounds__(256)
 adaptive_thresh_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H, int W) {
-  __shared__ uint8_t s_src[AT_SH][AT_SW + 4];
+  __shared__ __align__(16) uint8_t s_src[AT_SH][AT_SW + 4];
   __shared__ float s_row[AT_SH][AT_TW + 1];
   const int img = blockIdx.z;
   const int x0 = blockIdx.x * AT_TW, y0 = blockIdx.y * AT_TH;
@@ -154,26 +197,48 @@ adaptive_thresh_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ ds
     s_src[r][c] = im[(size_t)yy * W + xx];
   }
   __syncthreads();
-  for (int p = threadIdx.x; p < AT_SH * AT_TW; p += 256) {
-    const int r = p / AT_TW, c = p % AT_TW;
-    float acc = 0.0f;
+  // row pass: one thread = 8 consecutive columns of one row; its 28 source bytes are loaded once (7 words) and converted
+  // once, each output still accumulates its 21 taps in OpenCV's order
+  for (int p = threadIdx.x; p < AT_SH * (AT_TW / 8); p += 256) {
+    const int r = p / (AT_TW / 8), c0 = (p % (AT_TW / 8)) * 8;
+    float v[28];
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(&s_src[r][c0]);
 #pragma unroll
-    for (int j = 0; j < 21; ++j) acc = __fmaf_rn((float)s_src[r][c + j], __uint_as_float(c_gauss21[j]), acc);
-    s_row[r][c] = acc;
+    for (int q = 0; q < 7; ++q) {
+      const uint32_t w4 = sw[q];
+      v[4 * q] = (float)(w4 & 0xff);
+      v[4 * q + 1] = (float)((w4 >> 8) & 0xff);
+      v[4 * q + 2] = (float)((w4 >> 16) & 0xff);
+      v[4 * q + 3] = (float)(w4 >> 24);
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 21; ++j) acc = __fmaf_rn(v[o + j], __uint_as_float(c_gauss21[j]), acc);
+      s_row[r][c0 + o] = acc;
+    }
   }
   __syncthreads();
-  for (int p = threadIdx.x; p < AT_TH * AT_TW; p += 256) {
-    const int r = p / AT_TW, c = p % AT_TW;
-    const int y = y0 + r, x = x0 + c;
-    if (y >= H || x >= W) continue;
-    float acc = __fmaf_rn(s_row[r + AT_R][c], __uint_as_float(c_gauss21[10]), 0.0f);
+  // column pass: one thread = 8 consecutive rows of one column (28 row-pass values loaded once)
+  {
+    const int c = threadIdx.x % AT_TW, r0 = (threadIdx.x / AT_TW) * 8;
+    float v[28];
 #pragma unroll
-    for (int i = 1; i <= 10; ++i)
-      acc = __fmaf_rn(__fadd_rn(s_row[r + AT_R + i][c], s_row[r + AT_R - i][c]), __uint_as_float(c_gauss21[10 + i]), acc);
-    int mean = __float2int_rn(acc);
-    mean = min(max(mean, 0), 255);
-    const int s = s_src[r + AT_R][c + AT_R];
-    dst[((size_t)img * H + y) * W + x] = (s - mean > -10) ? 255 : 0;
+    for (int q = 0; q < 28; ++q) v[q] = s_row[r0 + q][c];
+    const int x = x0 + c;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int y = y0 + r0 + o;
+      float acc = __fmaf_rn(v[o + AT_R], __uint_as_float(c_gauss21[10]), 0.0f);
+#pragma unroll
+      for (int i = 1; i <= 10; ++i)
+        acc = __fmaf_rn(__fadd_rn(v[o + AT_R + i], v[o + AT_R - i]), __uint_as_float(c_gauss21[10 + i]), acc);
+      int mean = __float2int_rn(acc);
+      mean = min(max(mean, 0), 255);
+      const int sv = s_src[r0 + o + AT_R][c + AT_R];
+      if (y < H && x < W) dst[((size_t)img * H + y) * W + x] = (sv - mean > -10) ? 255 : 0;
+    }
   }
 }
 
@@ -194,6 +259,49 @@ sharpen_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H
           im[(size_t)y * rowb + xr * C + c];
   v = min(max(v, 0), 255);
   dst[((size_t)img * H + y) * rowb + xb] = (uint8_t)v;
+}
+
+// Four bytes per thread (rows of W * C bytes with W * C % 4 == 0): aligned 32-bit loads of the rows above / below and of the
+// previous / current / next word of the row, left / right neighbours (C bytes away) picked with byte permutes.  Words
+// that touch the first or last pixel of the row (reflect-101) take the byte path.
+__global__ void __launch_bounds__(256)
+sharpen4_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H, int W, int C) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int img = blockIdx.z;
+  const int rowb = W * C, nw = rowb >> 2;
+  if (w >= nw) return;
+  const uint8_t *im = src + (size_t)img * H * rowb;
+  uint8_t *om = dst + ((size_t)img * H + y) * rowb;
+  const int yu = reflect101(y - 1, H), yd = reflect101(y + 1, H);
+  const int xb = 4 * w;
+  if (w >= 1 && w + 1 < nw && xb + 3 < rowb - C) {
+    const uint32_t *rc = reinterpret_cast<const uint32_t *>(im + (size_t)y * rowb);
+    const uint32_t up = reinterpret_cast<const uint32_t *>(im + (size_t)yu * rowb)[w];
+    const uint32_t dn = reinterpret_cast<const uint32_t *>(im + (size_t)yd * rowb)[w];
+    const uint32_t prev = rc[w - 1], cur = rc[w], next = rc[w + 1];
+    const uint32_t left = C == 3 ? __byte_perm(prev, cur, 0x4321) : __byte_perm(prev, cur, 0x6543);
+    const uint32_t right = C == 3 ? __byte_perm(cur, next, 0x6543) : __byte_perm(cur, next, 0x4321);
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int sh = 8 * k;
+      int v = 5 * (int)((cur >> sh) & 0xff) - (int)((up >> sh) & 0xff) - (int)((dn >> sh) & 0xff) -
+              (int)((left >> sh) & 0xff) - (int)((right >> sh) & 0xff);
+      v = min(max(v, 0), 255);
+      o |= (uint32_t)v << sh;
+    }
+    reinterpret_cast<uint32_t *>(om)[w] = o;
+  } else {
+    for (int k = 0; k < 4; ++k) {
+      const int b = xb + k;
+      const int x = b / C, c = b - x * C;
+      const int xl = reflect101(x - 1, W), xr = reflect101(x + 1, W);
+      int v = 5 * im[(size_t)y * rowb + b] - im[(size_t)yu * rowb + b] - im[(size_t)yd * rowb + b] -
+              im[(size_t)y * rowb + xl * C + c] - im[(size_t)y * rowb + xr * C + c];
+      om[b] = (uint8_t)min(max(v, 0), 255);
+    }
+  }
 }
 
 // ───────────────────────── A.5 deskew ─────────────────────────
@@ -601,7 +709,10 @@ extern "C" int ocrb_clahe_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, in
   int rc = check_launch("clahe_lut_kernel");
   if (rc) return rc;
   volatile float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
-  clahe_apply_kernel<<<dim3(cdiv(W, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, lut_ws, H, W, inv_tw, inv_th);
+  if (W % 4 == 0 && ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 3) == 0)
+    clahe_apply4_kernel<<<dim3(cdiv(W / 4, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, lut_ws, H, W, inv_tw, inv_th);
+  else
+    clahe_apply_kernel<<<dim3(cdiv(W, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, lut_ws, H, W, inv_tw, inv_th);
   return check_launch("clahe_apply_kernel");
 }
 
@@ -615,7 +726,10 @@ extern "C" int ocrb_adaptive_gauss_thresh_u8(const uint8_t *src, uint8_t *dst, i
 extern "C" int ocrb_sharpen3x3_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t H, int32_t W, int32_t C,
                                   void *stream) {
   OCRB_REQUIRE(src && dst && n_img > 0 && H > 1 && W > 1 && (C == 1 || C == 3), "sharpen3x3_u8: bad arguments");
-  sharpen_kernel<<<dim3(cdiv((long long)W * C, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, C);
+  if ((W * C) % 4 == 0 && W >= 4 && ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 3) == 0)
+    sharpen4_kernel<<<dim3(cdiv((long long)W * C / 4, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, C);
+  else
+    sharpen_kernel<<<dim3(cdiv((long long)W * C, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, C);
   return check_launch("sharpen_kernel");
 }
 

@@ -222,3 +222,19 @@ def test_unknown_transforms(pp, synth, capsys):
     out = pp.apply_strategy(x, ["nonsense", "original"])
     assert out is x
     assert "Unknown transform 'nonsense'" in capsys.readouterr().out
+
+
+def test_vectorised_paths_small_widths(pp):
+    """The 4-bytes-per-thread sharpen / CLAHE kernels (row bytes % 4 == 0) at widths where most words touch a border,
+    gray and RGB, against the oracle; the register-blocked threshold kernel on tiles cut by the image edge."""
+    rng = np.random.default_rng(17)
+    for (h, w) in [(5, 4), (3, 8), (7, 12), (9, 64), (33, 100), (6, 5), (4, 7)]:
+        for shape in ((h, w), (h, w, 3)):
+            a = rng.integers(0, 256, shape, dtype=np.uint8)
+            assert np.array_equal(pp.sharpen(pp.to_device(a))[0].cpu().numpy(), R.sharpen(a)), shape
+    for (h, w) in [(16, 16), (24, 40), (50, 68), (31, 36)]:
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(pp.high_contrast(pp.to_device(a))[0].cpu().numpy(), R.clahe(a)), (h, w)
+    for (h, w) in [(33, 72), (70, 130), (8, 8), (40, 64)]:
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(pp.binarize(pp.to_device(a))[0].cpu().numpy(), R.adaptive_threshold(a)), (h, w)
