@@ -28,6 +28,9 @@ class OcrEngine:
         self.cfg: VLMConfig = weights.cfg
         self.dev = weights.device
         self.tok = tokenizer or SyntheticTokenizer()
+        # further EOS ids of the checkpoint's generation_config (e.g. <|endoftext|>): the device loop stops on <|im_end|>
+        # only; a row that emits one of these first is cut there on the host, which is where HF would have stopped it
+        self.extra_eos: tuple = ()
         self.max_batch, self.max_new, self.page = max_batch, max_new_tokens, page_size
         self.min_pixels, self.max_pixels = min_pixels, max_pixels
         self.pages_per_seq = math.ceil((max_prompt + max_new_tokens) / page_size)
@@ -153,7 +156,12 @@ class OcrEngine:
         # HF stops appending once every sequence is finished (finished rows are padded with eos until
         # then); the device loop only checks every 64 steps, so trim to HF's stopping point.
         toks = toks[:, :n_steps]
-        is_eos = toks == EOS
+        if self.extra_eos:
+            for i in range(n):
+                hit = np.isin(toks[i], self.extra_eos)
+                if hit.any():
+                    toks[i, int(hit.argmax()) + 1:] = EOS          # HF pads a finished row with pad = eos
+        is_eos = (toks == EOS) | (np.isin(toks, self.extra_eos) if self.extra_eos else False)
         first_eos = np.where(is_eos.any(1), is_eos.argmax(1), n_steps - 1)
         keep = int(first_eos.max()) + 1 if n_steps > 0 else 0
         out = [toks[i, :keep].tolist() for i in range(n)]

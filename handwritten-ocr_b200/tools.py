@@ -28,6 +28,7 @@ import torch
 from PIL import Image, ImageOps
 
 from . import _lib, preprocess
+from .vlm_config import EOS
 from .textops import (_find_differing_segments, _levenshtein_words, cer, compare_versions, evaluate,  # noqa: F401
                       levenshtein, merge_versions, normalize_text, tier1_metrics, wer)
 
@@ -47,6 +48,7 @@ _options = {
     "vlm_config": None,         # VLMConfig override (tests use the tiny config)
     "max_batch": 8,
     "seed": 0,
+    "force_greedy": False,      # decode greedily even if the checkpoint's generation_config.json asks for sampling
 }
 # processed path -> (device tensor [1,H,W(,3)], original path, label)
 _processed: dict = {}
@@ -136,7 +138,7 @@ def _load_ocr_model():
     from .engine import OcrEngine
     from .vlm import VLMWeights
     from .vlm_config import VLMConfig
-    cfg = _options["vlm_config"] or VLMConfig.olmocr_7b()
+    cfg, tokenizer, gen = checkpoint_metadata(_options["checkpoint"], _options["vlm_config"], _options["force_greedy"])
     dev = torch.device("cuda", torch.cuda.current_device())
     print(f"  [ocr] Loading {getattr(config, 'OLMOCR_MODEL', cfg.name)} on cuda...")
     if _options["checkpoint"]:
@@ -147,12 +149,41 @@ def _load_ocr_model():
         w = VLMWeights.from_state_dict(cfg, sd, free_source=True)
     else:
         w = VLMWeights.random(cfg, dev, seed=_options["seed"])
-    _ocr_engine = OcrEngine(w, max_batch=_options["max_batch"],
+    _ocr_engine = OcrEngine(w, max_batch=_options["max_batch"], tokenizer=tokenizer,
                             max_new_tokens=int(getattr(config, "OCR_MAX_NEW_TOKENS", 2048)),
                             min_pixels=int(getattr(config, "OCR_MIN_PIXELS", 256 * 256)),
                             max_pixels=int(getattr(config, "OCR_MAX_PIXELS", 1024 * 1024)))
+    _ocr_engine.extra_eos = tuple(e for e in gen["eos_token_ids"] if e != EOS)
     print("  [ocr] Model loaded.")
     return _ocr_engine
+
+
+def checkpoint_metadata(path, vlm_config=None, force_greedy: bool = False):
+    """Everything `AutoProcessor.from_pretrained` / `from_pretrained` (tools.py:700-709) read next to the weights, from a
+    LOCAL directory (the hub is not reachable): dimensions from `config.json`, the tokenizer from the HF tokenizer files,
+    the EOS ids from `generation_config.json` (sampling / beams / repetition penalty are refused unless force_greedy).
+    Without a checkpoint: the configured (or 7B-class) dimensions, the synthetic tokenizer, <|im_end|> as EOS.
+    Host-only (no CUDA needed)."""
+    from .vlm_config import HFTokenizer, VLMConfig, greedy_generation_params
+    if not path:
+        return vlm_config or VLMConfig.olmocr_7b(), None, {"eos_token_ids": [EOS]}
+    path = str(path)
+    if not os.path.isdir(path):
+        raise FileNotFoundError(f"checkpoint directory {path} does not exist")
+    cfg = vlm_config or (VLMConfig.from_pretrained_dir(path) if os.path.exists(os.path.join(path, "config.json"))
+                         else VLMConfig.olmocr_7b())
+    tokenizer = None
+    if any(os.path.exists(os.path.join(path, f)) for f in ("tokenizer.json", "vocab.json", "tokenizer_config.json")):
+        tokenizer = HFTokenizer(path)
+    try:
+        gen = greedy_generation_params(path)
+    except NotImplementedError:
+        if not force_greedy:
+            raise
+        gen = {"eos_token_ids": [EOS]}
+    if EOS not in gen["eos_token_ids"]:
+        raise ValueError(f"generation_config.json does not list <|im_end|> ({EOS}) as an EOS id: {gen['eos_token_ids']}")
+    return cfg, tokenizer, gen
 
 
 def unload_ocr_model():

@@ -87,6 +87,49 @@ class VLMConfig:
                    TextCfg(hidden=512, layers=text_layers, heads=4, kv_heads=2, head_dim=128, intermediate=1216,
                            vocab=152064), "tiny")
 
+    @classmethod
+    def from_hf_dict(cls, c: dict, name: str = "checkpoint"):
+        """VLMConfig from a Qwen2.5-VL `config.json` (what `AutoProcessor / from_pretrained` read at tools.py:700-709).
+        Both layouts are accepted: text fields nested under `text_config` with `rope_parameters` (transformers 5.x) or
+        flat at the top level with `rope_theta` + `rope_scaling` (the layout the published checkpoints ship)."""
+        if c.get("model_type") not in (None, "qwen2_5_vl"):
+            raise ValueError(f"model_type {c.get('model_type')!r}: only Qwen2.5-VL-class checkpoints are supported")
+        t = c.get("text_config") or c
+        v = c["vision_config"]
+        rp = t.get("rope_parameters") or t.get("rope_scaling") or c.get("rope_scaling") or {}
+        theta = rp.get("rope_theta", t.get("rope_theta", c.get("rope_theta", 1e6)))
+        heads = int(t["num_attention_heads"])
+        text = TextCfg(hidden=int(t["hidden_size"]), layers=int(t["num_hidden_layers"]), heads=heads,
+                       kv_heads=int(t.get("num_key_value_heads", heads)),
+                       head_dim=int(t.get("head_dim") or int(t["hidden_size"]) // heads),
+                       intermediate=int(t["intermediate_size"]), vocab=int(t["vocab_size"]),
+                       rms_eps=float(t.get("rms_norm_eps", 1e-6)), rope_theta=float(theta),
+                       mrope_section=tuple(int(x) for x in rp.get("mrope_section", (16, 24, 24))))
+        if t.get("tie_word_embeddings", c.get("tie_word_embeddings", False)):
+            raise ValueError("tied input / output embeddings are not supported by the weight layout")
+        if t.get("use_sliding_window", False):
+            raise ValueError("sliding-window text attention is not supported")
+        vis = VisionCfg(depth=int(v["depth"]), hidden=int(v["hidden_size"]), heads=int(v["num_heads"]),
+                        intermediate=int(v["intermediate_size"]), out_hidden=int(v["out_hidden_size"]),
+                        patch=int(v.get("patch_size", v.get("spatial_patch_size", 14))),
+                        temporal_patch=int(v.get("temporal_patch_size", 2)), merge=int(v.get("spatial_merge_size", 2)),
+                        window=int(v.get("window_size", 112)),
+                        fullatt_blocks=tuple(int(x) for x in v.get("fullatt_block_indexes", (7, 15, 23, 31))),
+                        tokens_per_second=int(v.get("tokens_per_second", 2)),
+                        in_channels=int(v.get("in_channels", v.get("in_chans", 3))))
+        if vis.out_hidden != text.hidden:
+            raise ValueError("vision out_hidden_size must equal the text hidden_size")
+        if text.head_dim != 128 or sum(text.mrope_section) * 2 != text.head_dim:
+            raise ValueError("the decode kernels are built for head_dim 128 with an mRoPE split of 64 pairs")
+        return cls(vis, text, name)
+
+    @classmethod
+    def from_pretrained_dir(cls, path: str):
+        import json
+        import os
+        with open(os.path.join(path, "config.json")) as f:
+            return cls.from_hf_dict(json.load(f), name=os.path.basename(os.path.normpath(path)))
+
     def to_hf(self):
         """The equivalent transformers config (used by tests to build the HF oracle)."""
         from transformers import Qwen2_5_VLConfig
@@ -149,6 +192,31 @@ class HFTokenizer:
 
     def decode(self, ids, skip_special_tokens=True):
         return self.tk.decode(ids, skip_special_tokens=skip_special_tokens)
+
+
+def greedy_generation_params(path: str) -> dict:
+    """What `model.generate(**inputs, max_new_tokens=...)` (tools.py:764-765) takes from the checkpoint's
+    `generation_config.json`: only greedy decoding exists here, so a checkpoint that asks for sampling, beams or a
+    repetition penalty is refused loudly instead of being decoded differently from the reference.  Returns the EOS ids."""
+    import json
+    import os
+    fn = os.path.join(path, "generation_config.json")
+    if not os.path.exists(fn):
+        return {"eos_token_ids": [EOS]}
+    with open(fn) as f:
+        g = json.load(f)
+    unsupported = []
+    if g.get("do_sample", False):
+        unsupported.append("do_sample=true")
+    if int(g.get("num_beams", 1)) != 1:
+        unsupported.append(f"num_beams={g['num_beams']}")
+    if float(g.get("repetition_penalty", 1.0)) != 1.0:
+        unsupported.append(f"repetition_penalty={g['repetition_penalty']}")
+    if unsupported:
+        raise NotImplementedError("generation_config.json asks for " + ", ".join(unsupported) + "; this engine decodes "
+                                  "greedily only (pass tools.configure(force_greedy=True) to decode greedily anyway)")
+    eos = g.get("eos_token_id", EOS)
+    return {"eos_token_ids": [int(e) for e in (eos if isinstance(eos, (list, tuple)) else [eos])]}
 
 
 SYSTEM_PROMPT = "You are a helpful assistant."
