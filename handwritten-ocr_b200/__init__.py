@@ -4,8 +4,9 @@ __version__ = "0.1.0"
 
 
 def install():
-    """Route the reference's `ocr_agent.tools` hot functions to this package (see install.py)."""
-    from .install import install as _install
+    """Route the reference's `ocr_agent.tools` hot functions to this package (see dropin.py).  The submodule is not
+    called `install`: importing a submodule binds its name on the package and would replace this function."""
+    from .dropin import install as _install
     return _install()
 
 
