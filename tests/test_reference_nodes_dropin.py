@@ -125,3 +125,85 @@ def test_node_initial_ocr_and_reocr_on_unmodified_nodes(rig, capsys):
     state.update(upd2)
     state.update(nodes.node_reocr(state))
     assert nodes.node_reocr(state) == {"reason": "exhausted", "trace_events": state["trace_events"]}
+
+
+# ───────────── the whole unmodified graph (graph.py) ─────────────
+def _langgraph_shim():
+    """`langgraph` is not installed here; graph.py uses only this much of it (graph.py:5,51-79)."""
+    START, END = "__start__", "__end__"
+
+    class _Compiled:
+        def __init__(self, nodes, edges, cond):
+            self.nodes, self.edges, self.cond = nodes, edges, cond
+
+        def invoke(self, state):
+            state = dict(state)
+            cur = self.edges[START]
+            for _ in range(200):
+                if cur == END:
+                    return state
+                state.update(self.nodes[cur](state) or {})             # partial update, last write wins
+                if cur in self.cond:
+                    route, mapping = self.cond[cur]
+                    cur = mapping[route(state)]
+                else:
+                    cur = self.edges[cur]
+            raise RuntimeError("graph did not terminate")
+
+    class StateGraph:
+        def __init__(self, _state_type):
+            self.nodes, self.edges, self.cond = {}, {}, {}
+
+        def add_node(self, name, fn):
+            self.nodes[name] = fn
+
+        def add_edge(self, a, b):
+            self.edges[a] = b
+
+        def add_conditional_edges(self, a, route, mapping):
+            self.cond[a] = (route, mapping)
+
+        def compile(self):
+            return _Compiled(self.nodes, self.edges, self.cond)
+
+    pkg = types.ModuleType("langgraph")
+    graph = types.ModuleType("langgraph.graph")
+    graph.START, graph.END, graph.StateGraph = START, END, StateGraph
+    pkg.graph = graph
+    return pkg, graph
+
+
+def test_full_graph_reocr_sweep_on_unmodified_graph(rig, monkeypatch, capsys):
+    """graph.py + nodes.py + agents.py unmodified; the LLM side is a fake `call_llm_json` whose critic asks for a re-OCR
+    with strictly rising confidence (a constant one trips the plateau exit: nodes.py:190-194), so the graph sweeps all
+    five configured strategies (BASELINE configs[3]) and stops on 'exhausted'.  All reads of the page come out of ONE
+    batched engine call."""
+    nodes, tools, eng, state, _ = rig
+    conf = iter(range(30, 84, 6))
+
+    def fake_llm(system_prompt, user_msg, json_schema=None, **kw):
+        title = (json_schema or {}).get("title", "")
+        if title == "CriticResult":
+            return {"overall_confidence": next(conf), "segments": [], "verdict": "needs_reocr", "reasoning": "fake"}
+        if title == "ArbitratorResult":
+            return {"final_text": "arbitrated " + user_msg[-40:], "decisions": [], "confidence": 55, "uncertain_segments": []}
+        return {"corrected_text": "edited", "changes": [], "unresolved": []}
+
+    import ocr_agent.agents as agents
+    monkeypatch.setattr(agents, "call_llm_json", fake_llm)
+    lg, lgg = _langgraph_shim()
+    monkeypatch.setitem(sys.modules, "langgraph", lg)
+    monkeypatch.setitem(sys.modules, "langgraph.graph", lgg)
+    sys.modules.pop("ocr_agent.graph", None)
+    import ocr_agent.graph as graph
+    assert graph.__file__.startswith(REF)
+    state["max_iterations"] = 10
+    final = graph.build_ocr_graph().invoke(state)
+    capsys.readouterr()
+    assert final["status"] == "completed" and final["reason"] == "exhausted"
+    assert final["strategies_used"] == ["+".join(s) for s in S]
+    assert [c["source"] for c in final["candidates"]] == ["ocr_" + "+".join(s) for s in S]
+    assert final["iteration"] == 3 and len(final["critiques"]) == 3 and final["current_best"].startswith("arbitrated ")
+    assert eng.calls == [5]
+    actions = [e["action"] for e in final["trace_events"]]
+    assert actions.count("ocr") == 5 and actions.count("arbitrate") == 2 and actions[-1] == "strategies_exhausted"
