@@ -207,3 +207,45 @@ def test_full_graph_reocr_sweep_on_unmodified_graph(rig, monkeypatch, capsys):
     assert eng.calls == [5]
     actions = [e["action"] for e in final["trace_events"]]
     assert actions.count("ocr") == 5 and actions.count("arbitrate") == 2 and actions[-1] == "strategies_exhausted"
+
+
+def test_transcribe_single_unmodified_with_ground_truth(rig, monkeypatch, tmp_path, capsys):
+    """The reference's own entry point (transcribe.py:21-116): graph run, transcription / trace / eval files, CER against a
+    ground-truth file through the `evaluate` this package exports (oracle arithmetic here, the kernel on the GPU)."""
+    import json
+    from pathlib import Path
+    from oracle import text_ref
+    nodes, tools, eng, state, ref_config = rig
+    monkeypatch.setattr(tools, "evaluate", text_ref.evaluate)
+    conf = iter(range(30, 84, 6))
+
+    def fake_llm(system_prompt, user_msg, json_schema=None, **kw):
+        title = (json_schema or {}).get("title", "")
+        if title == "CriticResult":
+            return {"overall_confidence": next(conf), "segments": [], "verdict": "needs_reocr", "reasoning": "fake"}
+        if title == "ArbitratorResult":
+            return {"final_text": "kalo miren tusha veon darel", "decisions": [], "confidence": 55, "uncertain_segments": []}
+        return {"corrected_text": "edited", "changes": [], "unresolved": []}
+
+    import ocr_agent.agents as agents
+    monkeypatch.setattr(agents, "call_llm_json", fake_llm)
+    lg, lgg = _langgraph_shim()
+    monkeypatch.setitem(sys.modules, "langgraph", lg)
+    monkeypatch.setitem(sys.modules, "langgraph.graph", lgg)
+    sys.modules.pop("ocr_agent.graph", None)
+    monkeypatch.setattr(ref_config, "PREPROCESSING_STRATEGIES", S, raising=False)
+    monkeypatch.setattr(ref_config, "AGREEMENT_THRESHOLD", 101, raising=False)
+    import ocr_agent.transcribe as tr
+    assert tr.__file__.startswith(REF)
+    gt = tmp_path / "gt.md"
+    gt.write_text("# page\n\n## Ground Truth\nkalo miren tusha veon darol\n", encoding="utf-8")
+    out_dir = tmp_path / "out"
+    path = tr.transcribe_single(Path(state["image_path"]), out_dir, ground_truth_path=gt, max_iterations=10)
+    capsys.readouterr()
+    assert path.read_text(encoding="utf-8") == "kalo miren tusha veon darel"
+    ev = json.loads((out_dir / "page_eval.json").read_text(encoding="utf-8"))
+    want = text_ref.tier1_metrics("kalo miren tusha veon darol", "kalo miren tusha veon darel")
+    assert ev["tier1_raw_vs_gt"] == want and 0 < want["cer"] < 0.1
+    assert ev["pipeline_status"] == "completed" and ev["iterations"] == 3
+    assert (out_dir / "page_trace.json").exists() and (out_dir / "page_trace_summary.txt").exists()
+    assert eng.calls == [5]
