@@ -234,7 +234,7 @@ __device__ int heap_seed(Heap &h, const uint8_t *rg, int row0, int row1, int ec,
     const unsigned b = __ballot_sync(0xffffffffu, is);
     if (is) {
       const int idx = n + __popc(b & ((1u << lane) - 1));
-      h.set(idx, 0u, (uint32_t)idx, row0 * ec + q);
+      h.set(idx, 0u, (uint32_t)idx, ((row0 + q / ec) << 16) | (q % ec));
     }
     n += __popc(b);
   }
@@ -265,12 +265,13 @@ __device__ __forceinline__ float fmm_solve(const uint8_t *f, const float *t, int
 
 // Lanes 0..15: lane = 4 * neighbour + solve.  Returns (for every lane of a neighbour group) whether that neighbour of p
 // is still INSIDE in `f`, and its arrival time (minimum of the four solves).
-__device__ __forceinline__ bool neighbour_dist(const uint8_t *f, const float *t, int p, int er, int ec, int lane, int &nb,
-                                               float &dist) {
+__device__ __forceinline__ bool neighbour_dist(const uint8_t *f, const float *t, int pk, int er, int ec, int lane, int &nb,
+                                               int &nb_pk, float &dist) {
   const int q = (lane >> 2) & 3, s = lane & 3;
-  const int ii = p / ec, jj = p - ii * ec;
+  const int ii = pk >> 16, jj = pk & 0xffff;             // queue entries carry (row << 16 | column): no division per pop
   const int i = ii + (q == 0 ? -1 : q == 2 ? 1 : 0), j = jj + (q == 1 ? -1 : q == 3 ? 1 : 0);
   nb = i * ec + j;
+  nb_pk = (i << 16) | j;
   bool valid = lane < 16 && !(i <= 0 || j <= 0 || i > er - 1 || j > ec - 1);
   valid = valid && f[nb] == F_INSIDE;
   float d = 3.0e38f;
@@ -389,8 +390,8 @@ __device__ void painter_loop(int k, int lane, volatile InpSync *sy, const int32_
     }
     outside_seen = true;
     __threadfence_block();
-    const int p = job[n];
-    const int i = p / ec, j = p - i * ec;
+    const int pk = job[n];
+    const int i = pk >> 16, j = pk & 0xffff, p = i * ec + j;
     const float tij = t[p];
     float gx, gy;
     {
@@ -564,25 +565,26 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
     if (warp == 0) {
       // march outwards through the ring: distances there, negated afterwards
       for (;;) {
-        const int p = heap_pop(h, lane);
-        if (p < 0) break;
+        const int pk = heap_pop(h, lane);
+        if (pk < 0) break;
+        const int p = (pk >> 16) * ec + (pk & 0xffff);
         if (lane == 0) rg[p] = rg[p] == F_SEED ? F_SEED_DONE : F_CHANGE;
         __syncwarp();
-        int nb;
+        int nb, nbk;
         float d;
-        const bool valid = neighbour_dist(rg, t, p, er, ec, lane, nb, d);
+        const bool valid = neighbour_dist(rg, t, pk, er, ec, lane, nb, nbk, d);
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const bool vq = __shfl_sync(0xffffffffu, (int)valid, 4 * q) != 0;
           const float dq = __shfl_sync(0xffffffffu, d, 4 * q);
-          const int nq = __shfl_sync(0xffffffffu, nb, 4 * q);
+          const int nq = __shfl_sync(0xffffffffu, nb, 4 * q), nk = __shfl_sync(0xffffffffu, nbk, 4 * q);
           if (vq) {
             if (lane == 0) {
               t[nq] = dq;
               rg[nq] = F_BAND;
             }
-            heap_push(h, nq, dq, lane);
+            heap_push(h, nk, dq, lane);
           }
         }
       }
@@ -598,30 +600,31 @@ inp_march_kernel(uint8_t *__restrict__ dst, InpWs w, int H, int W, int range, in
       // march inwards: arrival times of the mask pixels and the order in which they are painted
       int n = 0;
       for (;;) {
-        const int p = heap_pop(h, lane);
-        if (p < 0) break;
+        const int pk = heap_pop(h, lane);
+        if (pk < 0) break;
+        const int p = (pk >> 16) * ec + (pk & 0xffff);
         if (lane == 0) f[p] = F_KNOWN;
         __syncwarp();
-        int nb;
+        int nb, nbk;
         float d;
-        const bool valid = neighbour_dist(f, t, p, er, ec, lane, nb, d);
+        const bool valid = neighbour_dist(f, t, pk, er, ec, lane, nb, nbk, d);
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const bool vq = __shfl_sync(0xffffffffu, (int)valid, 4 * q) != 0;
           const float dq = __shfl_sync(0xffffffffu, d, 4 * q);
-          const int nq = __shfl_sync(0xffffffffu, nb, 4 * q);
+          const int nq = __shfl_sync(0xffffffffu, nb, 4 * q), nk = __shfl_sync(0xffffffffu, nbk, 4 * q);
           if (vq) {
             if (lane == 0) {
               t[nq] = dq;
               f[nq] = F_BAND;
               stamp[nq] = n;
-              job[n] = nq;
+              job[n] = nk;
             }
             __threadfence_block();
             if (lane == 0) sy->jobs_ready = n + 1;
             ++n;
-            heap_push(h, nq, dq, lane);
+            heap_push(h, nk, dq, lane);
           }
         }
       }
@@ -664,7 +667,7 @@ extern "C" int ocrb_inpaint_telea_u8(const uint8_t *src, const uint8_t *mask, ui
   OCRB_REQUIRE(H >= 2 && W >= 2, "inpaint_telea_u8: pages one pixel high or wide are not supported (OpenCV reads outside them)");
   OCRB_REQUIRE(radius >= 1 && radius <= INP_MAX_RANGE, "inpaint_telea_u8: radius must be in 1..7");
   OCRB_REQUIRE(src != dst && ((uintptr_t)ws & 15) == 0, "inpaint_telea_u8: in-place not supported; workspace must be 16-byte aligned");
-  OCRB_REQUIRE((size_t)(H + 2) * (W + 2) * 3 < ((size_t)1 << 31) && H + 2 <= 65535 && n_img <= 65535, "inpaint_telea_u8: page too large");
+  OCRB_REQUIRE((size_t)(H + 2) * (W + 2) * 3 < ((size_t)1 << 31) && H + 2 <= 32767 && W + 2 <= 65535 && n_img <= 65535, "inpaint_telea_u8: page too large");
   cudaStream_t st = (cudaStream_t)stream;
   InpWs w;
   inp_layout(&w, ws, n_img, H, W);
