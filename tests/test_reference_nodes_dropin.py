@@ -249,3 +249,37 @@ def test_transcribe_single_unmodified_with_ground_truth(rig, monkeypatch, tmp_pa
     assert ev["pipeline_status"] == "completed" and ev["iterations"] == 3
     assert (out_dir / "page_trace.json").exists() and (out_dir / "page_trace_summary.txt").exists()
     assert eng.calls == [5]
+
+
+def test_eval_final_batch_mode_unmodified(rig, monkeypatch, tmp_path, capsys, synth):
+    """eval_final.main() in directory mode (eval_final.py:94-134), unmodified: every file goes through the `evaluate` /
+    `parse_ground_truth` this package exports under `ocr_agent.tools`."""
+    import json
+    from oracle import text_ref
+    nodes, tools, eng, state, _ = rig
+    monkeypatch.setattr(tools, "evaluate", text_ref.evaluate)
+    res, gtd = tmp_path / "results", tmp_path / "gt"
+    res.mkdir()
+    gtd.mkdir()
+    want = {}
+    for i in range(3):
+        gt = synth.text(20 + i, 60)
+        ocr = synth.corrupt(gt, i, 0.04 * (i + 1))
+        (res / f"p{i}_transcription.txt").write_text(ocr, encoding="utf-8")
+        (gtd / f"p{i}.md").write_text(f"notes\n## Ground Truth\n{gt}\n", encoding="utf-8")
+        want[f"p{i}"] = text_ref.tier1_metrics(gt.strip(), ocr)
+    (res / "p9_transcription.txt").write_text("no ground truth for this one", encoding="utf-8")
+    import ocr_agent.eval_final as ef
+    assert ef.__file__.startswith(REF)
+    out = tmp_path / "eval.json"
+    monkeypatch.setattr(sys, "argv", ["eval_final", str(res), "--ground-truth-dir", str(gtd), "--output", str(out)])
+    ef.main()
+    text = capsys.readouterr().out
+    got = json.loads(out.read_text(encoding="utf-8"))
+    assert len(got) == 4 and "Batch Summary (3 files with GT)" in text
+    for r in got:
+        stem = os.path.basename(r["file"])[: -len("_transcription.txt")]
+        if stem in want:
+            assert r["tier1_raw_vs_gt"] == want[stem], stem
+        else:
+            assert "tier1_raw_vs_gt" not in r
