@@ -434,14 +434,9 @@ __device__ void painter_loop(int k, int lane, volatile InpSync *sy, const int32_
     const float Jy = __shfl_sync(0xffffffffu, acc, 6 + c), s = __shfl_sync(0xffffffffu, acc, 9);
     INP_PHASE(4)                                               // 4: ordered sums
     if (lane < C) {
-      // sat = Ia/s + (Jx+Jy)/(sqrt(Jx^2+Jy^2) + 1e-20) with the second term in double, then round(sat + 0.5).  The
-      // result only changes where sat crosses an integer, so an all-float estimate (error < 1e-4: the term is at most
-      // sqrt 2, |sat| < ~300) settles every case that is not within 1/64 of one; the rest take OpenCV's exact steps.
-      const float q1 = Ia / s, ss = Jx * Jx + Jy * Jy;
-      float sat = q1 + (Jx + Jy) / (sqrtf(ss) + 1.0e-20f);
-      const float fr = sat - floorf(sat);
-      if (!(fr > 0.015625f && fr < 0.984375f) || !(fabsf(sat) < 1.0e6f))
-        sat = (float)(q1 + (Jx + Jy) / (sqrt((double)ss) + (double)1.0e-20f));
+      // OpenCV evaluates the whole expression in float (quotient, sum of squares, square root, quotient, sum), adds
+      // 0.5f and rounds half to even; IEEE division and square root here (no fast-math), -fmad=false for the sums
+      const float sat = Ia / s + (Jx + Jy) / (sqrtf(Jx * Jx + Jy * Jy) + 1.0e-20f);
       const int v = __float2int_rn(sat + 0.5f);
       out[((i - 1) * W + (j - 1)) * C + lane] = (uint8_t)min(max(v, 0), 255);
     }

@@ -73,8 +73,8 @@ int ocrb_sharpen3x3_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t 
 int ocrb_remove_lines_mask_u8(const uint8_t *src, uint8_t *mask, int32_t *nonzero, uint8_t *tmp, int32_t n_img,
                               int32_t H, int32_t W, int32_t C, void *stream);
 
-/* tools.py:617 cv2.inpaint(img, mask, radius, cv2.INPAINT_TELEA), bit-exact against OpenCV 4.13 (the reference passes
- * radius 3; 1..7 accepted).  src, dst: uint8[n_img*H*W*C], C = 1 or 3, src != dst; mask: uint8[n_img*H*W], non-zero =
+/* tools.py:617 cv2.inpaint(img, mask, radius, cv2.INPAINT_TELEA), bit-exact against OpenCV 4.13 at radius 3, the radius the
+ * reference passes (1..7 accepted; at radii other than 2 and 3 a few flat-region pixels can differ from OpenCV by 1-4).  src, dst: uint8[n_img*H*W*C], C = 1 or 3, src != dst; mask: uint8[n_img*H*W], non-zero =
  * repaint; pages with an empty mask are copied.  H, W >= 2.  ws: ocrb_inpaint_workspace_bytes(n_img, H, W) bytes,
  * 16-byte aligned, contents irrelevant.  Row segments of the mask separated by 2*radius+2 clean rows are marched
  * concurrently (one warp each); within a segment the march order is OpenCV's. */

@@ -7,6 +7,9 @@
  * first march outwards to get negative distances in a `range`-wide ring, then the inward march that paints each pixel
  * from the known pixels of its disc) and is pinned against the installed wheel on random masks, ruled pages and edge
  * cases in tests/test_remove_lines.py, and against golden outputs of the unmodified reference (tests/golden).
+ * Pinned at radius 3, the only radius the reference passes (8000 random cases equal to cv2); radius 2 is equal on every
+ * case tried as well; at other radii a few pixels of flat regions, where the gradient term is pure rounding residue,
+ * can differ from cv2 by 1-4 grey levels.
  *
  * Build: oracle/Makefile (gcc -O2 -ffp-contract=off; the float / double steps below matter bit for bit).
  */
@@ -164,8 +167,10 @@ static void telea_pixel(const uint8_t *f, const float *t, uint8_t *out, int er, 
     }
   }
   for (int c = 0; c < C; c++) {
-    /* float quotient and float sum of squares; the square root, the second quotient and the sum are double */
-    const float sat = (float)(Ia[c] / s[c] + (Jx[c] + Jy[c]) / (sqrt(Jx[c] * Jx[c] + Jy[c] * Jy[c]) + 1.0e-20f));
+    /* all float: quotient, sum of squares, square root, second quotient, sum -- then + 0.5f and round half to even.
+     * (Pinned at radius 3 on 8000 random images / masks against cv2 4.13; a double square root here differs from cv2
+     * on about 1 image in 1000.) */
+    const float sat = Ia[c] / s[c] + (Jx[c] + Jy[c]) / (sqrtf(Jx[c] * Jx[c] + Jy[c] * Jy[c]) + 1.0e-20f);
     long v = lrintf(sat + 0.5f); /* OpenCV adds 0.5 and THEN rounds half to even (saturate_cast<uchar>) */
     out[((size_t)(i - 1) * W + (j - 1)) * C + c] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
   }

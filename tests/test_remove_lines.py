@@ -109,6 +109,33 @@ def test_oracle_inpaint_vs_cv2():
     assert np.array_equal(R.inpaint_telea(img, empty), img)
 
 
+def test_oracle_inpaint_vs_cv2_many_small():
+    """3000 small images at radius 3 (random, quantised, constant, blurred, paper-like; sparse to dense masks, bars):
+    the cases where only rounding residue decides a pixel.  A double-precision square root in the final quotient -- an
+    earlier form of the oracle -- fails about 1 in 1000 of these."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(777)
+    for it in range(3000):
+        H, W = int(rng.integers(2, 34)), int(rng.integers(2, 40))
+        C = int(rng.choice([1, 3]))
+        im = rng.integers(0, 256, (H, W, 3) if C == 3 else (H, W), dtype=np.uint8)
+        k = it % 6
+        if k == 1:
+            im = (im // 64 * 64 + 10).astype(np.uint8)
+        if k == 2:
+            im[:] = rng.integers(0, 256)
+        if k == 3 and H > 4 and W > 4:
+            im = cv2.GaussianBlur(im, (5, 5), 0)
+        if k == 4:
+            im = np.clip(228 + rng.integers(-10, 11, im.shape), 0, 255).astype(np.uint8)
+        m = (rng.random((H, W)) < rng.choice([0.03, 0.1, 0.3, 0.6, 0.9])).astype(np.uint8)
+        if k == 5:
+            m[:] = 0
+            y = int(rng.integers(0, H))
+            m[y:y + int(rng.integers(1, 5)), int(rng.integers(0, max(W // 2, 1))):] = 1
+        assert np.array_equal(R.inpaint_telea(im, m), cv2.inpaint(im, m, 3, cv2.INPAINT_TELEA)), (it, im.shape)
+
+
 @pytest.mark.gpu
 def test_gpu_inpaint_random(pkg):
     """The march kernel against the oracle: random masks (one segment, many segments, everything masked), bars on the
