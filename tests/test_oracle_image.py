@@ -121,3 +121,23 @@ def test_smart_resize_cases():
     assert R.smart_resize(100, 100) == (280, 280) or R.smart_resize(100, 100)[0] % 28 == 0
     h, w = R.smart_resize(3000, 4000)
     assert h * w <= 1024 * 1024 and h % 28 == 0 and w % 28 == 0
+
+
+def test_pixel_values_vs_hf_random_sizes():
+    """The image-processor oracle (smart_resize -> uint8 bicubic-antialias resize -> normalize -> patchify) against
+    HF's Qwen2VLImageProcessor itself on random sizes: upscaled, downscaled, extreme aspect ratios, no resize."""
+    from PIL import Image
+    tr = pytest.importorskip("transformers")
+    ip = tr.Qwen2VLImageProcessor(min_pixels=256 * 256, max_pixels=1024 * 1024)
+    rng = np.random.default_rng(4)
+    sizes = [(768, 1024), (56, 56), (761, 105), (117, 704), (1105, 911), (1133, 1041), (44, 1436), (1092, 532)]
+    for it, (H, W) in enumerate(sizes):
+        a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        if it % 3 == 0:
+            a = np.repeat(np.repeat(rng.integers(0, 256, (H // 8 + 1, W // 8 + 1, 3), dtype=np.uint8), 8, 0), 8, 1)[:H, :W]
+        r = ip(images=[Image.fromarray(a)], return_tensors="np")
+        rh, rw = R.smart_resize(H, W)
+        x = a if (rh, rw) == (H, W) else R.resize_bicubic_aa_u8(a, rh, rw)
+        pv, grid = R.normalize_patchify(x)
+        assert list(grid) == [int(v) for v in r["image_grid_thw"][0]], (H, W)
+        assert np.array_equal(pv.astype(np.float32), r["pixel_values"].astype(np.float32)), (H, W)
