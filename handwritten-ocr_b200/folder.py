@@ -10,7 +10,12 @@ box; `gloo` in the CPU tests).
 """
 from __future__ import annotations
 
+import json
+import sys
+from pathlib import Path
 from typing import Callable, Sequence
+
+IMAGE_EXTENSIONS = {".png", ".jpg", ".jpeg", ".bmp", ".tiff", ".tif", ".webp"}     # transcribe.py:18
 
 
 def shard_pages(n_pages: int, rank: int, world: int) -> list:
@@ -58,3 +63,139 @@ def read_folder(pages: Sequence, read_page: Callable, *, rank: int = 0, world: i
             raise RuntimeError("read_page must return one result per page")
         local.update(dict(zip(idx, out)))
     return gather_results(local, len(pages), group)
+
+
+# ───────────────────────── f1: the folder-batch driver (transcribe.py:185-210) ─────────────────────────
+def list_images(input_dir) -> list:
+    """transcribe.py:193-195: the images of a folder, sorted."""
+    return sorted(f for f in Path(input_dir).iterdir() if f.suffix.lower() in IMAGE_EXTENSIONS)
+
+
+def match_ground_truth(stem: str, ground_truth_dir):
+    """transcribe.py:201-207 / eval_final.py:107-117: `<stem>.md`, then `<stem>.txt`."""
+    if ground_truth_dir is None:
+        return None
+    for ext in (".md", ".txt"):
+        cand = Path(ground_truth_dir) / f"{stem}{ext}"
+        if cand.exists():
+            return cand
+    return None
+
+
+def initial_ocr_page(image_path: str, strategies=None, agreement_threshold=None, tools=None) -> dict:
+    """The read phase of one page exactly as `node_initial_ocr` sequences it (nodes.py:76-134, trace and LLM parts
+    left out): reads S0 and S1, `compare_versions`, the tiebreaker read S2 when the agreement is below the threshold,
+    `merge_versions`, `unload_ocr_model`.  Returns the node's state keys (candidate dicts as nodes.py:53-58 builds
+    them) plus the comparison.  This is the per-page function of the folder driver when the reference's own
+    `transcribe_single` (which also runs the LLM critic / editor over Ollama) is not what is wanted."""
+    if tools is None:
+        from . import tools
+    cfg = tools.config
+    strategy_list = list(strategies if strategies is not None else cfg.PREPROCESSING_STRATEGIES)
+    threshold = cfg.AGREEMENT_THRESHOLD if agreement_threshold is None else agreement_threshold
+    candidates, used = [], []
+
+    def one_pass(strategy):
+        label = "+".join(strategy) if isinstance(strategy, list) else strategy
+        if label in used:
+            return
+        used.append(label)
+        text = tools.run_ocr(tools.preprocess_image(image_path, strategy))
+        candidates.append({"text": text, "source": f"ocr_{label}", "ocr_params": {"strategy": label}, "score": None})
+
+    one_pass(strategy_list[0] if strategy_list else "original")
+    if len(strategy_list) > 1:
+        one_pass(strategy_list[1])
+    cmp = None
+    if len(candidates) >= 2:
+        cmp = tools.compare_versions(candidates[0]["text"], candidates[1]["text"])
+        if cmp["agreement_rate"] < threshold and len(strategy_list) > 2:
+            one_pass(strategy_list[2])
+    best = tools.merge_versions([c["text"] for c in candidates])
+    tools.unload_ocr_model()
+    return {"candidates": candidates, "current_best": best, "strategies_used": used, "comparison": cmp}
+
+
+def _reference_transcribe_single():
+    try:
+        from ocr_agent.transcribe import transcribe_single          # the reference's own per-page entry point
+    except Exception as e:                                          # pragma: no cover - no reference tree
+        raise RuntimeError("transcribe_folder needs `page_fn` or an importable `ocr_agent.transcribe` "
+                           f"(the reference package): {e}")
+    return transcribe_single
+
+
+def transcribe_folder(input_dir, output_dir=None, ground_truth_dir=None, *, pages_per_batch: int = 21,
+                      page_fn: Callable | None = None, rank: int = 0, world: int = 1, group=None, tools=None,
+                      strategies=None, **page_kwargs):
+    """Directory mode of `transcribe.main` (transcribe.py:185-210) with the reads batched across pages.
+
+    The reference loops `transcribe_single(image, output_dir, gt)` over the sorted images, each page reading its
+    candidates one by one.  Here this rank's pages (page i -> rank i mod world) are taken `pages_per_batch` at a time:
+    `tools.prime` preprocesses every configured strategy of those pages and reads ALL their candidates in one batched
+    vision / prefill / paged-KV decode pass; then the per-page function runs page by page and finds its
+    `preprocess_image` / `run_ocr` calls answered from the cache.  `page_fn(image_path, output_dir, gt_path, **kw)`
+    defaults to the reference's UNMODIFIED `transcribe_single` (install this package as `ocr_agent.tools` first:
+    `handwritten_ocr_b200.install()`).  Returns, on rank 0, the per-page results in folder order (others: None)."""
+    if tools is None:
+        from . import tools
+    input_dir = Path(input_dir)
+    images = list_images(input_dir)
+    if not images:
+        raise FileNotFoundError(f"No image files found in {input_dir}")
+    output_dir = Path(output_dir) if output_dir is not None else input_dir / "results"     # transcribe.py:167-168
+    fn = page_fn or _reference_transcribe_single()
+    if pages_per_batch > int(tools._options["cache_pages"]):
+        tools.configure(cache_pages=pages_per_batch)
+
+    def read_batch(batch_images):
+        tools.prime([str(p) for p in batch_images], strategies)
+        out = []
+        for img in batch_images:
+            out.append(fn(img, output_dir, match_ground_truth(img.stem, ground_truth_dir), **page_kwargs))
+            tools.forget(str(img))
+        return out
+
+    return read_folder(images, read_batch, rank=rank, world=world, pages_per_batch=pages_per_batch, group=group)
+
+
+# ───────────────────────── f2: the batch evaluator (eval_final.py:94-134) ─────────────────────────
+def eval_folder(results_dir, ground_truth_dir=None, output=None, *, lower: bool = False, tools=None,
+                textops=None, verbose: bool = False) -> list:
+    """Directory mode of `eval_final.main` (eval_final.py:94-134): every `*_transcription.txt` (else `*.txt`) of the
+    folder against the ground-truth file of the same stem.  The reference evaluates the files one after another
+    (3 pure-Python Levenshtein DPs each); here the 3 x N distances of ALL files go to the GPU in ONE
+    `ocrb_levenshtein_batch` launch.  Returns the list `eval_final.main` collects (and writes to `output` as the same
+    JSON): per file the `evaluate()` dict plus `"file"`."""
+    if tools is None:
+        from . import tools
+    if textops is None:
+        from . import textops
+    results_dir = Path(results_dir).resolve()
+    txt_files = sorted(results_dir.glob("*_transcription.txt")) or sorted(results_dir.glob("*.txt"))
+    if not txt_files:
+        raise FileNotFoundError(f"No .txt files found in {results_dir}")
+    texts, gts = [], []
+    for txt in txt_files:
+        stem = txt.stem[: -len("_transcription")] if txt.stem.endswith("_transcription") else txt.stem
+        gt_path = match_ground_truth(stem, ground_truth_dir)
+        texts.append(txt.read_text(encoding="utf-8"))
+        gts.append(tools.parse_ground_truth(gt_path) if gt_path else None)
+    with_gt = [i for i, g in enumerate(gts) if g is not None]
+    metrics = textops.tier1_metrics_batch([(gts[i], texts[i]) for i in with_gt], lower) if with_gt else []
+    by_index = dict(zip(with_gt, metrics))
+    results = []
+    for i, txt in enumerate(txt_files):
+        r = {}
+        if i in by_index:
+            r["tier1_raw_vs_gt"] = by_index[i]
+        r["file"] = str(txt)
+        results.append(r)
+    if verbose and metrics:
+        print(f"Batch Summary ({len(metrics)} files with GT)")
+        print(f"  Avg CER: {sum(m['cer'] for m in metrics) / len(metrics):.2%}")
+        print(f"  Avg WER: {sum(m['wer_token'] for m in metrics) / len(metrics):.2%}")
+    if output is not None:
+        with open(output, "w", encoding="utf-8") as f:
+            json.dump(results, f, indent=2, ensure_ascii=False)
+    return results

@@ -20,7 +20,9 @@ from __future__ import annotations
 
 import gc
 import os
+import sys
 import tempfile
+from collections import OrderedDict
 from pathlib import Path
 
 import numpy as np
@@ -49,13 +51,61 @@ _options = {
     "max_batch": 8,
     "seed": 0,
     "force_greedy": False,      # decode greedily even if the checkpoint's generation_config.json asks for sampling
+    "cache_pages": 64,          # originals whose preprocessed variants / texts stay cached (LRU)
+    "delete_evicted_files": True,   # remove the temp files of an evicted page (the reference leaks them: tools.py:670)
 }
-# processed path -> (device tensor [1,H,W(,3)], original path, label)
-_processed: dict = {}
-# original path -> {label: text}
-_texts: dict = {}
-# original path -> {label: processed path}
-_by_original: dict = {}
+# Cache of preprocessed pages and their transcriptions, keyed by the ORIGINAL image and guarded by the file's
+# (mtime_ns, size) signature: a changed file invalidates its entry.  Bounded LRU over originals (`cache_pages`): the
+# reference's callers never say when they are done with a page (nodes.py calls unload_ocr_model() between the
+# initial reads and the reocr sweep of the SAME page, so that call must not drop the page), hence eviction by age.
+class _Page:
+    __slots__ = ("sig", "variants", "texts")
+
+    def __init__(self, sig):
+        self.sig = sig
+        self.variants = {}          # label -> (processed path, device tensor [1,H,W(,3)])
+        self.texts = {}             # label -> transcription
+
+
+_pages: "OrderedDict[str, _Page]" = OrderedDict()
+_processed: dict = {}               # processed path -> (original path, label)
+
+
+def _signature(path: str):
+    st = os.stat(path)
+    return (st.st_mtime_ns, st.st_size)
+
+
+def _drop_page(original: str) -> None:
+    page = _pages.pop(original, None)
+    if page is None:
+        return
+    for path, _ in page.variants.values():
+        _processed.pop(path, None)
+        if _options["delete_evicted_files"]:
+            try:
+                os.unlink(path)
+            except OSError:
+                pass
+
+
+def _page_for(original: str, create: bool = True):
+    """The cache entry of an original image (most recently used last); a stale entry (file changed on disk)
+    is dropped first."""
+    sig = _signature(original)
+    page = _pages.get(original)
+    if page is not None and page.sig != sig:
+        _drop_page(original)
+        page = None
+    if page is None:
+        if not create:
+            return None
+        page = _pages[original] = _Page(sig)
+        while len(_pages) > max(1, int(_options["cache_pages"])):
+            _drop_page(next(iter(_pages)))
+    else:
+        _pages.move_to_end(original)
+    return page
 
 
 def configure(**kw) -> None:
@@ -93,6 +143,39 @@ def _save(arr: np.ndarray, image_path: str, label: str) -> str:
     return tmp.name
 
 
+def _wanted_strategies(steps) -> list:
+    wanted = [steps]
+    if _options["speculative"]:
+        for s in getattr(config, "PREPROCESSING_STRATEGIES", []):
+            s = _steps(s)
+            if _label(s) and all(_label(s) != _label(w) for w in wanted):
+                wanted.append(s)
+    return wanted
+
+
+def _preprocess_page(image_path: str, wanted: list, required_label: str | None) -> "_Page":
+    """Apply every strategy of `wanted` that the cache does not hold yet.  A failure in a SPECULATIVE strategy
+    (one the caller did not ask for) is reported and skipped: the reference would never have run it here."""
+    page = _page_for(image_path)
+    todo = [s for s in wanted if _label(s) not in page.variants]
+    if not todo:
+        return page
+    x = preprocess.to_device(_open_array(image_path))
+    for s in todo:
+        lab = _label(s)
+        try:
+            y = preprocess.apply_strategy(x, s)
+            path = _save(y[0].cpu().numpy(), image_path, lab)
+        except Exception as e:
+            if lab == required_label:
+                raise
+            print(f"  [preprocess] speculative {lab} skipped: {e}", file=sys.stderr)
+            continue
+        page.variants[lab] = (path, y)
+        _processed[path] = (image_path, lab)
+    return page
+
+
 def preprocess_image(image_path: str, strategy) -> str:
     """tools.py:633-673: apply the strategy on the GPU, save a temp file with the input's suffix,
     return its path ("original" / [] return the input path untouched)."""
@@ -101,29 +184,12 @@ def preprocess_image(image_path: str, strategy) -> str:
         return image_path
     label = _label(steps)
     print(f"  [preprocess] Applying {label}...")
-    cached = _by_original.get(image_path, {}).get(label)
-    if cached is not None and os.path.exists(cached):
-        return cached
-    arr = _open_array(image_path)
-    x = preprocess.to_device(arr)
-    wanted = [steps]
-    if _options["speculative"]:
-        for s in getattr(config, "PREPROCESSING_STRATEGIES", []):
-            s = _steps(s)
-            if _label(s) and all(_label(s) != _label(w) for w in wanted):
-                wanted.append(s)
-    result = None
-    for s in wanted:
-        lab = _label(s)
-        if lab in _by_original.get(image_path, {}):
-            continue
-        y = preprocess.apply_strategy(x, s)
-        path = _save(y[0].cpu().numpy(), image_path, lab)
-        _processed[path] = (y, image_path, lab)
-        _by_original.setdefault(image_path, {})[lab] = path
-        if s is steps:
-            result = path
-    return result if result is not None else _by_original[image_path][label]
+    page = _preprocess_page(image_path, _wanted_strategies(steps), label)
+    path, y = page.variants[label]
+    if not os.path.exists(path):
+        # somebody removed the temp file: write it again from the cached page
+        Image.fromarray(y[0].cpu().numpy()).save(path)
+    return path
 
 
 def _load_ocr_model():
@@ -203,6 +269,49 @@ def _load_page_for_model(image_path: str) -> torch.Tensor:
     return preprocess.to_device(np.array(img))
 
 
+def _read_pending(engine, originals: list, prompt: str, max_new_tokens: int, first=None) -> None:
+    """One batched read (per page shape) of every cached variant of `originals` that has no text yet -- at most
+    engine.max_batch sequences per read, `first` = (original, label) goes into the first batch."""
+    todo = []
+    for orig in originals:
+        page = _pages.get(orig)
+        if page is None:
+            continue
+        todo += [(orig, lab) for lab in page.variants if lab not in page.texts]
+    if first is not None and first in todo:
+        todo.remove(first)
+        todo.insert(0, first)
+    groups: dict = {}
+    for orig, lab in todo:
+        groups.setdefault(tuple(_pages[orig].variants[lab][1].shape), []).append((orig, lab))
+    for same in groups.values():
+        for i0 in range(0, len(same), engine.max_batch):
+            part = same[i0:i0 + engine.max_batch]
+            batch = torch.cat([_pages[o].variants[lab][1] for o, lab in part], 0)
+            toks = engine.read_batch(batch, prompt=prompt, max_new_tokens=max_new_tokens)
+            for (o, lab), tk in zip(part, toks):
+                _pages[o].texts[lab] = engine.detokenize(tk)
+
+
+def prime(image_paths, strategies=None) -> None:
+    """Folder mode (transcribe.py:193-209 runs the pages one after another): preprocess the configured strategies of
+    SEVERAL pages and read all their candidates in one batch, so that the per-page `preprocess_image` / `run_ocr`
+    calls the unmodified `transcribe_single` makes afterwards are cache hits.  `cache_pages` must cover the pages."""
+    engine = _load_ocr_model()
+    strategies = [_steps(s) for s in (strategies if strategies is not None else
+                                      getattr(config, "PREPROCESSING_STRATEGIES", []))]
+    strategies = [s for s in strategies if _label(s)]
+    paths = [str(p) for p in image_paths]
+    if len(paths) > int(_options["cache_pages"]):
+        raise ValueError(f"prime(): {len(paths)} pages exceed cache_pages={_options['cache_pages']}")
+    import contextlib
+    import io
+    for p in paths:
+        _preprocess_page(p, strategies, None)
+    with contextlib.redirect_stdout(io.StringIO()):
+        _read_pending(engine, paths, config.OCR_PROMPT, int(config.OCR_MAX_NEW_TOKENS))
+
+
 def run_ocr(image_path: str, params: dict | None = None) -> str:
     """tools.py:728-771: greedy transcription of the (already preprocessed) image."""
     print(f"  [ocr] Running OCR on {Path(image_path).name}...")
@@ -212,28 +321,17 @@ def run_ocr(image_path: str, params: dict | None = None) -> str:
     max_new_tokens = int(params.get("max_new_tokens", config.OCR_MAX_NEW_TOKENS))
     default_call = "prompt" not in params and "max_new_tokens" not in params
     entry = _processed.get(image_path)
+    page = _pages.get(entry[0]) if entry is not None else None
     lossless = Path(image_path).suffix.lower() in _LOSSLESS
-    if entry is not None and lossless and default_call:
-        _, original, label = entry
-        texts = _texts.setdefault(original, {})
-        if label not in texts:
+    if page is not None and lossless and default_call:
+        original, label = entry
+        if label not in page.texts:
             # one batched read for every preprocessed variant of this page that has no text yet
-            todo = [(lab, p) for lab, p in _by_original.get(original, {}).items() if lab not in texts]
-            todo = todo[: engine.max_batch]
-            if (label, image_path) not in todo:
-                todo = [(label, image_path)] + todo[: engine.max_batch - 1]
-            groups: dict = {}
-            for lab, p in todo:
-                groups.setdefault(tuple(_processed[p][0].shape), []).append((lab, p))
-            for same in groups.values():
-                batch = torch.cat([_processed[p][0] for _, p in same], 0)
-                toks = engine.read_batch(batch, prompt=prompt, max_new_tokens=max_new_tokens)
-                for (lab, _), tk in zip(same, toks):
-                    texts[lab] = engine.detokenize(tk)
-        result = texts[label]
+            _read_pending(engine, [original], prompt, max_new_tokens, first=(original, label))
+        result = page.texts[label]
     else:
-        page = entry[0] if (entry is not None and lossless) else _load_page_for_model(image_path)
-        toks = engine.read_batch(page, prompt=prompt, max_new_tokens=max_new_tokens)
+        x = page.variants[entry[1]][1] if (page is not None and lossless) else _load_page_for_model(image_path)
+        toks = engine.read_batch(x, prompt=prompt, max_new_tokens=max_new_tokens)
         result = engine.detokenize(toks[0])
     print(f"  [ocr] Done ({len(result)} chars)")
     return result
@@ -246,11 +344,8 @@ def transcribe(image: str, strategy) -> str:
 
 def forget(image_path: str | None = None) -> None:
     """Drop cached preprocessed pages / texts (all, or those of one original)."""
-    keys = [image_path] if image_path else list(_by_original)
-    for k in keys:
-        for p in _by_original.pop(k, {}).values():
-            _processed.pop(p, None)
-        _texts.pop(k, None)
+    for k in ([image_path] if image_path else list(_pages)):
+        _drop_page(k)
 
 
 # non-hot names the reference's callers import from tools (agents.py:12, transcribe.py:33,

@@ -184,6 +184,36 @@ def random_state_dict_text_only(cfg: VLMConfig, device, seed: int, vocab_rows: i
     return sd
 
 
+def normalize_checkpoint_key(key: str) -> str:
+    """Checkpoint tensor name -> the name HF's Qwen2_5_VLForConditionalGeneration holds after `from_pretrained`
+    (transformers conversion_mapping: `^visual` -> `model.visual`, `^model.(?!language_model|visual)` ->
+    `model.language_model.`).  New-style names pass through unchanged."""
+    if key.startswith("visual."):
+        return "model." + key
+    if key.startswith("model.") and not key.startswith(("model.language_model.", "model.visual.")):
+        return "model.language_model." + key[len("model."):]
+    return key
+
+
+def expected_state_dict_keys(cfg: VLMConfig) -> list:
+    """Every tensor name `VLMWeights.from_state_dict` consumes for this config (HF naming after load)."""
+    v, t = cfg.vision, cfg.text
+    keys = ["model.visual.patch_embed.proj.weight", "model.visual.merger.ln_q.weight"]
+    keys += [f"model.visual.merger.mlp.{i}.{wb}" for i in (0, 2) for wb in ("weight", "bias")]
+    for i in range(v.depth):
+        p = f"model.visual.blocks.{i}."
+        keys += [p + "norm1.weight", p + "norm2.weight"]
+        keys += [p + f"attn.{nm}.{wb}" for nm in ("qkv", "proj") for wb in ("weight", "bias")]
+        keys += [p + f"mlp.{nm}.{wb}" for nm in ("gate_proj", "up_proj", "down_proj") for wb in ("weight", "bias")]
+    keys += ["model.language_model.embed_tokens.weight", "model.language_model.norm.weight", "lm_head.weight"]
+    for i in range(t.layers):
+        p = f"model.language_model.layers.{i}."
+        keys += [p + "input_layernorm.weight", p + "post_attention_layernorm.weight", p + "self_attn.o_proj.weight"]
+        keys += [p + f"self_attn.{nm}.{wb}" for nm in ("q_proj", "k_proj", "v_proj") for wb in ("weight", "bias")]
+        keys += [p + f"mlp.{nm}.weight" for nm in ("gate_proj", "up_proj", "down_proj")]
+    return keys
+
+
 def _pack_swiglu(gate: torch.Tensor, up: torch.Tensor, ipad: int) -> torch.Tensor:
     """Rows interleaved per 64 as [gate64 | up64] (OCRB_EPI_SWIGLU); zero rows pad I up to `ipad`."""
     I = gate.shape[0]
@@ -217,11 +247,20 @@ class VLMWeights:
     def from_state_dict(cls, cfg: VLMConfig, sd: dict, free_source: bool = False) -> "VLMWeights":
         self = cls(cfg)
         v, t = cfg.vision, cfg.text
+        # published Qwen2.5-VL checkpoints carry the legacy names (`visual.*`, `model.layers.*`); `from_pretrained`
+        # renames them on load (HF conversion_mapping), so the same renaming happens here
+        names = {normalize_checkpoint_key(k): k for k in sd}
+        wanted = expected_state_dict_keys(cfg)
+        missing = sorted(k for k in wanted if k not in names)
+        if missing:
+            raise KeyError(f"checkpoint lacks {len(missing)} of {len(wanted)} tensors this config needs, e.g. "
+                           f"{missing[:6]} (has e.g. {sorted(sd)[:3]})")
 
         def take(name):
-            x = sd[name]
+            src = names[name]
+            x = sd[src]
             if free_source:
-                del sd[name]
+                del sd[src]
             return x.to(BF)
 
         self.patch_embed = take("model.visual.patch_embed.proj.weight").reshape(v.hidden, v.patch_dim).contiguous()

@@ -283,3 +283,137 @@ def test_eval_final_batch_mode_unmodified(rig, monkeypatch, tmp_path, capsys, sy
             assert r["tier1_raw_vs_gt"] == want[stem], stem
         else:
             assert "tier1_raw_vs_gt" not in r
+
+
+def _fake_llm_factory():
+    conf = iter(range(30, 10_000, 6))
+
+    def fake_llm(system_prompt, user_msg, json_schema=None, **kw):
+        title = (json_schema or {}).get("title", "")
+        if title == "CriticResult":
+            return {"overall_confidence": 90, "segments": [], "verdict": "accept", "reasoning": "fake"}
+        if title == "ArbitratorResult":
+            return {"final_text": "arbitrated", "decisions": [], "confidence": next(conf), "uncertain_segments": []}
+        return {"corrected_text": "edited", "changes": [], "unresolved": []}
+
+    return fake_llm
+
+
+def test_transcribe_folder_runs_unmodified_transcribe_single_on_primed_batches(rig, monkeypatch, tmp_path, capsys, synth):
+    """f1 (transcribe.py:185-210): the folder driver primes the cache for `pages_per_batch` pages with ONE batched read,
+    then the reference's unmodified `transcribe_single` runs per page and every read of it is a cache hit."""
+    import json
+    from oracle import text_ref
+    from handwritten_ocr_b200 import folder
+    nodes, tools, eng, state, ref_config = rig
+    eng.max_batch = 16
+    monkeypatch.setattr(tools, "evaluate", text_ref.evaluate)
+    import ocr_agent.agents as agents
+    monkeypatch.setattr(agents, "call_llm_json", _fake_llm_factory())
+    lg, lgg = _langgraph_shim()
+    monkeypatch.setitem(sys.modules, "langgraph", lg)
+    monkeypatch.setitem(sys.modules, "langgraph.graph", lgg)
+    sys.modules.pop("ocr_agent.graph", None)
+    monkeypatch.setattr(ref_config, "PREPROCESSING_STRATEGIES", S, raising=False)
+    monkeypatch.setattr(ref_config, "AGREEMENT_THRESHOLD", 101, raising=False)
+    src, gtd, out = tmp_path / "in", tmp_path / "gt", tmp_path / "out"
+    src.mkdir()
+    gtd.mkdir()
+    for i in range(5):
+        Image.fromarray(synth.page(100 + i, 200, 120)).save(src / f"p{i}.png")
+        (gtd / f"p{i}.md").write_text(f"## Ground Truth\n{synth.text(i, 30)}\n", encoding="utf-8")
+    (src / "notes.txt").write_text("not an image")
+    res = folder.transcribe_folder(src, out, gtd, pages_per_batch=2, tools=tools, max_iterations=4)
+    capsys.readouterr()
+    # 5 pages x 5 strategies read in batches of 2 pages: 10 + 10 + 5 sequences, nothing else
+    assert eng.calls == [10, 10, 5], eng.calls
+    assert [p.name for p in res] == [f"p{i}_transcription.txt" for i in range(5)]
+    for i in range(5):
+        ev = json.loads((out / f"p{i}_eval.json").read_text(encoding="utf-8"))
+        text = (out / f"p{i}_transcription.txt").read_text(encoding="utf-8")
+        assert ev["tier1_raw_vs_gt"] == text_ref.tier1_metrics(synth.text(i, 30).strip(), text)
+        assert ev["pipeline_status"] == "completed"
+    assert not tools._pages, "the driver forgets a page once its per-page function returned"
+
+
+def test_eval_folder_json_equals_eval_final_main(rig, monkeypatch, tmp_path, capsys, synth):
+    """f2 (eval_final.py:94-134): one batched metrics call for the whole folder, JSON equal to `eval_final.main --output`."""
+    import json
+    from oracle import text_ref
+    from handwritten_ocr_b200 import folder
+    nodes, tools, eng, state, _ = rig
+    monkeypatch.setattr(tools, "evaluate", text_ref.evaluate)
+    res, gtd = tmp_path / "results", tmp_path / "gt"
+    res.mkdir()
+    gtd.mkdir()
+    for i in range(9):
+        gt = synth.text(40 + i, 50)
+        (res / f"q{i}_transcription.txt").write_text(synth.corrupt(gt, i, 0.03 * (i + 1)), encoding="utf-8")
+        if i != 4:
+            ext = ".md" if i % 2 else ".txt"
+            (gtd / f"q{i}{ext}").write_text(f"## Ground Truth\n{gt}\n" if ext == ".md" else gt, encoding="utf-8")
+    import ocr_agent.eval_final as ef
+    ref_out, our_out = tmp_path / "ref.json", tmp_path / "ours.json"
+    monkeypatch.setattr(sys, "argv", ["eval_final", str(res), "--ground-truth-dir", str(gtd), "--output", str(ref_out)])
+    ef.main()
+    capsys.readouterr()
+    calls = []
+
+    class BatchOracle:                                          # stands where textops stands (the GPU kernel on the box)
+        @staticmethod
+        def tier1_metrics_batch(items, lower=False):
+            calls.append(len(items))
+            return [text_ref.tier1_metrics(g, o, lower) for g, o in items]
+
+    got = folder.eval_folder(res, gtd, our_out, tools=tools, textops=BatchOracle)
+    assert calls == [8], "all files with a ground truth go through ONE batched call"
+    assert json.loads(our_out.read_text(encoding="utf-8")) == json.loads(ref_out.read_text(encoding="utf-8"))
+    assert got == json.loads(ref_out.read_text(encoding="utf-8"))
+    assert our_out.read_text(encoding="utf-8") == ref_out.read_text(encoding="utf-8")
+
+
+def test_cache_signature_lru_and_resave(rig, tmp_path, synth, capsys):
+    """the cache is keyed on the file signature, bounded (LRU), and a removed temp file is written again."""
+    nodes, tools, eng, state, _ = rig
+    img = state["image_path"]
+    p0 = tools.preprocess_image(img, S[0])
+    t0 = tools.run_ocr(p0)
+    assert eng.calls == [5]
+    os.unlink(p0)
+    assert tools.preprocess_image(img, S[0]) == p0 and os.path.isfile(p0)       # re-saved from the cached page
+    assert tools.run_ocr(p0) == t0 and eng.calls == [5]
+    # the file changes on disk: the stale page and its texts are dropped
+    Image.fromarray(synth.page(78, 200, 120)).save(img)
+    os.utime(img, ns=(1, 1))
+    p1 = tools.preprocess_image(img, S[0])
+    assert p1 != p0 and not os.path.exists(p0)
+    tools.run_ocr(p1)
+    assert eng.calls == [5, 5]
+    # bounded: with cache_pages=2 a third original evicts the oldest
+    tools.configure(cache_pages=2)
+    others = []
+    for i in range(2):
+        q = str(tmp_path / f"other{i}.png")
+        Image.fromarray(synth.page(300 + i, 200, 120)).save(q)
+        others.append(q)
+        tools.preprocess_image(q, S[1])
+    assert list(tools._pages) == others and not os.path.exists(p1)
+    capsys.readouterr()
+
+
+def test_speculative_failure_does_not_fail_the_requested_strategy(rig, monkeypatch, capsys):
+    nodes, tools, eng, state, _ = rig
+    from handwritten_ocr_b200 import preprocess
+    real = preprocess.apply_strategy
+
+    def flaky(x, s):
+        if "remove_lines" in s:
+            raise RuntimeError("workspace too small")
+        return real(x, s)
+
+    monkeypatch.setattr(preprocess, "apply_strategy", flaky)
+    p = tools.preprocess_image(state["image_path"], S[0])
+    assert os.path.isfile(p)
+    assert "speculative deskew+remove_lines+high_contrast skipped" in capsys.readouterr().err
+    with pytest.raises(RuntimeError, match="workspace too small"):
+        tools.preprocess_image(state["image_path"], S[4])

@@ -60,3 +60,39 @@ def test_safetensors_checkpoint_roundtrip(pkg, tmp_path):
         assert all(torch.equal(la[k], lb[k]) for k in la)
     for va, vb in zip(a.vis_blocks, b.vis_blocks):
         assert all(torch.equal(va[k], vb[k]) for k in va)
+
+
+def test_legacy_checkpoint_key_names(pkg):
+    """Published Qwen2.5-VL safetensors use `visual.*` / `model.layers.*` / `model.embed_tokens.*` / `model.norm.*`
+    (HF renames them in from_pretrained); packing must accept them and give the same weights."""
+    import pytest
+    from handwritten_ocr_b200 import vlm
+    from handwritten_ocr_b200.vlm_config import VLMConfig
+    cfg = VLMConfig.tiny()
+    sd = vlm.random_state_dict(cfg, "cpu", seed=7)
+
+    def legacy(k):
+        if k.startswith("model.visual."):
+            return k[len("model."):]
+        if k.startswith("model.language_model."):
+            return "model." + k[len("model.language_model."):]
+        return k
+
+    old = {legacy(k): x for k, x in sd.items()}
+    assert "visual.patch_embed.proj.weight" in old and "model.layers.0.self_attn.q_proj.weight" in old
+    assert "model.embed_tokens.weight" in old and "model.norm.weight" in old and "lm_head.weight" in old
+    assert all(vlm.normalize_checkpoint_key(legacy(k)) == k for k in sd)
+    assert sorted(vlm.expected_state_dict_keys(cfg)) == sorted(sd)
+    a = vlm.VLMWeights.from_state_dict(cfg, dict(sd))
+    b = vlm.VLMWeights.from_state_dict(cfg, old, free_source=True)
+    assert not old
+    assert torch.equal(a.lm_head, b.lm_head) and torch.equal(a.embed, b.embed) and torch.equal(a.final_norm, b.final_norm)
+    assert torch.equal(a.patch_embed, b.patch_embed) and torch.equal(a.merger_w2, b.merger_w2)
+    for la, lb in zip(a.layers, b.layers):
+        assert all(torch.equal(la[k], lb[k]) for k in la)
+    for va, vb in zip(a.vis_blocks, b.vis_blocks):
+        assert all(torch.equal(va[k], vb[k]) for k in va)
+    # a truncated checkpoint fails with the list of what is missing, not a bare KeyError on the first name
+    broken = {k: x for k, x in sd.items() if "layers.1.mlp.down_proj" not in k}
+    with pytest.raises(KeyError, match="down_proj"):
+        vlm.VLMWeights.from_state_dict(cfg, broken)
