@@ -41,7 +41,6 @@ _SIGS = {
     "ocrb_resize_bicubic_aa_u8": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ocrb_normalize_patchify": [_P, _P, _I, _I, _I, _I, _P, _I, _P],
     "ocrb_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P],
-    "ocrb_gemv_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P, _F, _P],
     "ocrb_skinny_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P, _F, _P, _P],
     "ocrb_rmsnorm_bf16": [_P, _L, _P, _P, _L, _I, _I, _F, _P],
     "ocrb_rope_vision": [_P, _I, _I, _I, _P, _P, _P],

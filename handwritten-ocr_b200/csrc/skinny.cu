@@ -1,11 +1,11 @@
 // Weight-streaming "skinny" GEMM for batched greedy decode (HF generation loop utils.py:2743-2806: one new
 // token per sequence per step, so every nn.Linear of the decoder sees only B <= 64 activation rows):
 //
-//     D[b, n] = epilogue( sum_k X[b, k] * W[n, k] )          X: [B, K] bf16,  W: [N, K] bf16
+//     D[b, n] = epilogue( sum_k X[b, k] * W[n, k] )          X: [B, K] bf16 (B <= 128),  W: [N, K] bf16
 //
 // HBM-bound: each weight byte must cross HBM exactly once per step whatever B is.  Design (sm_100a):
 //   * swap-AB on the 5th-gen tensor cores: the 128 x 64 WEIGHT tile is the UMMA "A" operand (M = 128 weight
-//     rows), the activations are the "B" operand (N = BP = 16/32/64 batch columns), fp32 accumulators
+//     rows), the activations are the "B" operand (N = BP = 16/32/64/96/128 batch columns), fp32 accumulators
 //     [128 lanes x BP columns] in TMEM, double buffered so the epilogue of one tile overlaps the MMAs of the next;
 //   * weights arrive through a TMA ring (cp.async.bulk.tensor, 128B swizzle, L2 evict-first) that never
 //     depends on the activations, so it starts before the previous kernel's results are needed;
@@ -38,7 +38,7 @@ constexpr int SK_BK = 64;           // k-block: 64 bf16 = one 128-byte swizzle r
 constexpr int SK_STAGES = SK_STAGES_N;           // 5 x 18 KiB (BP=16): two CTAs of consecutive kernels fit one SM under PDL
 constexpr int SK_THREADS = 192;
 constexpr int SK_MAX_GRID = 296;    // workspace slots (2 x 148)
-constexpr int SK_MAXBP = 64;
+constexpr int SK_MAXBP = 128;
 constexpr int SK_MAX_NORM_K = 32768;  // widest row the B > 16 RMSNorm scratch holds
 constexpr uint32_t SK_W_BYTES = SK_BM * SK_BK * 2;   // 16 KiB
 
@@ -276,12 +276,14 @@ skinny_norm_rows_kernel(SkinnyParams p, bf16 *__restrict__ xn) {
 // BP = MMA N (activation rows staged per k-block: 16/32/64); BC = accumulator columns the epilogue actually reads,
 // publishes and stores (4/8/16/32/64 >= B): with B = 3 sequences the fix-up moves 4 columns, not 16.
 template <int BP, int BC>
-__global__ void __launch_bounds__(SK_THREADS, 2)
+__global__ void __launch_bounds__(SK_THREADS, (BP > 64) ? 1 : 2)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, SkinnyParams p) {
-  constexpr int ST = (BP >= 64) ? 4 : SK_STAGES;   // ring depth: 4 x 24 KiB at BP = 64 keeps two CTAs per SM
+  // ring depth: 4 x 24 KiB at BP = 64 keeps two CTAs per SM; above that one CTA per SM with 6 stages (96 KiB of weights in flight)
+  constexpr int ST = (BP > 64) ? 6 : ((BP >= 64) ? 4 : SK_STAGES);
   constexpr uint32_t X_BYTES = BP * SK_BK * 2;
   constexpr uint32_t STAGE_BYTES = SK_W_BYTES + X_BYTES;
-  constexpr int TMEM_COLS = (2 * BP < 32) ? 32 : 2 * BP;
+  constexpr int ACC_STRIDE = (BP <= 16) ? 16 : (BP <= 32 ? 32 : (BP <= 64 ? 64 : 128));   // TMEM columns between the two accumulators
+  constexpr int TMEM_COLS = (2 * ACC_STRIDE < 32) ? 32 : 2 * ACC_STRIDE;              // power of two >= 32
   extern __shared__ uint8_t sk_smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sk_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *full_w = reinterpret_cast<uint64_t *>(smem + ST * STAGE_BYTES);
@@ -377,7 +379,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         const int acc = seg & 1;
         mbar_wait(&tmem_empty[acc], ((seg >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t tacc = tmem_base + acc * BP;
+        const uint32_t tacc = tmem_base + acc * ACC_STRIDE;
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(&full_w[s], ph);
           if (seg == 0 && i == 0) sk_stamp(p, 3);   // first weight tile landed
@@ -419,7 +421,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       const bool n_ok = n < p.N;
       auto load_chunk = [&](int c0, float (&v)[CC]) {
         uint32_t r[CC];
-        tmem_ld_cols<CC>(lane_addr + acc * BP + c0, r);
+        tmem_ld_cols<CC>(lane_addr + acc * ACC_STRIDE + c0, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < CC; ++i) v[i] = __uint_as_float(r[i]);
@@ -548,7 +550,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 
 template <int BP, int BC>
 static int launch_skinny(const CUtensorMap &mw, const CUtensorMap &mx, const SkinnyParams &p, int grid, cudaStream_t st) {
-  constexpr int ST = (BP >= 64) ? 4 : SK_STAGES;
+  constexpr int ST = (BP > 64) ? 6 : ((BP >= 64) ? 4 : SK_STAGES);
   constexpr int CC = (BC < 16) ? BC : 16;
   constexpr size_t smem = (size_t)ST * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 256 /*barriers*/ +
                           64 * CC * sizeof(float) + 64;
@@ -589,7 +591,7 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
                                      int32_t N, int32_t K, const void *bias, const void *residual, int64_t ldr,
                                      int32_t epilogue, const void *norm_w, float eps, void *workspace, void *stream) {
   OCRB_REQUIRE(X && W && D && workspace, "skinny_gemm_bf16: null pointer");
-  OCRB_REQUIRE(B >= 1 && B <= SK_MAXBP, "skinny_gemm_bf16: B must be in 1..64 (use ocrb_gemm_bf16 for larger batches)");
+  OCRB_REQUIRE(B >= 1 && B <= SK_MAXBP, "skinny_gemm_bf16: B must be in 1..128 (use ocrb_gemm_bf16 for larger batches)");
   OCRB_REQUIRE(N > 0 && K > 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0,
                "skinny_gemm_bf16: K and row strides must be multiples of 8");
   OCRB_REQUIRE(((uintptr_t)X & 15) == 0 && ((uintptr_t)W & 15) == 0 && (!norm_w || ((uintptr_t)norm_w & 15) == 0),
@@ -630,7 +632,7 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
   int rc = make_tensor_map_bf16(&mw, W, N, K, ldw, SK_BM);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const int BPsel = B <= 16 ? 16 : (B <= 32 ? 32 : 64);
+  const int BPsel = B <= 16 ? 16 : (B <= 32 ? 32 : (B <= 64 ? 64 : (B <= 96 ? 96 : 128)));
   if (norm_w) {
     // normalise the rows once (same rstd routine as the fused path), then treat them as a plain input
     OCRB_REQUIRE(K <= SK_MAX_NORM_K, "skinny_gemm_bf16: the RMSNorm prologue supports K <= 32768");
@@ -653,5 +655,8 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
   if (B <= 8) return launch_skinny<16, 8>(mw, mx, p, grid, st);
   if (B <= 16) return launch_skinny<16, 16>(mw, mx, p, grid, st);
   if (B <= 32) return launch_skinny<32, 32>(mw, mx, p, grid, st);
-  return launch_skinny<64, 64>(mw, mx, p, grid, st);
+  if (B <= 64) return launch_skinny<64, 64>(mw, mx, p, grid, st);
+  // 65..128 rows (a folder batch: 32 pages x 3 candidates): still ONE pass over the weights; 28 / 32 KiB stages, one CTA per SM
+  if (B <= 96) return launch_skinny<96, 96>(mw, mx, p, grid, st);
+  return launch_skinny<128, 128>(mw, mx, p, grid, st);
 }

@@ -148,15 +148,38 @@ def transcribe_folder(input_dir, output_dir=None, ground_truth_dir=None, *, page
     if pages_per_batch > int(tools._options["cache_pages"]):
         tools.configure(cache_pages=pages_per_batch)
 
+    # host pipeline: while the GPU reads batch k, a thread decodes the image files of batch k + 1 (PIL releases the GIL)
+    from concurrent.futures import ThreadPoolExecutor
+    mine = [images[i] for i in shard_pages(len(images), rank, world)]
+    batches = [mine[i:i + pages_per_batch] for i in range(0, len(mine), pages_per_batch)]
+    pool = ThreadPoolExecutor(max_workers=4)
+    pending = {}
+
+    def submit(k):
+        if 0 <= k < len(batches) and k not in pending:
+            pending[k] = {str(p): pool.submit(tools._open_array, str(p)) for p in batches[k]}
+
+    submit(0)
+    state = {"k": 0}
+
     def read_batch(batch_images):
-        tools.prime([str(p) for p in batch_images], strategies)
+        k = state["k"]
+        state["k"] += 1
+        submit(k)
+        decoded = {p: f.result() for p, f in pending.pop(k).items()}
+        submit(k + 1)
+        tools.prime([str(p) for p in batch_images], strategies, decoded)
+        del decoded
         out = []
         for img in batch_images:
             out.append(fn(img, output_dir, match_ground_truth(img.stem, ground_truth_dir), **page_kwargs))
             tools.forget(str(img))
         return out
 
-    return read_folder(images, read_batch, rank=rank, world=world, pages_per_batch=pages_per_batch, group=group)
+    try:
+        return read_folder(images, read_batch, rank=rank, world=world, pages_per_batch=pages_per_batch, group=group)
+    finally:
+        pool.shutdown(wait=False, cancel_futures=True)
 
 
 # ───────────────────────── f2: the batch evaluator (eval_final.py:94-134) ─────────────────────────

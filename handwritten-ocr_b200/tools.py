@@ -48,7 +48,7 @@ _options = {
     "keep_resident": True,      # unload_ocr_model() keeps the 16.6 GB of weights in the 180 GB of HBM
     "checkpoint": os.environ.get("OCRB_CHECKPOINT"),   # dir with HF safetensors; None -> random init
     "vlm_config": None,         # VLMConfig override (tests use the tiny config)
-    "max_batch": 8,
+    "max_batch": 64,            # sequences per batched read (paged KV: 57 KB per token per sequence at 7B)
     "seed": 0,
     "force_greedy": False,      # decode greedily even if the checkpoint's generation_config.json asks for sampling
     "cache_pages": 64,          # originals whose preprocessed variants / texts stay cached (LRU)
@@ -137,8 +137,9 @@ def _save(arr: np.ndarray, image_path: str, label: str) -> str:
     suffix = Path(image_path).suffix or ".png"
     tmp = tempfile.NamedTemporaryFile(suffix=suffix, delete=False, prefix=f"ocr_{label}_")
     tmp.close()
-    # lossless either way; PNG level 1 instead of Pillow's default 6 only makes the temp file larger and the save ~4x faster
-    kw = {"compress_level": 1} if suffix.lower() == ".png" else {}
+    # lossless either way; a stored (level 0) PNG instead of Pillow's default level 6 only makes the temp file larger
+    # and the save ~30x faster (the file exists for callers that open it; run_ocr reads the cached page)
+    kw = {"compress_level": 0} if suffix.lower() == ".png" else {}
     Image.fromarray(arr).save(tmp.name, **kw)
     return tmp.name
 
@@ -153,14 +154,15 @@ def _wanted_strategies(steps) -> list:
     return wanted
 
 
-def _preprocess_page(image_path: str, wanted: list, required_label: str | None) -> "_Page":
+def _preprocess_page(image_path: str, wanted: list, required_label: str | None, decoded=None) -> "_Page":
     """Apply every strategy of `wanted` that the cache does not hold yet.  A failure in a SPECULATIVE strategy
-    (one the caller did not ask for) is reported and skipped: the reference would never have run it here."""
+    (one the caller did not ask for) is reported and skipped: the reference would never have run it here.
+    `decoded`: the already decoded page array (folder mode decodes the next batch on a host thread)."""
     page = _page_for(image_path)
     todo = [s for s in wanted if _label(s) not in page.variants]
     if not todo:
         return page
-    x = preprocess.to_device(_open_array(image_path))
+    x = preprocess.to_device(decoded if decoded is not None else _open_array(image_path))
     for s in todo:
         lab = _label(s)
         try:
@@ -293,10 +295,11 @@ def _read_pending(engine, originals: list, prompt: str, max_new_tokens: int, fir
                 _pages[o].texts[lab] = engine.detokenize(tk)
 
 
-def prime(image_paths, strategies=None) -> None:
+def prime(image_paths, strategies=None, decoded: dict | None = None) -> None:
     """Folder mode (transcribe.py:193-209 runs the pages one after another): preprocess the configured strategies of
     SEVERAL pages and read all their candidates in one batch, so that the per-page `preprocess_image` / `run_ocr`
-    calls the unmodified `transcribe_single` makes afterwards are cache hits.  `cache_pages` must cover the pages."""
+    calls the unmodified `transcribe_single` makes afterwards are cache hits.  `cache_pages` must cover the pages.
+    `decoded`: {path: uint8 array} of pages somebody already decoded (see folder.transcribe_folder)."""
     engine = _load_ocr_model()
     strategies = [_steps(s) for s in (strategies if strategies is not None else
                                       getattr(config, "PREPROCESSING_STRATEGIES", []))]
@@ -307,7 +310,7 @@ def prime(image_paths, strategies=None) -> None:
     import contextlib
     import io
     for p in paths:
-        _preprocess_page(p, strategies, None)
+        _preprocess_page(p, strategies, None, decoded.get(p) if decoded else None)
     with contextlib.redirect_stdout(io.StringIO()):
         _read_pending(engine, paths, config.OCR_PROMPT, int(config.OCR_MAX_NEW_TOKENS))
 

@@ -11,6 +11,7 @@ Reference semantics: HF transformers modeling_qwen2_5_vl.py (vision tower :345-5
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -38,14 +39,6 @@ def gemm(A, W, out, *, bias=None, residual=None, epilogue=EPI_NONE, N=None, K=No
     return out
 
 
-def gemv(X, W, out, *, bias=None, residual=None, epilogue=EPI_NONE, norm_w=None, eps=1e-6):
-    B, K = X.shape
-    _lib.call("ocrb_gemv_bf16", X.data_ptr(), X.stride(0), W.data_ptr(), W.stride(0), out.data_ptr(), out.stride(0),
-              B, W.shape[0], K, _lib.ptr(bias), _lib.ptr(residual), residual.stride(0) if residual is not None else 0,
-              epilogue, _lib.ptr(norm_w), float(eps), _sp())
-    return out
-
-
 _SKINNY_WS = {}
 
 
@@ -60,11 +53,12 @@ def skinny_workspace(device) -> torch.Tensor:
     return ws
 
 
-SKINNY_MAX_ROWS = 64
+SKINNY_MAX_ROWS = 128
+DECODE_KEYS_PER_CTA = int(os.environ.get("OCRB_ATTN_KEYS", "128"))    # decode attention: keys per CTA (4 warps x 16-key tiles)
 
 
 def skinny(X, W, out, *, bias=None, residual=None, epilogue=EPI_NONE, norm_w=None, eps=1e-6):
-    """out[B, N'] = epilogue(X[B,K] @ W[N,K]^T), B <= 64: every weight byte crosses HBM once (tcgen05 swap-AB)."""
+    """out[B, N'] = epilogue(X[B,K] @ W[N,K]^T), B <= 128: every weight byte crosses HBM once (tcgen05 swap-AB)."""
     B, K = X.shape
     _lib.call("ocrb_skinny_gemm_bf16", X.data_ptr(), X.stride(0), W.data_ptr(), W.stride(0), out.data_ptr(),
               out.stride(0), B, W.shape[0], K, _lib.ptr(bias), _lib.ptr(residual),
@@ -74,7 +68,7 @@ def skinny(X, W, out, *, bias=None, residual=None, epilogue=EPI_NONE, norm_w=Non
 
 
 def linear_small_or_big(X, W, out, **kw):
-    """Row count decides the datapath: <= 64 rows stream the weights once (skinny GEMM), else full tiles."""
+    """Row count decides the datapath: <= 128 rows stream the weights once (skinny GEMM), else full tiles."""
     if X.shape[0] <= SKINNY_MAX_ROWS:
         return skinny(X, W, out, **kw)
     return gemm(X, W, out, **kw)
@@ -620,8 +614,9 @@ class DecodeState:
         self.cos = torch.empty((B, t.head_dim), dtype=BF, device=dev)
         self.sin = torch.empty((B, t.head_dim), dtype=BF, device=dev)
         max_ctx = block_table.shape[1] * dec.kv.page
-        # split-KV: 64-key chunks, one CTA per (chunk, kv head, sequence); chunks beyond the context exit at once
-        self.n_splits = int(max(1, math.ceil(max_ctx / 64)))
+        # split-KV: one CTA per (key range, kv head, sequence); ranges beyond the context exit at once.  The range length
+        # is a property of the engine (never of B), so a sequence's bits do not depend on its batch.
+        self.n_splits = int(max(1, math.ceil(max_ctx / DECODE_KEYS_PER_CTA)))
         self.split_ws = torch.empty(B * t.heads * self.n_splits * (t.head_dim + 2), dtype=torch.float32, device=dev)
         self.graph = None
         self.graph_launches = 0

@@ -143,17 +143,11 @@ int ocrb_gemm_bf16(const void *A, int64_t lda, const void *W, int64_t ldw, void 
                    int32_t M, int32_t N, int32_t K, const void *bias, const void *residual,
                    int64_t ldr, int32_t epilogue, void *stream);
 
-/* Skinny GEMM for decode (M = B <= 16 rows): weight-streaming, HBM-bound.  Same epilogues.
- * Optional fused RMSNorm prologue: if norm_w != NULL, A is first normalised row-wise the HF way
- * (fp32 normalise -> bf16 -> * weight in bf16) with `eps`.  out_f32 != NULL additionally stores
- * fp32(bf16(acc)) (used for lm_head logits). */
-int ocrb_gemv_bf16(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd,
-                   int32_t B, int32_t N, int32_t K, const void *bias, const void *residual,
-                   int64_t ldr, int32_t epilogue, const void *norm_w, float eps, void *stream);
-
 /* Weight-streaming skinny GEMM for decode on tcgen05 (swap-AB: the 128x64 weight tile is the UMMA M operand,
- * the B <= 64 activation rows are the N operand; TMA weight ring; stream-K split over all SMs with a
- * deterministic, batch-invariant fix-up).  Same contract and epilogues as ocrb_gemv_bf16, B in 1..64.
+ * the B <= 128 activation rows are the N operand; TMA weight ring; stream-K split over all SMs with a
+ * deterministic, batch-invariant fix-up).  B in 1..128, same epilogues as ocrb_gemm_bf16.
+ * Optional RMSNorm prologue: if norm_w != NULL, X is first normalised row-wise the HF way
+ * (fp32 normalise -> bf16 -> * weight in bf16) with `eps`.
  * workspace: ocrb_skinny_workspace_bytes() bytes, ZERO-initialised once by the caller and then owned by
  * this entry point (it holds stream-K partials and their ready flags; flags are returned to zero by every
  * launch).  One workspace must not be shared by launches that can run concurrently. */
@@ -197,7 +191,9 @@ int ocrb_kv_write_prefill(const void *k, int64_t ldk, const void *v, int64_t ldv
 
 /* One decode step of attention for B sequences: applies mRoPE (bf16) to q,k of the new token,
  * appends k,v at position ctx_len[b], attends over ctx_len[b]+1 tokens.  qkv: [B, (n_q+2*n_kv)*hd].
- * cos/sin: bf16 [B, hd] for this step.  out: [B, n_q*hd]. */
+ * cos/sin: bf16 [B, hd] for this step.  out: [B, n_q*hd].  hd = 64 or 128, n_q / n_kv <= 16, page_size % 16 == 0.
+ * Split-KV: every sequence's max_pages*page_size key positions are cut into n_splits ranges, one CTA per
+ * (range, kv head, sequence); split_ws: fp32 [B * n_q * n_splits * (hd + 2)] partials (max, sum, o[hd]). */
 int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cache, void *v_cache,
                           const int32_t *block_table, int32_t max_pages, const int32_t *ctx_len,
                           int32_t B, int32_t page_size, int32_t n_q, int32_t n_kv, int32_t hd,

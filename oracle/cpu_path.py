@@ -11,9 +11,10 @@ reference makes, on the box's host cores:
     timed instead and the record says so);
   * the read: HF transformers' Qwen2.5-VL classes (what `AutoModelForImageTextToText` resolves to
     for the configured checkpoint, tools.py:705-709) in bf16 eager mode with `generate`
-    (tools.py:764-765), full WIDTH but a bounded number of layers / decode steps, extrapolated
-    linearly in depth and step count -- a full-depth 512-token read takes ~5 min on 8 cores
-    (SURVEY.md §6), far beyond a bounded sample;
+    (tools.py:764-765), at full width and (by default in bench.py) full depth; the vision tower,
+    the prefill and a few decode steps are measured, only the NUMBER of decode steps is scaled to
+    the 512-token read -- a complete read takes ~5 min on 8 cores, far beyond a
+    bounded sample;
   * agreement / merge / CER: pure-Python dynamic programmes, line-for-line the algorithm of
     tools.py:69-100,465-493 (text_ref.levenshtein_py / align_to_backbone_py), on a bounded prefix and
     scaled by the cell count n*m.
@@ -128,8 +129,10 @@ class HFCpuReader:
         hf_cfg.text_config.num_hidden_layers = text_layers
         hf_cfg.text_config.layer_types = hf_cfg.text_config.layer_types[:text_layers] if getattr(
             hf_cfg.text_config, "layer_types", None) else None
-        hf_cfg.vision_config.depth = vision_depth
-        hf_cfg.vision_config.fullatt_block_indexes = [vision_depth - 1]   # one windowed block + one full block
+        if vision_depth < cfg.vision.depth:
+            hf_cfg.vision_config.depth = vision_depth
+            hf_cfg.vision_config.fullatt_block_indexes = [vision_depth - 1]   # one windowed block + one full block
+        self.full_blocks = set(int(i) for i in hf_cfg.vision_config.fullatt_block_indexes)
         self.text_layers, self.vision_depth = text_layers, vision_depth
         with initialization.no_init_weights():
             m = Qwen2_5_VLForConditionalGeneration._from_config(hf_cfg, dtype=torch.bfloat16)
@@ -165,7 +168,7 @@ class HFCpuReader:
 
         for i, b in enumerate(vis):
             b.register_forward_pre_hook(pre(("v", i)))
-            b.register_forward_hook(post(("v", i), "vis_full" if i == self.vision_depth - 1 else "vis_win"))
+            b.register_forward_hook(post(("v", i), "vis_full" if i in self.full_blocks else "vis_win"))
         for i, l in enumerate(txt):
             l.register_forward_pre_hook(pre(("t", i)))
             l.register_forward_hook(post(("t", i), "txt"))
@@ -197,6 +200,7 @@ class HFCpuReader:
         n_dec_calls = max(n_gen - 1, 1)
         other_prefill_share = other / (n_dec_calls + 1)     # per forward call (lm_head etc.), rough
         n_full_blocks = len(fc.vision.fullatt_blocks)
+        # (at full depth these sums are the measured totals: nothing is scaled)
         est_vision = (fc.vision.depth - n_full_blocks) * vis_win + n_full_blocks * vis_full
         est_prefill = L * prefill_layer + other_prefill_share
         est_step = L * dec_layer + other_prefill_share
@@ -205,6 +209,29 @@ class HFCpuReader:
                 "vision_block_full_s": vis_full, "prefill_layer_s": prefill_layer, "decode_layer_s": dec_layer,
                 "per_call_other_s": other_prefill_share, "est_vision_s": est_vision, "est_prefill_s": est_prefill,
                 "est_decode_step_s": est_step, "est_read_s": est_total, "full_new_tokens": full_new}
+
+
+    def decode_sample(self, n_new: int = 4, prompt_tokens: int = 16):
+        """`n_new` greedy decode steps on a short text-only prompt: seconds per decode step of the (full-depth) model.
+        The per-step cost on the CPU is the 14 GB weight pass; the context length changes it by well under 1 %."""
+        torch = self.torch
+        for v in self._t.values():
+            v.clear()
+        ids = torch.arange(1000, 1000 + prompt_tokens, dtype=torch.int64)[None]
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            out = self.model.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=n_new + 1,
+                                      min_new_tokens=n_new + 1, do_sample=False)
+        total = time.perf_counter() - t0
+        Lm = self.text_layers
+        txt = self._t["txt"]
+        n_calls = len(txt) // Lm                                 # 1 prefill call + n_new decode calls
+        dec_layers = txt[Lm:]
+        per_call_layers = sum(dec_layers) / max(n_calls - 1, 1)
+        other = (total - sum(txt)) / max(n_calls, 1)             # lm_head, sampling loop: per forward call
+        scale = self.full_cfg.text.layers / Lm
+        return {"decode_step_s": per_call_layers * scale + other, "decode_steps_measured": int(n_calls - 1),
+                "layers_run": Lm, "wall_s": total, "new_tokens": int(out.shape[1] - ids.shape[1])}
 
 
 # ───────────── pure-Python text DP, as the reference runs it ─────────────

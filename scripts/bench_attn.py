@@ -6,8 +6,9 @@ import handwritten_ocr_b200
 from handwritten_ocr_b200 import _lib
 BF = torch.bfloat16
 nq, nkv, hd, page = 28, 4, 128, 16
-CASES = [(3, 1300)] if len(sys.argv) > 1 and sys.argv[1] == "one" else [(3, 1300), (3, 1500), (24, 1300), (48, 1300)]
-for B, ctx in CASES:
+CASES = [(3, 1300)] if len(sys.argv) > 1 and sys.argv[1] == "one" else [(3, 1300), (3, 1500), (24, 1300), (63, 1300), (96, 1300)]
+KEYS = [int(k) for k in os.environ.get("KEYS", "64,128,256").split(",")]        # keys per CTA
+for B, ctx in [(b, c) for b, c in CASES for _ in KEYS]:
     max_ctx = 2112
     max_pages = max_ctx // page
     n_pages = B * max_pages
@@ -18,7 +19,9 @@ for B, ctx in CASES:
     qkv = torch.randn(B, (nq + 2 * nkv) * hd, device="cuda").to(BF)
     cos = torch.randn(B, hd, device="cuda").to(BF); sin = torch.randn(B, hd, device="cuda").to(BF)
     ctx_d = torch.full((B,), ctx, dtype=torch.int32, device="cuda")
-    n_splits = math.ceil(max_ctx / 64)
+    KEYS.append(KEYS.pop(0))
+    keys = KEYS[-1]
+    n_splits = math.ceil(max_ctx / keys)
     ws = torch.empty(B * nq * n_splits * (hd + 2), device="cuda", dtype=torch.float32)
     out = torch.empty(B, nq * hd, device="cuda", dtype=BF)
     sp = lambda: torch.cuda.current_stream().cuda_stream
@@ -37,4 +40,4 @@ for B, ctx in CASES:
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     kvb = B * ctx * 2 * nkv * hd * 2
-    print(f"decode attention B={B:2d} ctx={ctx}: {us:7.2f} us per layer (partial+combine), KV bytes {kvb/1e6:.1f} MB -> {kvb/us/1e3:.0f} GB/s", flush=True)
+    print(f"decode attention B={B:2d} ctx={ctx} keys/CTA={keys:3d}: {us:7.2f} us per layer (partial+combine), KV bytes {kvb/1e6:.1f} MB -> {kvb/us/1e3:.0f} GB/s", flush=True)

@@ -37,7 +37,7 @@ def test_host_only_entry_points(pkg):
     assert preprocess.smart_resize(768, 1024) == (756, 1036)       # HF smart_resize
     assert preprocess.smart_resize(1024, 768) == (1036, 756)
     with pytest.raises(_lib.OcrbError):
-        _lib.call("ocrb_gemv_bf16", None, 0, None, 0, None, 0, 1, 8, 8, None, None, 0, 0, None, 0.0, None)
+        _lib.call("ocrb_skinny_gemm_bf16", None, 0, None, 0, None, 0, 1, 8, 8, None, None, 0, 0, None, 0.0, None, None)
     assert b"null pointer" in L.ocrb_last_error()
 
 
