@@ -336,12 +336,12 @@ def run_b200(args):
                    "read through tools.prime / preprocess_image / run_ocr / compare_versions / merge_versions, final gather)")
     else:
         def step_e2e(s):
-            out = []
-            for p in range(P):
-                img = e2e_files[(s % n_distinct) * P + p]
+            imgs = [e2e_files[(s % n_distinct) * P + p] for p in range(P)]
+            for img in imgs:
                 tools.forget(img)
-                out.append(folder.initial_ocr_page(img, tools=tools))      # nodes.py:86-127 call order
-            return out
+            if P > 1:
+                tools.prime(imgs, STRATEGIES)          # folder mode: one batched read for the P pages of the step
+            return [folder.initial_ocr_page(img, tools=tools) for img in imgs]      # nodes.py:86-127 call order
 
         e2e_steps = max(1, min(args.steps, 8))
         with contextlib.redirect_stdout(io.StringIO()):

@@ -46,8 +46,9 @@ _SIGS = {
     "ocrb_rope_vision": [_P, _I, _I, _I, _P, _P, _P],
     "ocrb_rope_text": [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _P],
     "ocrb_attention_varlen": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    "ocrb_flash_attention_bf16": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "ocrb_kv_write_prefill": [_P, _L, _P, _L, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
-    "ocrb_decode_attention": [_P, _L, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _F, _P, _L, _P, _I, _P],
+    "ocrb_decode_attention": [_P, _L, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _F, _P, _L, _P, _I, _P],
     "ocrb_argmax_step": [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "ocrb_embed_gather": [_P, _P, _P, _I, _I, _P],
     "ocrb_rows_copy": [_P, _L, _P, _P, _L, _P, _I, _I, _P],
@@ -87,11 +88,42 @@ def load():
     return L
 
 
+_NVTX = os.environ.get("OCRB_NVTX", "0") == "1"
+
+
 def call(name: str, *args):
+    """One C-ABI call.  OCRB_NVTX=1 wraps every call in an NVTX range named after the entry point (visible to
+    `ncu --nvtx` / Nsight Systems timelines); the engine adds phase ranges around them (engine.py)."""
     L = load()
-    rc = getattr(L, name)(*args)
+    if _NVTX:
+        import torch
+        torch.cuda.nvtx.range_push(name)
+        try:
+            rc = getattr(L, name)(*args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        rc = getattr(L, name)(*args)
     if rc != 0:
         raise OcrbError(f"{name} failed ({rc}): {L.ocrb_last_error().decode(errors='replace')}")
+
+
+class nvtx_range:
+    """`with nvtx_range("vision"):` -- a phase range when OCRB_NVTX=1, nothing otherwise."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def ptr(t):

@@ -2,25 +2,25 @@
 // split-KV attention over the cache.  (The weight-streaming linears of the step are in skinny.cu.)
 //
 // HBM-bound: every cached K and V byte of every sequence is read exactly once per step (B * ctx * 57 344 B for the 7B
-// config over 28 layers).  Flash-decoding layout:
-//   * grid = (key ranges, KV heads, sequences); a CTA owns `chunk` consecutive keys of one (sequence, KV head);
-//   * the G query heads that share the KV head are the 16 rows of mma.sync.m16n8k16 tiles (rows >= G are zero);
-//   * every WARP is an independent online-softmax worker: it takes the 16-key tiles t = warp, warp + 4, ... of the CTA's
-//     range, streams their K/V rows with cp.async into its private 3-stage shared-memory ring (issued BEFORE
-//     griddepcontrol.wait: the cache was written by earlier steps, not by the preceding qkv GEMM), keeps its running
-//     (max, sum, O[16 x hd]) in registers and never meets another warp inside the loop (no __syncthreads);
-//   * the four warps merge once through shared memory and the CTA stores one fp32 partial (max, sum, o[hd]) per head;
-//     decode_attn_combine_kernel folds the partials of a sequence's key ranges.
+// config over 28 layers).  Layout and schedule:
+//   * cache layout [page][kv head][16 tokens][hd]: the K (or V) rows a 16-key tile needs are ONE contiguous 4 KiB block,
+//     fetched by the TMA unit (cp.async.bulk.tensor, two [16 x 64]-column boxes, 128B swizzle) straight into shared memory;
+//   * work item = (sequence, KV head, range of `chunk` keys); the G query heads that share the KV head are the 16 rows
+//     of mma.sync.m16n8k16 tiles (rows >= G are zero);
+//   * every WARP is an independent flash-decoding worker: it owns whole work items (item = warp * grid + cta, then
+//     strided), streams their 16-key tiles through its private shared-memory ring (lane 0 issues the TMA loads, an
+//     mbarrier per slot counts the bytes), keeps the running (max, sum, O[16 x hd]) in registers and writes one fp32
+//     partial (max, sum, o[hd]) per head and item -- there is no block-level barrier anywhere in the kernel, so the
+//     memory pipe of an SM never drains while one warp finishes an item and another is in the middle of its own;
+//   * decode_attn_combine_kernel folds the partials of a sequence's key ranges.
 // mRoPE of the new token's q / k (bf16 arithmetic, as HF) and the append of its k, v to the cache are fused: the warp
 // whose tile holds position ctx builds that row in shared memory and writes it to the cache.
 // The arithmetic of a sequence depends only on (its context length, chunk) -- never on B or on the other sequences.
-#include "common.cuh"
+#include "tc_common.cuh"
 #include <math.h>
 #include <stdlib.h>
 
 namespace ocrb {
-
-typedef __nv_bfloat16 bf16;
 
 __device__ __forceinline__ float rope_elem_bf16(const bf16 *vec, int i, int hd, const bf16 *c, const bf16 *s) {
   const int half = hd >> 1;
@@ -31,24 +31,18 @@ __device__ __forceinline__ float rope_elem_bf16(const bf16 *vec, int i, int hd, 
   return bf16_round(t + u);
 }
 
-constexpr int DA_TILE = 16;            // keys per warp tile (one k-step of the P.V product)
-constexpr int DA_WARPS = 4;
-constexpr int DA_STAGES = 3;           // per-warp cp.async ring depth
+constexpr int DA_TILE = 16;            // keys per tile (one k-step of the P.V product) = one (page, kv head) block at page size 16
+// workers (warps) per CTA x per-warp TMA ring depth: 6 x 4 keeps four 8 KiB tiles in flight per worker (a lone worker is
+// latency-bound by its ring depth: tile time ~0.4 us against ~1.5 us of memory latency); 8 x 2 is the experiment (OCRB_ATTN_CFG=82)
 constexpr int DA_MAXG = 16;            // query heads per KV head (rows of the m16 tile)
 
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void *p) {
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
 }
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void *p) {
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
 }
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -59,218 +53,223 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
-template <int HD>
+// Shared memory per warp: Q staging [16][HD + 8] bf16, then (1024-byte aligned) the ring of tiles.  One tile slot:
+// K atoms then V atoms; an atom = [16 keys][64 dims] bf16 = 2 KiB in the 128B-swizzled layout the TMA unit writes
+// (16-byte chunk c of row r sits at chunk c ^ (r & 7)).
+template <int HD, int DA_WARPS, int DA_STAGES>
 struct DaSmem {
-  static constexpr int PITCH = HD + 8;                       // bf16 per shared row (conflict-free ldmatrix)
-  static constexpr int TILE_ELEMS = DA_TILE * PITCH;         // one K (or V) tile
-  static constexpr int STAGE_ELEMS = 2 * TILE_ELEMS;         // K then V
-  static constexpr int WARP_ELEMS = DA_STAGES * STAGE_ELEMS;
-  static constexpr size_t BYTES = (size_t)(16 * PITCH + DA_WARPS * WARP_ELEMS) * sizeof(bf16) + DA_WARPS * 32 * sizeof(float);
+  static constexpr int ATOMS = HD / 64;                      // 64-dim column groups per K (or V) tile
+  static constexpr uint32_t ATOM_BYTES = DA_TILE * 128;
+  static constexpr uint32_t TILE_BYTES = 2 * ATOMS * ATOM_BYTES;      // K + V
+  static constexpr int QPITCH = HD + 8;
+  static constexpr uint32_t Q_BYTES = 16 * QPITCH * 2;
+  static constexpr uint32_t RING_BYTES = DA_WARPS * DA_STAGES * TILE_BYTES;
+  static constexpr size_t BYTES = 1024 + RING_BYTES + DA_WARPS * Q_BYTES + DA_WARPS * DA_STAGES * 8;
 };
 
-template <int HD>
-__global__ void __launch_bounds__(DA_WARPS * 32)
-decode_attn_kernel(const bf16 *__restrict__ qkv, long long ldqkv, bf16 *__restrict__ k_cache, bf16 *__restrict__ v_cache,
-                   const int32_t *__restrict__ block_table, int max_pages, const int32_t *__restrict__ ctx_len,
+template <int HD, int DA_WARPS, int DA_STAGES>
+__global__ void __launch_bounds__(DA_WARPS * 32, 1)
+decode_attn_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                   const bf16 *__restrict__ qkv, long long ldqkv, bf16 *__restrict__ k_cache, bf16 *__restrict__ v_cache,
+                   const int32_t *__restrict__ block_table, int max_pages, const int32_t *__restrict__ ctx_len, int B,
                    int page_size, int n_q, int n_kv, const bf16 *__restrict__ cosT, const bf16 *__restrict__ sinT,
                    float scale, float *__restrict__ split_ws, int n_splits, int chunk) {
-  using SM = DaSmem<HD>;
-  constexpr int PITCH = SM::PITCH;
+  using SM = DaSmem<HD, DA_WARPS, DA_STAGES>;
+  constexpr int QP = SM::QPITCH;
   constexpr int NJ = HD / 8;                                  // 8-wide output column tiles of O
-  extern __shared__ __align__(16) uint8_t da_smem[];
-  bf16 *sQ = reinterpret_cast<bf16 *>(da_smem);
-  bf16 *ring = sQ + 16 * PITCH;
-  float *s_ml = reinterpret_cast<float *>(ring + DA_WARPS * SM::WARP_ELEMS);   // [warp][16 rows][m, l]
+  extern __shared__ uint8_t da_smem_raw[];
+  uint8_t *smem = da_smem_raw + ((1024u - (smem_u32(da_smem_raw) & 1023u)) & 1023u);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t *ring = smem + (size_t)warp * DA_STAGES * SM::TILE_BYTES;
+  bf16 *sQ = reinterpret_cast<bf16 *>(smem + SM::RING_BYTES + (size_t)warp * SM::Q_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SM::RING_BYTES + DA_WARPS * SM::Q_BYTES) + warp * DA_STAGES;
   const int G = n_q / n_kv;
-  const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) pdl_launch_dependents();
-  const int ctx = ctx_len[b];            // written by the previous step's argmax kernel: complete long before this launch
-  const int total = ctx + 1;
-  const int k0 = split * chunk;
-  const int k1 = min(total, k0 + chunk);
-  float *ws = split_ws + (((size_t)b * n_q + (size_t)kvh * G) * n_splits + split) * (HD + 2);
-  const size_t ws_head = (size_t)n_splits * (HD + 2);
-  if (k0 >= k1) {
-    pdl_wait();                          // split_ws may still be read by the previous layer's combine kernel
-    for (int g = tid; g < G; g += DA_WARPS * 32) { ws[g * ws_head] = -INFINITY; ws[g * ws_head + 1] = 0.f; }
-    return;
-  }
-  const int n_tiles = (k1 - k0 + DA_TILE - 1) / DA_TILE;     // tiles of this CTA; warp w takes w, w + 4, ...
-  const int my_tiles = (n_tiles - warp + DA_WARPS - 1) / DA_WARPS;
-  const size_t tok_stride = (size_t)n_kv * HD;
-  const int32_t *bt = block_table + (size_t)b * max_pages;
-  bf16 *wring = ring + warp * SM::WARP_ELEMS;
-
-  // K / V rows of one tile: 16 rows x (HD / 8) 16-byte pieces each, spread over the 32 lanes.  Rows of tokens that are
-  // not cached yet (the new token, written below) or beyond the context are zero-filled.
-  auto issue_tile = [&](int i) {
-    if (i < my_tiles) {
-      const int key0 = k0 + (warp + i * DA_WARPS) * DA_TILE;
-      bf16 *sk = wring + (i % DA_STAGES) * SM::STAGE_ELEMS, *sv = sk + SM::TILE_ELEMS;
-      const size_t row0 = (size_t)bt[key0 / page_size] * page_size + key0 % page_size;   // page_size % 16 == 0: one page per tile
-      constexpr int PIECES = HD / 8;                         // 16-byte pieces per row
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  if (lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
 #pragma unroll
-      for (int j = 0; j < DA_TILE * PIECES / 32; ++j) {
-        const int idx = lane + j * 32;
-        const int r = idx / PIECES, c = idx % PIECES;
-        bf16 *dk = sk + r * PITCH + c * 8, *dv = sv + r * PITCH + c * 8;
-        if (key0 + r < ctx) {
-          const size_t off = (row0 + r) * tok_stride + (size_t)kvh * HD + c * 8;
-          cp_async16(dk, k_cache + off);
-          cp_async16(dv, v_cache + off);
-        } else {
-          *reinterpret_cast<uint4 *>(dk) = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4 *>(dv) = make_uint4(0, 0, 0, 0);
-        }
-      }
-    }
-    cp_async_commit();                   // one group per ring slot use, empty or not, so the wait counts stay uniform
-  };
-#pragma unroll
-  for (int i = 0; i < DA_STAGES; ++i) issue_tile(i);
-
-  pdl_wait();                            // qkv comes from the preceding skinny GEMM
-  const bf16 *row = qkv + (size_t)b * ldqkv;
-  const bf16 *c = cosT + (size_t)b * HD, *s = sinT + (size_t)b * HD;
-  for (int i = tid; i < 16 * HD; i += DA_WARPS * 32) {
-    const int g = i / HD, d = i % HD;
-    float v = 0.f;
-    if (g < G) v = rope_elem_bf16(row + (size_t)(kvh * G + g) * HD, d, HD, c, s);
-    sQ[g * PITCH + d] = __float2bfloat16_rn(v);
+    for (int s = 0; s < DA_STAGES; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
+  // rows >= G of the Q tile stay zero for the whole kernel
+  for (int i = lane; i < 16 * QP / 2; i += 32) reinterpret_cast<uint32_t *>(sQ)[i] = 0u;
+  __syncwarp();
 
+  const int n_items = B * n_kv * n_splits;
   const int m = lane >> 3, l8 = lane & 7;
   const int r0 = lane >> 2, cq = (lane & 3) * 2;
-  uint32_t qf[HD / 16][4];
-#pragma unroll
-  for (int kk = 0; kk < HD / 16; ++kk) ldmatrix_x4(qf[kk], sQ + ((m & 1) * 8 + l8) * PITCH + kk * 16 + (m >> 1) * 8);
-  float o[NJ][4];
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-  float run_m[2] = {-INFINITY, -INFINITY}, run_l[2] = {0.f, 0.f};
+  const uint32_t ring_s = smem_u32(ring);
+  uint32_t phase_bits = 0;                                    // bit s = parity of the next completion of ring slot s
+  bool waited = false;                                        // griddepcontrol.wait executed (first item only)
 
-  for (int i = 0; i < my_tiles; ++i) {
-    cp_async_wait<DA_STAGES - 1>();
+  // items in the order (key range, sequence, kv head): neighbouring workers get the same range of different sequences,
+  // so live and dead ranges are spread evenly; worker id = warp * grid + cta spreads a small batch over all SMs
+  for (int item = warp * (int)gridDim.x + (int)blockIdx.x; item < n_items; item += DA_WARPS * (int)gridDim.x) {
+    const int split = item / (B * n_kv);
+    const int pair = item - split * (B * n_kv);
+    const int b = pair / n_kv, kvh = pair - b * n_kv;
+    const int ctx = ctx_len[b];          // written by the previous step's argmax kernel: complete long before this launch
+    const int total = ctx + 1;
+    const int k0 = split * chunk;
+    const int k1 = min(total, k0 + chunk);
+    float *ws = split_ws + (((size_t)b * n_q + (size_t)kvh * G) * n_splits + split) * (HD + 2);
+    const size_t ws_head = (size_t)n_splits * (HD + 2);
+    if (k0 >= k1) {
+      if (!waited) { pdl_wait(); waited = true; }             // split_ws may still be read by the previous layer's combine kernel
+      for (int g = lane; g < G; g += 32) { ws[g * ws_head] = -INFINITY; ws[g * ws_head + 1] = 0.f; }
+      continue;
+    }
+    const int n_tiles = (k1 - k0 + DA_TILE - 1) / DA_TILE;
+    const int32_t *bt = block_table + (size_t)b * max_pages;
+
+    // one tile = the K and the V block of 16 consecutive keys of this kv head: 2 * ATOMS boxes of [16 rows x 64 dims]
+    auto issue_tile = [&](int i) {
+      if (i < n_tiles && lane == 0) {
+        const int s = i % DA_STAGES;
+        const int key0 = k0 + i * DA_TILE;
+        const int row = (bt[key0 / page_size] * n_kv + kvh) * page_size + key0 % page_size;
+        uint8_t *dst = ring + (size_t)s * SM::TILE_BYTES;
+        mbar_expect_tx(&bars[s], SM::TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < SM::ATOMS; ++a) {
+          tma_load_2d(dst + a * SM::ATOM_BYTES, &map_k, &bars[s], a * 64, row);
+          tma_load_2d(dst + (SM::ATOMS + a) * SM::ATOM_BYTES, &map_v, &bars[s], a * 64, row);
+        }
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < DA_STAGES; ++i) issue_tile(i);
+
+    if (!waited) { pdl_wait(); waited = true; }               // qkv comes from the preceding skinny GEMM
+    const bf16 *row = qkv + (size_t)b * ldqkv;
+    const bf16 *c = cosT + (size_t)b * HD, *s_ = sinT + (size_t)b * HD;
+    for (int i = lane; i < G * HD; i += 32) {
+      const int g = i / HD, d = i % HD;
+      sQ[g * QP + d] = __float2bfloat16_rn(rope_elem_bf16(row + (size_t)(kvh * G + g) * HD, d, HD, c, s_));
+    }
     __syncwarp();
-    const int key0 = k0 + (warp + i * DA_WARPS) * DA_TILE;
-    bf16 *sk = wring + (i % DA_STAGES) * SM::STAGE_ELEMS, *sv = sk + SM::TILE_ELEMS;
-    if (ctx >= key0 && ctx < key0 + DA_TILE) {
-      // this tile holds the new token: rope its key, place k / v in the tile and append them to the cache
-      const bf16 *knew = row + (size_t)n_q * HD + (size_t)kvh * HD;
-      const bf16 *vnew = row + (size_t)(n_q + n_kv) * HD + (size_t)kvh * HD;
-      const size_t dst = ((size_t)bt[ctx / page_size] * page_size + ctx % page_size) * tok_stride + (size_t)kvh * HD;
-      const int r = ctx - key0;
-      for (int d = lane; d < HD; d += 32) {
-        const bf16 kr = __float2bfloat16_rn(rope_elem_bf16(knew, d, HD, c, s));
-        const bf16 vr = vnew[d];
-        sk[r * PITCH + d] = kr;
-        sv[r * PITCH + d] = vr;
-        k_cache[dst + d] = kr;
-        v_cache[dst + d] = vr;
+    uint32_t qf[HD / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) ldmatrix_x4(qf[kk], smem_u32(sQ + ((m & 1) * 8 + l8) * QP + kk * 16 + (m >> 1) * 8));
+    float o[NJ][4];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+    float run_m[2] = {-INFINITY, -INFINITY}, run_l[2] = {0.f, 0.f};
+
+    for (int i = 0; i < n_tiles; ++i) {
+      const int s = i % DA_STAGES;
+      mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+      phase_bits ^= 1u << s;
+      const int key0 = k0 + i * DA_TILE;
+      const uint32_t sk = ring_s + (uint32_t)s * SM::TILE_BYTES, sv = sk + SM::ATOMS * SM::ATOM_BYTES;
+      if (ctx >= key0 && ctx < key0 + DA_TILE) {
+        // this tile holds the new token: rope its key, place k / v in the (swizzled) tile and append them to the cache
+        const bf16 *knew = row + (size_t)n_q * HD + (size_t)kvh * HD;
+        const bf16 *vnew = row + (size_t)(n_q + n_kv) * HD + (size_t)kvh * HD;
+        const int r = ctx - key0;
+        const size_t dst = ((size_t)(bt[ctx / page_size] * n_kv + kvh) * page_size + ctx % page_size) * HD;
+        uint8_t *tk = ring + (size_t)s * SM::TILE_BYTES, *tv = tk + SM::ATOMS * SM::ATOM_BYTES;
+        for (int d = lane; d < HD; d += 32) {
+          const bf16 kr = __float2bfloat16_rn(rope_elem_bf16(knew, d, HD, c, s_));
+          const bf16 vr = vnew[d];
+          const uint32_t off = (uint32_t)(d >> 6) * SM::ATOM_BYTES + r * 128 + ((((d & 63) >> 3) ^ (r & 7)) << 4) + (d & 7) * 2;
+          *reinterpret_cast<bf16 *>(tk + off) = kr;
+          *reinterpret_cast<bf16 *>(tv + off) = vr;
+          k_cache[dst + d] = kr;
+          v_cache[dst + d] = vr;
+        }
+        __syncwarp();
       }
-      __syncwarp();
-    }
-    // ---- S = Q.K^T for the 16 keys of the tile (two 8-key column tiles) ----
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      // ---- S = Q.K^T for the 16 keys of the tile (two 8-key column tiles) ----
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      {
+        const int kr = (m >> 1) * 8 + l8;                     // key row this lane addresses
 #pragma unroll
-    for (int kk = 0; kk < HD / 16; ++kk) {
-      uint32_t bb[4];
-      ldmatrix_x4(bb, sk + ((m >> 1) * 8 + l8) * PITCH + kk * 16 + (m & 1) * 8);
-      mma_bf16_16816(acc[0], qf[kk], bb[0], bb[1]);
-      mma_bf16_16816(acc[1], qf[kk], bb[2], bb[3]);
-    }
-    // ---- online softmax: this thread holds rows r0 (e = 0, 1) and r0 + 8 (e = 2, 3), keys j * 8 + cq + (e & 1) ----
-    float tmax[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool ok = key0 + j * 8 + cq + (e & 1) < total;
-        acc[j][e] = ok ? acc[j][e] * scale : -INFINITY;
-        tmax[e >> 1] = fmaxf(tmax[e >> 1], acc[j][e]);
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          uint32_t bb[4];
+          const int ch = (kk & 3) * 2 + (m & 1);              // 16-byte chunk inside the 64-dim atom
+          ldmatrix_x4(bb, sk + (kk >> 2) * SM::ATOM_BYTES + kr * 128 + ((ch ^ (kr & 7)) << 4));
+          mma_bf16_16816(acc[0], qf[kk], bb[0], bb[1]);
+          mma_bf16_16816(acc[1], qf[kk], bb[2], bb[3]);
+        }
       }
-    float corr[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      tmax[h] = fmaxf(tmax[h], __shfl_xor_sync(0xffffffffu, tmax[h], 1));
-      tmax[h] = fmaxf(tmax[h], __shfl_xor_sync(0xffffffffu, tmax[h], 2));
-      const float mn = fmaxf(run_m[h], tmax[h]);              // finite: every processed tile has a live key
-      corr[h] = __expf(run_m[h] - mn);                        // exp(-inf) = 0 on the first tile
-      run_m[h] = mn;
-      run_l[h] *= corr[h];
-    }
-    uint32_t pa[4];
-    {
-      float pv[2][4];
+      // ---- online softmax: this thread holds rows r0 (e = 0, 1) and r0 + 8 (e = 2, 3), keys j * 8 + cq + (e & 1) ----
+      float tmax[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          pv[j][e] = __expf(acc[j][e] - run_m[e >> 1]);
-          run_l[e >> 1] += pv[j][e];
+          const bool ok = key0 + j * 8 + cq + (e & 1) < total;
+          acc[j][e] = ok ? acc[j][e] * scale : -INFINITY;
+          tmax[e >> 1] = fmaxf(tmax[e >> 1], acc[j][e]);
         }
-      pa[0] = pack_bf16(pv[0][0], pv[0][1]);
-      pa[1] = pack_bf16(pv[0][2], pv[0][3]);
-      pa[2] = pack_bf16(pv[1][0], pv[1][1]);
-      pa[3] = pack_bf16(pv[1][2], pv[1][3]);
-    }
-    // ---- O = O * corr + P.V ----
+      float corr[2];
 #pragma unroll
-    for (int jj = 0; jj < HD / 16; ++jj) {
-      uint32_t bb[4];
-      ldmatrix_x4_trans(bb, sv + ((m & 1) * 8 + l8) * PITCH + jj * 16 + (m >> 1) * 8);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        float (&oo)[4] = o[jj * 2 + t];
-        oo[0] *= corr[0]; oo[1] *= corr[0]; oo[2] *= corr[1]; oo[3] *= corr[1];
+      for (int h = 0; h < 2; ++h) {
+        tmax[h] = fmaxf(tmax[h], __shfl_xor_sync(0xffffffffu, tmax[h], 1));
+        tmax[h] = fmaxf(tmax[h], __shfl_xor_sync(0xffffffffu, tmax[h], 2));
+        const float mn = fmaxf(run_m[h], tmax[h]);            // finite: every processed tile has a live key
+        corr[h] = __expf(run_m[h] - mn);                      // exp(-inf) = 0 on the first tile
+        run_m[h] = mn;
+        run_l[h] *= corr[h];
       }
-      mma_bf16_16816(o[jj * 2], pa, bb[0], bb[1]);
-      mma_bf16_16816(o[jj * 2 + 1], pa, bb[2], bb[3]);
+      uint32_t pa[4];
+      {
+        float pv[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            pv[j][e] = __expf(acc[j][e] - run_m[e >> 1]);
+            run_l[e >> 1] += pv[j][e];
+          }
+        pa[0] = pack_bf16(pv[0][0], pv[0][1]);
+        pa[1] = pack_bf16(pv[0][2], pv[0][3]);
+        pa[2] = pack_bf16(pv[1][0], pv[1][1]);
+        pa[3] = pack_bf16(pv[1][2], pv[1][3]);
+      }
+      // ---- O = O * corr + P.V (the scaling is skipped when no row of the warp moved its maximum: corr == 1 exactly) ----
+      {
+        const bool rescale = __any_sync(0xffffffffu, corr[0] != 1.0f || corr[1] != 1.0f);
+        const int vr = (m & 1) * 8 + l8;                      // key row this lane addresses
+#pragma unroll
+        for (int jj = 0; jj < HD / 16; ++jj) {
+          uint32_t bb[4];
+          const int ch = (jj & 3) * 2 + (m >> 1);
+          ldmatrix_x4_trans(bb, sv + (jj >> 2) * SM::ATOM_BYTES + vr * 128 + ((ch ^ (vr & 7)) << 4));
+          if (rescale) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              float (&oo)[4] = o[jj * 2 + t];
+              oo[0] *= corr[0]; oo[1] *= corr[0]; oo[2] *= corr[1]; oo[3] *= corr[1];
+            }
+          }
+          mma_bf16_16816(o[jj * 2], pa, bb[0], bb[1]);
+          mma_bf16_16816(o[jj * 2 + 1], pa, bb[2], bb[3]);
+        }
+      }
+      __syncwarp();                      // every lane is done with this ring slot
+      issue_tile(i + DA_STAGES);
     }
-    __syncwarp();                        // every lane is done with this ring slot
-    issue_tile(i + DA_STAGES);
-  }
-  cp_async_wait<0>();
-  // ---- merge the four warps (fixed order: warp 0..3), one fp32 partial per head ----
+    // ---- one fp32 partial (max, sum, o[hd]) per head of this item, straight from the registers ----
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    run_l[h] += __shfl_xor_sync(0xffffffffu, run_l[h], 1);
-    run_l[h] += __shfl_xor_sync(0xffffffffu, run_l[h], 2);
-  }
-  __syncthreads();                       // all warps left their rings: the space is reused for the fp32 O tiles
-  float *sO = reinterpret_cast<float *>(ring);               // [warp][16][HD + 4]
-  constexpr int OP = HD + 4;
-  static_assert((size_t)DA_WARPS * 16 * OP * sizeof(float) <= (size_t)DA_WARPS * SM::WARP_ELEMS * sizeof(bf16), "merge buffer");
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    *reinterpret_cast<float2 *>(sO + ((size_t)warp * 16 + r0) * OP + j * 8 + cq) = make_float2(o[j][0], o[j][1]);
-    *reinterpret_cast<float2 *>(sO + ((size_t)warp * 16 + r0 + 8) * OP + j * 8 + cq) = make_float2(o[j][2], o[j][3]);
-  }
-  if ((lane & 3) == 0) {
-    s_ml[(warp * 16 + r0) * 2] = run_m[0];
-    s_ml[(warp * 16 + r0) * 2 + 1] = run_l[0];
-    s_ml[(warp * 16 + r0 + 8) * 2] = run_m[1];
-    s_ml[(warp * 16 + r0 + 8) * 2 + 1] = run_l[1];
-  }
-  __syncthreads();
-  for (int idx = tid; idx < G * HD; idx += DA_WARPS * 32) {
-    const int g = idx / HD, d = idx % HD;
-    float M = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < DA_WARPS; ++w) M = fmaxf(M, s_ml[(w * 16 + g) * 2]);
-    float L = 0.f, a = 0.f;
-#pragma unroll
-    for (int w = 0; w < DA_WARPS; ++w) {
-      const float mw = s_ml[(w * 16 + g) * 2];
-      const float f = (mw == -INFINITY) ? 0.f : __expf(mw - M);
-      L += s_ml[(w * 16 + g) * 2 + 1] * f;
-      a += sO[((size_t)w * 16 + g) * OP + d] * f;
+    for (int h = 0; h < 2; ++h) {
+      run_l[h] += __shfl_xor_sync(0xffffffffu, run_l[h], 1);
+      run_l[h] += __shfl_xor_sync(0xffffffffu, run_l[h], 2);
     }
-    ws[g * ws_head + 2 + d] = a;
-    if (d == 0) { ws[g * ws_head] = M; ws[g * ws_head + 1] = L; }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (r0 < G) *reinterpret_cast<float2 *>(ws + r0 * ws_head + 2 + j * 8 + cq) = make_float2(o[j][0], o[j][1]);
+      if (r0 + 8 < G) *reinterpret_cast<float2 *>(ws + (r0 + 8) * ws_head + 2 + j * 8 + cq) = make_float2(o[j][2], o[j][3]);
+    }
+    if ((lane & 3) == 0) {
+      if (r0 < G) { ws[r0 * ws_head] = run_m[0]; ws[r0 * ws_head + 1] = run_l[0]; }
+      if (r0 + 8 < G) { ws[(r0 + 8) * ws_head] = run_m[1]; ws[(r0 + 8) * ws_head + 1] = run_l[1]; }
+    }
+    __syncwarp();                        // the Q staging rows are rewritten by the next item
   }
+  if (!waited) pdl_wait();               // a worker without items still has to honour the dependency before it exits
 }
 
 // grid = (n_q, B), hd threads
@@ -295,18 +294,32 @@ __global__ void decode_attn_combine_kernel(const float *__restrict__ split_ws, i
   out[(size_t)b * ldo + (size_t)h * hd + d] = __float2bfloat16_rn(acc / L);
 }
 
-template <int HD>
-static int launch_decode_attn(const bf16 *qkv, long long ldqkv, bf16 *kc, bf16 *vc, const int32_t *bt, int max_pages,
-                              const int32_t *ctx_len, int B, int page_size, int n_q, int n_kv, const bf16 *cosT,
-                              const bf16 *sinT, float scale, float *split_ws, int n_splits, int chunk, cudaStream_t st) {
-  constexpr size_t smem = DaSmem<HD>::BYTES;
+// 2-D view of one layer's K (or V) cache: rows = n_cache_pages * n_kv * page_size tokens, cols = hd; box [16 x 64].
+static int make_cache_map(CUtensorMap *m, const void *cache, long long rows, int hd) {
+  return make_tensor_map_bf16(m, cache, rows, hd, hd, DA_TILE);
+}
+
+template <int HD, int WARPS, int STAGES>
+static int launch_decode_attn(const CUtensorMap &mk, const CUtensorMap &mv, const bf16 *qkv, long long ldqkv, bf16 *kc, bf16 *vc,
+                              const int32_t *bt, int max_pages, const int32_t *ctx_len, int B, int page_size, int n_q, int n_kv,
+                              const bf16 *cosT, const bf16 *sinT, float scale, float *split_ws, int n_splits, int chunk,
+                              cudaStream_t st) {
+  constexpr size_t smem = DaSmem<HD, WARPS, STAGES>::BYTES;
+  static_assert(smem <= 227 * 1024, "decode attention: shared memory budget");
   static bool attr_set = false;
+  static int n_sm = 0;
   if (!attr_set) {
-    OCRB_CUDA(cudaFuncSetAttribute(decode_attn_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OCRB_CUDA(cudaFuncSetAttribute(decode_attn_kernel<HD, WARPS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
     attr_set = true;
   }
-  OCRB_CUDA(launch_pdl_bit(2, decode_attn_kernel<HD>, dim3(n_splits, n_kv, B), dim3(DA_WARPS * 32), smem, st, qkv, ldqkv, kc, vc,
-                           bt, max_pages, ctx_len, page_size, n_q, n_kv, cosT, sinT, scale, split_ws, n_splits, chunk));
+  const long long items = (long long)B * n_kv * n_splits;
+  const int grid = (int)(items < n_sm ? items : n_sm);       // persistent: one CTA of independent warps per SM
+  OCRB_CUDA(launch_pdl_bit(2, decode_attn_kernel<HD, WARPS, STAGES>, dim3(grid), dim3(WARPS * 32), smem, st, mk, mv, qkv, ldqkv,
+                           kc, vc, bt, max_pages, ctx_len, B, page_size, n_q, n_kv, cosT, sinT, scale, split_ws, n_splits, chunk));
   return check_launch("decode_attn_kernel");
 }
 
@@ -314,7 +327,7 @@ static int launch_decode_attn(const bf16 *qkv, long long ldqkv, bf16 *kc, bf16 *
 
 using namespace ocrb;
 
-extern "C" int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cache, void *v_cache,
+extern "C" int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cache, void *v_cache, int32_t n_cache_pages,
                                      const int32_t *block_table, int32_t max_pages, const int32_t *ctx_len, int32_t B,
                                      int32_t page_size, int32_t n_q, int32_t n_kv, int32_t hd, const void *cosT,
                                      const void *sinT, float scale, void *out, int64_t ldo, float *split_ws,
@@ -324,19 +337,31 @@ extern "C" int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cac
   OCRB_REQUIRE(B > 0 && n_kv > 0 && n_q % n_kv == 0 && n_q / n_kv <= DA_MAXG && (hd == 64 || hd == 128) && n_splits > 0,
                "decode_attention: needs n_q / n_kv <= 16 query heads per KV head and hd of 64 or 128");
   OCRB_REQUIRE(page_size > 0 && page_size % DA_TILE == 0, "decode_attention: page_size must be a multiple of 16");
-  OCRB_REQUIRE(B <= 65535 && n_kv <= 65535, "decode_attention: grid too large");
+  OCRB_REQUIRE(n_cache_pages > 0 && ((uintptr_t)k_cache & 15) == 0 && ((uintptr_t)v_cache & 15) == 0,
+               "decode_attention: cache pointers must be 16-byte aligned, n_cache_pages > 0");
   const int max_ctx = max_pages * page_size;
-  const int chunk = cdiv(cdiv(max_ctx, n_splits), DA_TILE) * DA_TILE;     // keys per CTA, whole tiles
+  const int chunk = cdiv(cdiv(max_ctx, n_splits), DA_TILE) * DA_TILE;     // keys per work item, whole tiles
   cudaStream_t st = (cudaStream_t)stream;
-  int rc;
+  const long long rows = (long long)n_cache_pages * n_kv * page_size;
+  CUtensorMap mk, mv;
+  int rc = make_cache_map(&mk, k_cache, rows, hd);
+  if (rc) return rc;
+  rc = make_cache_map(&mv, v_cache, rows, hd);
+  if (rc) return rc;
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char *e = getenv("OCRB_ATTN_CFG");
+    cfg = e ? atoi(e) : 64;
+  }
+#define DA_LAUNCH(HD_, W_, S_)                                                                                              \
+  launch_decode_attn<HD_, W_, S_>(mk, mv, (const bf16 *)qkv, (long long)ldqkv, (bf16 *)k_cache, (bf16 *)v_cache, block_table, \
+                                  (int)max_pages, ctx_len, (int)B, (int)page_size, (int)n_q, (int)n_kv, (const bf16 *)cosT,    \
+                                  (const bf16 *)sinT, scale, split_ws, (int)n_splits, chunk, st)
   if (hd == 128)
-    rc = launch_decode_attn<128>((const bf16 *)qkv, (long long)ldqkv, (bf16 *)k_cache, (bf16 *)v_cache, block_table,
-                                 (int)max_pages, ctx_len, (int)B, (int)page_size, (int)n_q, (int)n_kv, (const bf16 *)cosT,
-                                 (const bf16 *)sinT, scale, split_ws, (int)n_splits, chunk, st);
+    rc = (cfg == 82) ? DA_LAUNCH(128, 8, 2) : DA_LAUNCH(128, 6, 4);
   else
-    rc = launch_decode_attn<64>((const bf16 *)qkv, (long long)ldqkv, (bf16 *)k_cache, (bf16 *)v_cache, block_table,
-                                (int)max_pages, ctx_len, (int)B, (int)page_size, (int)n_q, (int)n_kv, (const bf16 *)cosT,
-                                (const bf16 *)sinT, scale, split_ws, (int)n_splits, chunk, st);
+    rc = DA_LAUNCH(64, 8, 4);
+#undef DA_LAUNCH
   if (rc) return rc;
   OCRB_CUDA(launch_pdl_bit(4, decode_attn_combine_kernel, dim3(n_q, B), dim3(hd), 0, st, (const float *)split_ws, (int)n_q,
                            (int)n_splits, (int)hd, (bf16 *)out, (long long)ldo));

@@ -55,7 +55,92 @@ rmsnorm_kernel(const bf16 *__restrict__ x, long long ldx, const bf16 *__restrict
   }
 }
 
+// One warp per row, the row stays in registers between the statistics and the scaling (one pass over memory, no block
+// barrier): dim <= 4096.  16-byte accesses; lanes stride the row so every request is a full 512-byte line group.
+__global__ void __launch_bounds__(256)
+rmsnorm_warp_kernel(const bf16 *__restrict__ x, long long ldx, const bf16 *__restrict__ w, bf16 *__restrict__ y,
+                    long long ldy, int rows, int dim, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bf16 *xr = x + (size_t)row * ldx;
+  bf16 *yr = y + (size_t)row * ldy;
+  const int nvec = dim >> 3;
+  uint4 raw[16];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int v = lane + i * 32;
+    raw[i] = make_uint4(0, 0, 0, 0);
+    if (v < nvec) raw[i] = *reinterpret_cast<const uint4 *>(xr + v * 8);
+    const bf16 *e = reinterpret_cast<const bf16 *>(&raw[i]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float f = __bfloat162float(e[k]);
+      ss = fmaf(f, f, ss);
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / (float)dim + eps);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const uint4 wraw = __ldg(reinterpret_cast<const uint4 *>(w + v * 8));
+      const bf16 *e = reinterpret_cast<const bf16 *>(&raw[i]);
+      const bf16 *we = reinterpret_cast<const bf16 *>(&wraw);
+      uint4 o;
+      bf16 *oe = reinterpret_cast<bf16 *>(&o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float n = bf16_round(__bfloat162float(e[k]) * rstd);
+        oe[k] = __float2bfloat16_rn(__bfloat162float(we[k]) * n);
+      }
+      *reinterpret_cast<uint4 *>(yr + v * 8) = o;
+    }
+  }
+}
+
 // ───────────── vision RoPE (fp32 math, unfused like eager torch) ─────────────
+// 16-byte version: a thread rotates 8 (x1, x2) pairs -- x1 from the first half of a head, x2 from the second half.
+// Same per-element arithmetic as the scalar kernel below (which stays for head dims whose half is not a multiple of 8).
+__global__ void __launch_bounds__(256)
+rope_vision_vec_kernel(bf16 *__restrict__ qkv, int S, int heads, int hd, const float *__restrict__ cosT,
+                       const float *__restrict__ sinT) {
+  const int half = hd >> 1, nv = half >> 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = S * 2 * heads * nv;
+  if (idx >= total) return;
+  const int v = idx % nv;
+  int r = idx / nv;
+  const int h = r % heads;
+  r /= heads;
+  const int which = r & 1;
+  const int s = r >> 1;
+  bf16 *p = qkv + ((size_t)s * 3 + which) * heads * hd + (size_t)h * hd + v * 8;
+  const uint4 a = *reinterpret_cast<const uint4 *>(p), b = *reinterpret_cast<const uint4 *>(p + half);
+  const float *c = cosT + (size_t)s * hd + v * 8, *sn = sinT + (size_t)s * hd + v * 8;
+  float c1[8], c2[8], s1[8], s2[8];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    *reinterpret_cast<float4 *>(c1 + 4 * q) = __ldg(reinterpret_cast<const float4 *>(c + 4 * q));
+    *reinterpret_cast<float4 *>(c2 + 4 * q) = __ldg(reinterpret_cast<const float4 *>(c + half + 4 * q));
+    *reinterpret_cast<float4 *>(s1 + 4 * q) = __ldg(reinterpret_cast<const float4 *>(sn + 4 * q));
+    *reinterpret_cast<float4 *>(s2 + 4 * q) = __ldg(reinterpret_cast<const float4 *>(sn + half + 4 * q));
+  }
+  const bf16 *ae = reinterpret_cast<const bf16 *>(&a), *be = reinterpret_cast<const bf16 *>(&b);
+  uint4 oa, ob;
+  bf16 *oae = reinterpret_cast<bf16 *>(&oa), *obe = reinterpret_cast<bf16 *>(&ob);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float x1 = __bfloat162float(ae[k]), x2 = __bfloat162float(be[k]);
+    oae[k] = __float2bfloat16_rn(__fadd_rn(__fmul_rn(x1, c1[k]), __fmul_rn(-x2, s1[k])));
+    obe[k] = __float2bfloat16_rn(__fadd_rn(__fmul_rn(x2, c2[k]), __fmul_rn(x1, s2[k])));
+  }
+  *reinterpret_cast<uint4 *>(p) = oa;
+  *reinterpret_cast<uint4 *>(p + half) = ob;
+}
+
+
 // qkv: [S, 3, heads, hd]; rotates q (slot 0) and k (slot 1) in place.
 __global__ void __launch_bounds__(256)
 rope_vision_kernel(bf16 *__restrict__ qkv, int S, int heads, int hd, const float *__restrict__ cosT,
@@ -89,6 +174,31 @@ __device__ __forceinline__ void rope_bf16_pair(bf16 &a, bf16 &b, bf16 c1, bf16 s
   const float u2 = bf16_round(x1 * __bfloat162float(s2));
   a = __float2bfloat16_rn(t1 + u1);
   b = __float2bfloat16_rn(t2 + u2);
+}
+
+// 16-byte version of the text mRoPE below (head-dim half a multiple of 8, 16-byte aligned rows): same arithmetic.
+__global__ void __launch_bounds__(256)
+rope_text_vec_kernel(bf16 *__restrict__ q, long long ldq, bf16 *__restrict__ k, long long ldk, int T, int n_q, int n_kv,
+                     int hd, const bf16 *__restrict__ cosT, const bf16 *__restrict__ sinT) {
+  const int half = hd >> 1, nv = half >> 3;
+  const int heads = n_q + n_kv;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T * heads * nv) return;
+  const int v = idx % nv;
+  const int r = idx / nv;
+  const int h = r % heads, t = r / heads;
+  bf16 *p = ((h < n_q) ? q + (size_t)t * ldq + (size_t)h * hd : k + (size_t)t * ldk + (size_t)(h - n_q) * hd) + v * 8;
+  const bf16 *c = cosT + (size_t)t * hd + v * 8, *sn = sinT + (size_t)t * hd + v * 8;
+  uint4 a = *reinterpret_cast<const uint4 *>(p), b = *reinterpret_cast<const uint4 *>(p + half);
+  const uint4 c1 = __ldg(reinterpret_cast<const uint4 *>(c)), c2 = __ldg(reinterpret_cast<const uint4 *>(c + half));
+  const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(sn)), s2 = __ldg(reinterpret_cast<const uint4 *>(sn + half));
+  bf16 *ae = reinterpret_cast<bf16 *>(&a), *be = reinterpret_cast<bf16 *>(&b);
+  const bf16 *c1e = reinterpret_cast<const bf16 *>(&c1), *c2e = reinterpret_cast<const bf16 *>(&c2);
+  const bf16 *s1e = reinterpret_cast<const bf16 *>(&s1), *s2e = reinterpret_cast<const bf16 *>(&s2);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) rope_bf16_pair(ae[e], be[e], c1e[e], s1e[e], c2e[e], s2e[e]);
+  *reinterpret_cast<uint4 *>(p) = a;
+  *reinterpret_cast<uint4 *>(p + half) = b;
 }
 
 __global__ void __launch_bounds__(256)
@@ -143,7 +253,7 @@ __global__ void __launch_bounds__(256)
 kv_write_prefill_kernel(const bf16 *__restrict__ k, long long ldk, const bf16 *__restrict__ v, long long ldv,
                         bf16 *__restrict__ k_cache, bf16 *__restrict__ v_cache, const int32_t *__restrict__ block_table,
                         int max_pages, const int32_t *__restrict__ cu_seqlens, int n_seq, int T, int page_size,
-                        int row_vec /* n_kv*hd/8 */) {
+                        int row_vec /* n_kv*hd/8 */, int hd_vec /* hd/8 */) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)T * row_vec) return;
   const int t = (int)(idx / row_vec), vv = (int)(idx - (long long)t * row_vec);
@@ -151,7 +261,10 @@ kv_write_prefill_kernel(const bf16 *__restrict__ k, long long ldk, const bf16 *_
   while (s + 1 < n_seq && t >= cu_seqlens[s + 1]) ++s;
   const int pos = t - cu_seqlens[s];
   const int page = block_table[(size_t)s * max_pages + pos / page_size];
-  const size_t dst = ((size_t)page * page_size + pos % page_size) * row_vec * 8 + (size_t)vv * 8;
+  // cache layout [page][kv head][token in page][hd]: the 16 tokens of a (page, kv head) are one contiguous block
+  const int kvh = vv / hd_vec, dv = vv - kvh * hd_vec;
+  const int n_kv = row_vec / hd_vec;
+  const size_t dst = ((((size_t)page * n_kv + kvh) * page_size + pos % page_size) * hd_vec + dv) * 8;
   *reinterpret_cast<uint4 *>(k_cache + dst) = *reinterpret_cast<const uint4 *>(k + (size_t)t * ldk + vv * 8);
   *reinterpret_cast<uint4 *>(v_cache + dst) = *reinterpret_cast<const uint4 *>(v + (size_t)t * ldv + vv * 8);
 }
@@ -212,6 +325,11 @@ extern "C" int ocrb_rmsnorm_bf16(const void *x, int64_t ldx, const void *w, void
                                  int32_t dim, float eps, void *stream) {
   OCRB_REQUIRE(x && w && y && rows > 0 && dim > 0 && dim % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0,
                "rmsnorm_bf16: bad arguments (dim and strides must be multiples of 8)");
+  if (dim <= 4096 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0) {
+    rmsnorm_warp_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, ldx, (const bf16 *)w, (bf16 *)y, ldy,
+                                                                         rows, dim, eps);
+    return check_launch("rmsnorm_warp_kernel");
+  }
   rmsnorm_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, ldx, (const bf16 *)w, (bf16 *)y, ldy, dim, eps);
   return check_launch("rmsnorm_kernel");
 }
@@ -219,6 +337,12 @@ extern "C" int ocrb_rmsnorm_bf16(const void *x, int64_t ldx, const void *w, void
 extern "C" int ocrb_rope_vision(void *qkv, int32_t S, int32_t heads, int32_t hd, const float *cosT, const float *sinT,
                                 void *stream) {
   OCRB_REQUIRE(qkv && cosT && sinT && S > 0 && heads > 0 && hd > 0 && hd % 2 == 0, "rope_vision: bad arguments");
+  if ((hd / 2) % 8 == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)cosT & 15) == 0 && ((uintptr_t)sinT & 15) == 0 &&
+      (long long)S * 2 * heads * (hd / 16) < (1ll << 31)) {
+    const int total_v = S * 2 * heads * (hd / 16);
+    rope_vision_vec_kernel<<<cdiv(total_v, 256), 256, 0, (cudaStream_t)stream>>>((bf16 *)qkv, S, heads, hd, cosT, sinT);
+    return check_launch("rope_vision_vec_kernel");
+  }
   const long long total = (long long)S * 2 * heads * (hd / 2);
   rope_vision_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((bf16 *)qkv, S, heads, hd, cosT, sinT);
   return check_launch("rope_vision_kernel");
@@ -227,6 +351,13 @@ extern "C" int ocrb_rope_vision(void *qkv, int32_t S, int32_t heads, int32_t hd,
 extern "C" int ocrb_rope_text(void *q, int64_t ldq, void *k, int64_t ldk, int32_t T, int32_t n_q, int32_t n_kv,
                               int32_t hd, const void *cosT, const void *sinT, void *stream) {
   OCRB_REQUIRE(q && k && cosT && sinT && T > 0 && n_q > 0 && n_kv > 0 && hd % 2 == 0, "rope_text: bad arguments");
+  if ((hd / 2) % 8 == 0 && ldq % 8 == 0 && ldk % 8 == 0 && ((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 &&
+      ((uintptr_t)cosT & 15) == 0 && ((uintptr_t)sinT & 15) == 0 && (long long)T * (n_q + n_kv) * (hd / 16) < (1ll << 31)) {
+    const int total_v = T * (n_q + n_kv) * (hd / 16);
+    rope_text_vec_kernel<<<cdiv(total_v, 256), 256, 0, (cudaStream_t)stream>>>((bf16 *)q, ldq, (bf16 *)k, ldk, T, n_q, n_kv, hd,
+                                                                               (const bf16 *)cosT, (const bf16 *)sinT);
+    return check_launch("rope_text_vec_kernel");
+  }
   const long long total = (long long)T * (n_q + n_kv) * (hd / 2);
   rope_text_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((bf16 *)q, ldq, (bf16 *)k, ldk, T, n_q, n_kv, hd,
                                                                       (const bf16 *)cosT, (const bf16 *)sinT);
@@ -285,12 +416,12 @@ extern "C" int ocrb_kv_write_prefill(const void *k, int64_t ldk, const void *v, 
                                      const int32_t *block_table, int32_t max_pages, const int32_t *cu_seqlens,
                                      int32_t n_seq, int32_t T, int32_t page_size, int32_t n_kv, int32_t hd, void *stream) {
   OCRB_REQUIRE(k && v && k_cache && v_cache && block_table && cu_seqlens, "kv_write_prefill: null pointer");
-  OCRB_REQUIRE(T > 0 && n_seq > 0 && page_size > 0 && (n_kv * hd) % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0,
+  OCRB_REQUIRE(T > 0 && n_seq > 0 && page_size > 0 && hd % 8 == 0 && n_kv > 0 && ldk % 8 == 0 && ldv % 8 == 0,
                "kv_write_prefill: bad sizes");
   const int row_vec = n_kv * hd / 8;
   kv_write_prefill_kernel<<<cdiv((long long)T * row_vec, 256), 256, 0, (cudaStream_t)stream>>>(
       (const bf16 *)k, ldk, (const bf16 *)v, ldv, (bf16 *)k_cache, (bf16 *)v_cache, block_table, max_pages, cu_seqlens,
-      n_seq, T, page_size, row_vec);
+      n_seq, T, page_size, row_vec, hd / 8);
   return check_launch("kv_write_prefill_kernel");
 }
 

@@ -62,7 +62,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   constexpr int TMEM_COLS = 2 * BN;                 // 256 / 512 columns: two accumulators
   extern __shared__ uint8_t gm_smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(gm_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem = gm_smem_raw + ((1024u - (smem_u32(gm_smem_raw) & 1023u)) & 1023u);   // offset into the __shared__ array: keeps the address space
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + GM_STAGES * STAGE_BYTES);
   uint64_t *empty_bar = full_bar + GM_STAGES;
   uint64_t *tmem_full = empty_bar + GM_STAGES;      // [2]
@@ -173,17 +173,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int out_col = (n0 >> 1) + blk * 64 + c;
             if (row_ok && ng < p.N) {
               bf16 *drow = p.D + (size_t)row * p.ldd + out_col;
+              uint4 bg4[4], bu4[4];
+#pragma unroll
+              for (int v8 = 0; v8 < 4; ++v8) {
+                bg4[v8] = make_uint4(0, 0, 0, 0);
+                bu4[v8] = make_uint4(0, 0, 0, 0);
+                if (p.bias) {
+                  bg4[v8] = __ldg(reinterpret_cast<const uint4 *>(p.bias + ng + v8 * 8));
+                  bu4[v8] = __ldg(reinterpret_cast<const uint4 *>(p.bias + ng + 64 + v8 * 8));
+                }
+              }
 #pragma unroll
               for (int v8 = 0; v8 < 4; ++v8) {
                 uint4 pk;
                 bf16 *pe = reinterpret_cast<bf16 *>(&pk);
+                const bf16 *bge = reinterpret_cast<const bf16 *>(&bg4[v8]);
+                const bf16 *bue = reinterpret_cast<const bf16 *>(&bu4[v8]);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                   const int i = v8 * 8 + e;
                   float gv = __uint_as_float(g[i]), uv = __uint_as_float(u[i]);
                   if (p.bias) {
-                    gv += __bfloat162float(p.bias[ng + i]);
-                    uv += __bfloat162float(p.bias[ng + 64 + i]);
+                    gv += __bfloat162float(bge[e]);
+                    uv += __bfloat162float(bue[e]);
                   }
                   pe[e] = __float2bfloat16_rn(silu_bf16r(bf16_round(gv)) * bf16_round(uv));
                 }
@@ -206,18 +218,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (row_ok && n < p.N) {
             bf16 *drow = p.D + (size_t)row * p.ldd + n;
             const bf16 *rrow = p.residual ? p.residual + (size_t)row * p.ldr + n : nullptr;
+            // all loads of the chunk first: the residual is usually updated in place (D == residual), so a load inside
+            // the store loop may not be moved above the preceding store and every 16-byte piece would cost its own
+            // L2 round trip (4 per chunk, 32 per tile: longer than the tile's MMAs at K = 1280)
+            uint4 rk4[4], bk4[4];
+#pragma unroll
+            for (int v8 = 0; v8 < 4; ++v8) {
+              rk4[v8] = make_uint4(0, 0, 0, 0);
+              bk4[v8] = make_uint4(0, 0, 0, 0);
+              if (n + v8 * 8 < p.N) {
+                if (p.epilogue == OCRB_EPI_RESIDUAL) rk4[v8] = *reinterpret_cast<const uint4 *>(rrow + v8 * 8);
+                if (p.bias) bk4[v8] = __ldg(reinterpret_cast<const uint4 *>(p.bias + n + v8 * 8));
+              }
+            }
 #pragma unroll
             for (int v8 = 0; v8 < 4; ++v8) {
               if (n + v8 * 8 >= p.N) break;
-              uint4 pk, rk = make_uint4(0, 0, 0, 0);
+              uint4 pk;
+              const uint4 rk = rk4[v8];
               bf16 *pe = reinterpret_cast<bf16 *>(&pk);
-              if (p.epilogue == OCRB_EPI_RESIDUAL) rk = *reinterpret_cast<const uint4 *>(rrow + v8 * 8);
               const bf16 *re = reinterpret_cast<const bf16 *>(&rk);
+              const bf16 *be = reinterpret_cast<const bf16 *>(&bk4[v8]);
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int i = v8 * 8 + e;
                 float v = __uint_as_float(r[i]);
-                if (p.bias) v += __bfloat162float(p.bias[n + i]);
+                if (p.bias) v += __bfloat162float(be[e]);
                 v = bf16_round(v);
                 if (p.epilogue == OCRB_EPI_RESIDUAL) v += __bfloat162float(re[e]);
                 else if (p.epilogue == OCRB_EPI_GELU) v = gelu_bf16r(v);
@@ -311,6 +337,7 @@ extern "C" int ocrb_gemm_bf16(const void *A, int64_t lda, const void *W, int64_t
   OCRB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)D & 15) == 0,
                "gemm_bf16: pointers must be 16-byte aligned");
   OCRB_REQUIRE(epilogue >= 0 && epilogue <= 3, "gemm_bf16: bad epilogue");
+  OCRB_REQUIRE(!bias || ((uintptr_t)bias & 15) == 0, "gemm_bf16: bias must be 16-byte aligned");
   OCRB_REQUIRE(epilogue != OCRB_EPI_RESIDUAL || (residual && ldr % 8 == 0 && ((uintptr_t)residual & 15) == 0),
                "gemm_bf16: residual epilogue needs a 16-byte aligned residual with ldr % 8 == 0");
   OCRB_REQUIRE(epilogue != OCRB_EPI_SWIGLU || N % 128 == 0, "gemm_bf16: SwiGLU needs packed N % 128 == 0");

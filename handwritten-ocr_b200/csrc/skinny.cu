@@ -71,6 +71,13 @@ __device__ __forceinline__ void tma_load_2d_hint(void *dst, const CUtensorMap *m
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (TMA engine, no tensor map), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ void sk_stamp(const SkinnyParams &p, int slot) {
   if (p.trace) {
     unsigned long long t;
@@ -285,13 +292,16 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   constexpr int ACC_STRIDE = (BP <= 16) ? 16 : (BP <= 32 ? 32 : (BP <= 64 ? 64 : 128));   // TMEM columns between the two accumulators
   constexpr int TMEM_COLS = (2 * ACC_STRIDE < 32) ? 32 : 2 * ACC_STRIDE;              // power of two >= 32
   extern __shared__ uint8_t sk_smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sk_smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for the swizzle atoms, computed as an OFFSET into the __shared__ array so that the compiler keeps
+  // the shared address space (LDS / STS instead of generic LD / ST, and no false aliasing with the global stores)
+  uint8_t *smem = sk_smem_raw + ((1024u - (smem_u32(sk_smem_raw) & 1023u)) & 1023u);
   uint64_t *full_w = reinterpret_cast<uint64_t *>(smem + ST * STAGE_BYTES);
   uint64_t *full_x = full_w + ST;
   uint64_t *empty = full_x + ST;
   uint64_t *tmem_full = empty + ST;     // [2]
   uint64_t *tmem_empty = tmem_full + 2;        // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+  uint64_t *fix_bar = tmem_empty + 2;          // partials of the other contributors landed in the (idle) ring
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fix_bar + 1);
   float *s_up = reinterpret_cast<float *>(tmem_slot + 2);          // [64][CC] SwiGLU exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -314,6 +324,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 128);
     }
+    mbar_init(fix_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -409,16 +420,28 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       int tile, kb0, nkb;
       sp.seg(seg, tile, kb0, nkb);
       const int acc = seg & 1;
-      mbar_wait(&tmem_full[acc], (seg >> 1) & 1);
-      if (et == 0 && seg == 0) sk_stamp(p, 5);      // first segment accumulated
-      if (et == 0 && seg == n_segs - 1) sk_stamp(p, 6);   // last segment accumulated
-      tcgen05_fence_after();
       // The BC live accumulator columns are processed in chunks of CC <= 16, so the register footprint (and with it
       // the two-CTAs-per-SM co-residency PDL needs) is the same for 4 and for 64 sequences.
       constexpr int CC = (BC < 16) ? BC : 16;
       const bool finishes = (kb0 + nkb == KB);
       const int n = tile * SK_BM + et;
       const bool n_ok = n < p.N;
+      // Residual values are fetched one chunk AHEAD of their use and the first chunk before the accumulator is even
+      // complete: the residual is usually updated in place (D == residual), so the compiler must keep every load behind
+      // the stores that precede it in program order -- loading inside the store loop serialised one L2 round trip per
+      // sequence (60 us of a 64 us o_proj at B = 96).
+      const bool use_res = finishes && p.epilogue == OCRB_EPI_RESIDUAL && n_ok;
+      uint32_t rr_next[CC];
+      auto load_res = [&](int c0, uint32_t (&rr)[CC]) {
+#pragma unroll
+        for (int i = 0; i < CC; ++i)
+          rr[i] = (c0 + i < p.B) ? (uint32_t)__ldcg(reinterpret_cast<const unsigned short *>(p.residual + (size_t)(c0 + i) * p.ldr + n)) : 0u;
+      };
+      if (use_res) load_res(0, rr_next);
+      mbar_wait(&tmem_full[acc], (seg >> 1) & 1);
+      if (et == 0 && seg == 0) sk_stamp(p, 5);      // first segment accumulated
+      if (et == 0 && seg == n_segs - 1) sk_stamp(p, 6);   // last segment accumulated
+      tcgen05_fence_after();
       auto load_chunk = [&](int c0, float (&v)[CC]) {
         uint32_t r[CC];
         tmem_ld_cols<CC>(lane_addr + acc * ACC_STRIDE + c0, r);
@@ -438,7 +461,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           float v[CC];
           load_chunk(c0, v);
 #pragma unroll
-          for (int i = 0; i < CC; ++i) __stcg(slot + (c0 + i) * 128 + et, v[i]);
+          for (int i = 0; i < CC; ++i) slot[(c0 + i) * 128 + et] = v[i];   // plain stores: __threadfence + release flag publish them
         }
         __threadfence();
         named_bar_sync(1, 128);
@@ -448,6 +471,9 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         }
       } else {
         int c_first = (int)blockIdx.x;               // first contributing CTA (== blockIdx.x: none)
+        constexpr uint32_t PART_BYTES = BC * 128 * sizeof(float);
+        constexpr int FIX_SLOTS = (ST * STAGE_BYTES / PART_BYTES) < 8 ? (int)(ST * STAGE_BYTES / PART_BYTES) : 8;
+        bool in_smem = false;
         if (kb0 > 0) {
           // this CTA finishes a tile that earlier CTAs started: their partials are added in k order, then ours.
           // First contributing CTA = the one whose span contains the tile's first unit.
@@ -472,13 +498,47 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             }
           }
           named_bar_sync(1, 128);
+          // This is the CTA's LAST segment (only the head tile of a span can have been started by others), all its
+          // MMAs have completed and the producer has nothing left to load: the weight ring is idle.  Fetch every
+          // contributor's [BC][128] fp32 partial into it with ONE batch of bulk copies -- a single L2 round trip
+          // instead of one per 16-column chunk per pair of contributors (at B = 96 the chunked loads cost ~30 us).
+          if ((int)blockIdx.x - c_first <= FIX_SLOTS) {
+            in_smem = true;
+            if (et == 0) {
+              asm volatile("fence.proxy.async;" ::: "memory");     // partials were written through the generic proxy
+              const int nc = (int)blockIdx.x - c_first;
+              mbar_expect_tx(fix_bar, (uint32_t)nc * PART_BYTES);
+              for (int j = 0; j < nc; ++j)
+                bulk_load(smem + (size_t)j * PART_BYTES, p.partials + (size_t)(c_first + j) * BC * 128, PART_BYTES, fix_bar);
+            }
+            mbar_wait(fix_bar, 0);
+            if (et == 0) sk_stamp(p, 10);              // contributors' partials are in shared memory
+          }
         }
         const float bv = (p.bias && n_ok) ? __bfloat162float(p.bias[n]) : 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < BC; c0 += CC) {
           float v[CC];
+          uint32_t rr[CC];
+#pragma unroll
+          for (int i = 0; i < CC; ++i) rr[i] = rr_next[i];
+          if (use_res && c0 + CC < BC) load_res(c0 + CC, rr_next);
           load_chunk(c0, v);
-          if (c_first < (int)blockIdx.x) {
+          if (p.trace && et == 0 && seg == n_segs - 1) sk_stamp(p, 40 + c0 / CC);
+          if (in_smem) {
+            // same summation order as the register path below: contributors in k order, own accumulator last
+            float sum[CC];
+#pragma unroll
+            for (int i = 0; i < CC; ++i) sum[i] = 0.f;
+            const int nc = (int)blockIdx.x - c_first;
+            for (int j = 0; j < nc; ++j) {
+              const float *slot = reinterpret_cast<const float *>(smem + (size_t)j * PART_BYTES);
+#pragma unroll
+              for (int i = 0; i < CC; ++i) sum[i] += slot[(c0 + i) * 128 + et];
+            }
+#pragma unroll
+            for (int i = 0; i < CC; ++i) v[i] = sum[i] + v[i];
+          } else if (c_first < (int)blockIdx.x) {
             float sum[CC];
 #pragma unroll
             for (int i = 0; i < CC; ++i) sum[i] = 0.f;
@@ -503,34 +563,47 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             for (int i = 0; i < CC; ++i) v[i] = sum[i] + v[i];
           }
           // ───── epilogue math on the complete accumulator (HF rounding points) ─────
+          // All CC columns are computed unconditionally (columns >= B hold zeros) and only the stores are predicated:
+          // with the arithmetic inside `if (column < B)` every column became its own basic block and the 16 columns of
+          // a chunk ran as 16 serial latency chains (1.6 us per chunk at B = 96).
+          float o[CC];
 #pragma unroll
-          for (int i = 0; i < CC; ++i) v[i] = bf16_round(v[i] + bv);
+          for (int i = 0; i < CC; ++i) o[i] = bf16_round(v[i] + bv);
           if (p.epilogue == OCRB_EPI_SWIGLU) {
             // tile rows 0..63 = gate, 64..127 = up of output columns tile*64 + j
             if (et >= 64) {
 #pragma unroll
-              for (int i = 0; i < CC; ++i) s_up[(et - 64) * CC + i] = v[i];
+              for (int i = 0; i < CC; ++i) s_up[(et - 64) * CC + i] = o[i];
             }
             named_bar_sync(1, 128);
-            if (et < 64 && n_ok) {
-              const int oc = tile * 64 + et;
+            if (et < 64) {
+#pragma unroll
+              for (int i = 0; i < CC; ++i) o[i] = sk_silu(o[i]) * s_up[et * CC + i];
+              if (n_ok) {
+                bf16 *dcol = p.D + (size_t)c0 * p.ldd + (tile * 64 + et);
+#pragma unroll
+                for (int i = 0; i < CC; ++i)
+                  if (c0 + i < p.B) dcol[(size_t)i * p.ldd] = __float2bfloat16_rn(o[i]);
+              }
+            }
+            named_bar_sync(1, 128);
+          } else {
+            if (p.epilogue == OCRB_EPI_RESIDUAL) {
+#pragma unroll
+              for (int i = 0; i < CC; ++i) o[i] += __uint_as_float(rr[i] << 16);
+            } else if (p.epilogue == OCRB_EPI_GELU) {
+#pragma unroll
+              for (int i = 0; i < CC; ++i) o[i] = sk_gelu(o[i]);
+            }
+            if (n_ok) {
+              bf16 *dcol = p.D + (size_t)c0 * p.ldd + n;
 #pragma unroll
               for (int i = 0; i < CC; ++i)
-                if (c0 + i < p.B) p.D[(size_t)(c0 + i) * p.ldd + oc] = __float2bfloat16_rn(sk_silu(v[i]) * s_up[et * CC + i]);
-            }
-            named_bar_sync(1, 128);
-          } else if (n_ok) {
-#pragma unroll
-            for (int i = 0; i < CC; ++i) {
-              if (c0 + i < p.B) {
-                float o = v[i];
-                if (p.epilogue == OCRB_EPI_RESIDUAL) o += __bfloat162float(p.residual[(size_t)(c0 + i) * p.ldr + n]);
-                else if (p.epilogue == OCRB_EPI_GELU) o = sk_gelu(o);
-                p.D[(size_t)(c0 + i) * p.ldd + n] = __float2bfloat16_rn(o);
-              }
+                if (c0 + i < p.B) dcol[(size_t)i * p.ldd] = __float2bfloat16_rn(o[i]);
             }
           }
         }
+        if (et == 0 && seg == n_segs - 1) sk_stamp(p, 11);   // epilogue of the last segment stored
         if (c_first < (int)blockIdx.x) {
           named_bar_sync(1, 128);                    // every thread is done reading the partials
           for (int c = c_first + et; c < (int)blockIdx.x; c += 128) p.flags[c] = 0;   // consumed: ready for the next launch
@@ -552,7 +625,7 @@ template <int BP, int BC>
 static int launch_skinny(const CUtensorMap &mw, const CUtensorMap &mx, const SkinnyParams &p, int grid, cudaStream_t st) {
   constexpr int ST = (BP > 64) ? 6 : ((BP >= 64) ? 4 : SK_STAGES);
   constexpr int CC = (BC < 16) ? BC : 16;
-  constexpr size_t smem = (size_t)ST * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 256 /*barriers*/ +
+  constexpr size_t smem = (size_t)ST * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 320 /*barriers*/ +
                           64 * CC * sizeof(float) + 64;
   static bool attr_set = false;
   if (!attr_set) {

@@ -173,7 +173,7 @@ def transcribe_folder(input_dir, output_dir=None, ground_truth_dir=None, *, page
         out = []
         for img in batch_images:
             out.append(fn(img, output_dir, match_ground_truth(img.stem, ground_truth_dir), **page_kwargs))
-            tools.forget(str(img))
+            tools.forget(str(img), delete_files=True)
         return out
 
     try:

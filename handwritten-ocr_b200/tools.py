@@ -52,6 +52,7 @@ _options = {
     "seed": 0,
     "force_greedy": False,      # decode greedily even if the checkpoint's generation_config.json asks for sampling
     "cache_pages": 64,          # originals whose preprocessed variants / texts stay cached (LRU)
+    "io_threads": 8,            # host threads decoding pages / writing temp files in prime() (folder mode)
     "delete_evicted_files": True,   # remove the temp files of an evicted page (the reference leaks them: tools.py:670)
 }
 # Cache of preprocessed pages and their transcriptions, keyed by the ORIGINAL image and guarded by the file's
@@ -76,13 +77,13 @@ def _signature(path: str):
     return (st.st_mtime_ns, st.st_size)
 
 
-def _drop_page(original: str) -> None:
+def _drop_page(original: str, delete_files: bool = False) -> None:
     page = _pages.pop(original, None)
     if page is None:
         return
     for path, _ in page.variants.values():
         _processed.pop(path, None)
-        if _options["delete_evicted_files"]:
+        if delete_files:
             try:
                 os.unlink(path)
             except OSError:
@@ -95,14 +96,14 @@ def _page_for(original: str, create: bool = True):
     sig = _signature(original)
     page = _pages.get(original)
     if page is not None and page.sig != sig:
-        _drop_page(original)
+        _drop_page(original, _options["delete_evicted_files"])
         page = None
     if page is None:
         if not create:
             return None
         page = _pages[original] = _Page(sig)
         while len(_pages) > max(1, int(_options["cache_pages"])):
-            _drop_page(next(iter(_pages)))
+            _drop_page(next(iter(_pages)), _options["delete_evicted_files"])
     else:
         _pages.move_to_end(original)
     return page
@@ -133,15 +134,24 @@ def _open_array(image_path: str) -> np.ndarray:
     return arr
 
 
-def _save(arr: np.ndarray, image_path: str, label: str) -> str:
+def _temp_name(image_path: str, label: str) -> str:
     suffix = Path(image_path).suffix or ".png"
-    tmp = tempfile.NamedTemporaryFile(suffix=suffix, delete=False, prefix=f"ocr_{label}_")
+    tmp = tempfile.NamedTemporaryFile(suffix=suffix, delete=False, prefix=f"ocr_{label}_")      # tools.py:670
     tmp.close()
+    return tmp.name
+
+
+def _write(arr: np.ndarray, path: str) -> None:
     # lossless either way; a stored (level 0) PNG instead of Pillow's default level 6 only makes the temp file larger
     # and the save ~30x faster (the file exists for callers that open it; run_ocr reads the cached page)
-    kw = {"compress_level": 0} if suffix.lower() == ".png" else {}
-    Image.fromarray(arr).save(tmp.name, **kw)
-    return tmp.name
+    kw = {"compress_level": 0} if Path(path).suffix.lower() == ".png" else {}
+    Image.fromarray(arr).save(path, **kw)
+
+
+def _save(arr: np.ndarray, image_path: str, label: str) -> str:
+    path = _temp_name(image_path, label)
+    _write(arr, path)
+    return path
 
 
 def _wanted_strategies(steps) -> list:
@@ -154,10 +164,11 @@ def _wanted_strategies(steps) -> list:
     return wanted
 
 
-def _preprocess_page(image_path: str, wanted: list, required_label: str | None, decoded=None) -> "_Page":
+def _preprocess_page(image_path: str, wanted: list, required_label: str | None, decoded=None, pool=None) -> "_Page":
     """Apply every strategy of `wanted` that the cache does not hold yet.  A failure in a SPECULATIVE strategy
     (one the caller did not ask for) is reported and skipped: the reference would never have run it here.
-    `decoded`: the already decoded page array (folder mode decodes the next batch on a host thread)."""
+    `decoded`: the already decoded page array (folder mode decodes the next batch on a host thread); `pool`: a thread
+    pool the temp files are written on (they are complete when the pool is shut down, i.e. before prime() returns)."""
     page = _page_for(image_path)
     todo = [s for s in wanted if _label(s) not in page.variants]
     if not todo:
@@ -167,7 +178,11 @@ def _preprocess_page(image_path: str, wanted: list, required_label: str | None, 
         lab = _label(s)
         try:
             y = preprocess.apply_strategy(x, s)
-            path = _save(y[0].cpu().numpy(), image_path, lab)
+            if pool is None:
+                path = _save(y[0].cpu().numpy(), image_path, lab)
+            else:
+                path = _temp_name(image_path, lab)
+                pool.submit(_write, y[0].cpu().numpy(), path)
         except Exception as e:
             if lab == required_label:
                 raise
@@ -309,8 +324,18 @@ def prime(image_paths, strategies=None, decoded: dict | None = None) -> None:
         raise ValueError(f"prime(): {len(paths)} pages exceed cache_pages={_options['cache_pages']}")
     import contextlib
     import io
-    for p in paths:
-        _preprocess_page(p, strategies, None, decoded.get(p) if decoded else None)
+    from concurrent.futures import ThreadPoolExecutor
+    # host pipeline: decode the image files and write the temp files on threads (PIL releases the GIL in both), the GPU
+    # preprocessing of page i runs while pages i+1.. are still being decoded and page i-1's temp files are being written
+    decoded = dict(decoded or {})
+    with ThreadPoolExecutor(max_workers=int(_options["io_threads"])) as pool:
+        arrays = {p: pool.submit(_open_array, p) for p in paths
+                  if p not in decoded and any(_label(s) not in (_pages.get(p).variants if p in _pages else {}) for s in strategies)}
+        for p in paths:
+            arr = decoded.get(p)
+            if arr is None and p in arrays:
+                arr = arrays.pop(p).result()
+            _preprocess_page(p, strategies, None, arr, pool)
     with contextlib.redirect_stdout(io.StringIO()):
         _read_pending(engine, paths, config.OCR_PROMPT, int(config.OCR_MAX_NEW_TOKENS))
 
@@ -345,10 +370,11 @@ def transcribe(image: str, strategy) -> str:
     return run_ocr(preprocess_image(image, strategy))
 
 
-def forget(image_path: str | None = None) -> None:
-    """Drop cached preprocessed pages / texts (all, or those of one original)."""
+def forget(image_path: str | None = None, delete_files: bool = False) -> None:
+    """Drop cached preprocessed pages / texts (all, or those of one original).  The temp files stay unless asked
+    (a path handed out earlier can still be given to run_ocr: it is then read from the file)."""
     for k in ([image_path] if image_path else list(_pages)):
-        _drop_page(k)
+        _drop_page(k, delete_files)
 
 
 # non-hot names the reference's callers import from tools (agents.py:12, transcribe.py:33,

@@ -86,7 +86,16 @@ def rmsnorm(x, w, out, eps=1e-6):
     return out
 
 
+FLASH_TC_MIN_LEN = int(os.environ.get("OCRB_FLASH_TC_MIN_LEN", "256"))   # shorter sequences (vision windows) use mma.sync
+
+
 def attention(q, k, v, out, cu, n_seq, max_len, n_q, n_kv, hd, causal):
+    if max_len >= FLASH_TC_MIN_LEN and hd in (80, 128):
+        # long sequences (vision full-attention blocks, prefill): tcgen05 + TMEM + TMA flash attention
+        _lib.call("ocrb_flash_attention_bf16", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                  v.stride(0), out.data_ptr(), out.stride(0), cu.data_ptr(), n_seq, q.shape[0], max_len, n_q, n_kv, hd,
+                  float(hd ** -0.5), int(causal), _sp())
+        return out
     _lib.call("ocrb_attention_varlen", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
               out.data_ptr(), out.stride(0), cu.data_ptr(), n_seq, max_len, n_q, n_kv, hd, float(hd ** -0.5),
               int(causal), _sp())
@@ -395,13 +404,14 @@ def text_rope_tables(cfg: VLMConfig, pos3: torch.Tensor):
 
 
 class PagedKV:
-    """Paged KV cache for all layers: k/v [layers, n_pages, page, n_kv, hd] bf16 + a free list."""
+    """Paged KV cache for all layers: k/v [layers, n_pages, n_kv, page, hd] bf16 (the 16 tokens of a (page, kv head) are
+    one contiguous 4 KiB block: one TMA box per attention tile) + a free list."""
 
     def __init__(self, cfg: VLMConfig, n_pages: int, page_size: int, device):
         t = cfg.text
         self.page = page_size
         self.n_pages = n_pages
-        self.k = torch.zeros((t.layers, n_pages, page_size, t.kv_heads, t.head_dim), dtype=BF, device=device)
+        self.k = torch.zeros((t.layers, n_pages, t.kv_heads, page_size, t.head_dim), dtype=BF, device=device)
         self.v = torch.zeros_like(self.k)
         self.free = list(range(n_pages - 1, -1, -1))
 
@@ -499,7 +509,7 @@ class Decoder:
                 sl = slice(b0, min(B, b0 + SKINNY_MAX_ROWS))
                 skinny(st.x[sl], lay["qkv_w"], st.qkv[sl], bias=lay["qkv_b"], norm_w=lay["ln1"], eps=t.rms_eps)
             _lib.call("ocrb_decode_attention", st.qkv.data_ptr(), st.qkv.stride(0), self.kv.k[li].data_ptr(),
-                      self.kv.v[li].data_ptr(), st.block_table.data_ptr(), max_pages, st.ctx_len.data_ptr(), B,
+                      self.kv.v[li].data_ptr(), self.kv.n_pages, st.block_table.data_ptr(), max_pages, st.ctx_len.data_ptr(), B,
                       self.kv.page, nq, nkv, hd, st.cos.data_ptr(), st.sin.data_ptr(), float(hd ** -0.5),
                       st.att.data_ptr(), st.att.stride(0), st.split_ws.data_ptr(), st.n_splits, _sp())
             for b0 in range(0, B, SKINNY_MAX_ROWS):

@@ -179,7 +179,8 @@ int ocrb_attention_varlen(const void *q, int64_t ldq, const void *k, int64_t ldk
                           int32_t n_seq, int32_t max_seqlen, int32_t n_q, int32_t n_kv, int32_t hd,
                           float scale, int32_t causal, void *stream);
 
-/* Paged KV cache: pages of `page_size` tokens; k_cache/v_cache: bf16 [n_pages, page_size, n_kv, hd].
+/* Paged KV cache: pages of `page_size` tokens; k_cache/v_cache: bf16 [n_pages, n_kv, page_size, hd] (the tokens of a
+ * (page, kv head) are one contiguous block, so a 16-key attention tile is a single 4 KiB TMA box).
  * block_table: int32[B, max_pages_per_seq].  ctx_len: int32[B] on the device (tokens already cached). */
 
 /* Scatter T tokens of k/v (prefill) into the paged cache: token t of sequence s goes to
@@ -189,16 +190,26 @@ int ocrb_kv_write_prefill(const void *k, int64_t ldk, const void *v, int64_t ldv
                           const int32_t *cu_seqlens, int32_t n_seq, int32_t T, int32_t page_size,
                           int32_t n_kv, int32_t hd, void *stream);
 
+/* Flash attention on tcgen05 / TMEM / TMA for long sequences (vision full-attention blocks: hd 80, non-causal;
+ * decoder prefill: hd 128, causal, GQA).  Same tensors as ocrb_attention_varlen plus total_tokens (rows of q/k/v/out);
+ * pointers 16-byte aligned, strides multiples of 8.  Replaces the attention inside HF's
+ * Qwen2_5_VLVisionAttention / Qwen2_5_VLAttention forward (modeling_qwen2_5_vl.py:231-283,718-760). */
+int ocrb_flash_attention_bf16(const void *q, int64_t ldq, const void *k, int64_t ldk, const void *v,
+                              int64_t ldv, void *out, int64_t ldo, const int32_t *cu_seqlens,
+                              int32_t n_seq, int32_t total_tokens, int32_t max_seqlen, int32_t n_q,
+                              int32_t n_kv, int32_t hd, float scale, int32_t causal, void *stream);
+
 /* One decode step of attention for B sequences: applies mRoPE (bf16) to q,k of the new token,
  * appends k,v at position ctx_len[b], attends over ctx_len[b]+1 tokens.  qkv: [B, (n_q+2*n_kv)*hd].
  * cos/sin: bf16 [B, hd] for this step.  out: [B, n_q*hd].  hd = 64 or 128, n_q / n_kv <= 16, page_size % 16 == 0.
- * Split-KV: every sequence's max_pages*page_size key positions are cut into n_splits ranges, one CTA per
+ * k_cache / v_cache: one layer's cache, bf16 [n_cache_pages, n_kv, page_size, hd] (read through TMA).
+ * Split-KV: every sequence's max_pages*page_size key positions are cut into n_splits ranges, one work item per
  * (range, kv head, sequence); split_ws: fp32 [B * n_q * n_splits * (hd + 2)] partials (max, sum, o[hd]). */
 int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cache, void *v_cache,
-                          const int32_t *block_table, int32_t max_pages, const int32_t *ctx_len,
-                          int32_t B, int32_t page_size, int32_t n_q, int32_t n_kv, int32_t hd,
-                          const void *cos, const void *sin, float scale, void *out, int64_t ldo,
-                          float *split_ws, int32_t n_splits, void *stream);
+                          int32_t n_cache_pages, const int32_t *block_table, int32_t max_pages,
+                          const int32_t *ctx_len, int32_t B, int32_t page_size, int32_t n_q, int32_t n_kv,
+                          int32_t hd, const void *cos, const void *sin, float scale, void *out,
+                          int64_t ldo, float *split_ws, int32_t n_splits, void *stream);
 
 /* Greedy pick (HF generation/utils.py:2793 argmax over fp32 logits, lowest index on ties) +
  * sequence bookkeeping for one decode step, all on the device:

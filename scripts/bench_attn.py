@@ -13,8 +13,8 @@ for B, ctx in [(b, c) for b, c in CASES for _ in KEYS]:
     max_pages = max_ctx // page
     n_pages = B * max_pages
     layers = 8   # rotate over several layers' caches so L2 does not hold everything
-    kc = [torch.randn(n_pages, page, nkv, hd, device="cuda").to(BF) for _ in range(layers)]
-    vc = [torch.randn(n_pages, page, nkv, hd, device="cuda").to(BF) for _ in range(layers)]
+    kc = [torch.randn(n_pages, nkv, page, hd, device="cuda").to(BF) for _ in range(layers)]
+    vc = [torch.randn(n_pages, nkv, page, hd, device="cuda").to(BF) for _ in range(layers)]
     bt = torch.arange(n_pages, device="cuda", dtype=torch.int32).view(B, max_pages).contiguous()
     qkv = torch.randn(B, (nq + 2 * nkv) * hd, device="cuda").to(BF)
     cos = torch.randn(B, hd, device="cuda").to(BF); sin = torch.randn(B, hd, device="cuda").to(BF)
@@ -27,7 +27,7 @@ for B, ctx in [(b, c) for b, c in CASES for _ in KEYS]:
     sp = lambda: torch.cuda.current_stream().cuda_stream
     def run(i):
         _lib.call("ocrb_decode_attention", qkv.data_ptr(), qkv.stride(0), kc[i % layers].data_ptr(), vc[i % layers].data_ptr(),
-                  bt.data_ptr(), max_pages, ctx_d.data_ptr(), B, page, nq, nkv, hd, cos.data_ptr(), sin.data_ptr(), hd ** -0.5,
+                  n_pages, bt.data_ptr(), max_pages, ctx_d.data_ptr(), B, page, nq, nkv, hd, cos.data_ptr(), sin.data_ptr(), hd ** -0.5,
                   out.data_ptr(), nq * hd, ws.data_ptr(), n_splits, sp())
     for i in range(3): run(i)
     torch.cuda.synchronize()

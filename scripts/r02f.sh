@@ -1,0 +1,20 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_dense.py -q -m gpu > gpurun_out/r02f_dense.log 2>&1
+echo "dense exit=$?"; tail -n 6 gpurun_out/r02f_dense.log
+timeout 300 python scripts/trace_skinny.py 96 qkv,o > gpurun_out/r02f_trace96.log 2>&1; echo "trace exit=$?"; grep "==\|owner\|period\|wait_ret\|published\|fixup_done" gpurun_out/r02f_trace96.log
+timeout 600 python scripts/bench_skinny.py 3,24,96 > gpurun_out/r02f_skinny.log 2>&1; echo "skinny exit=$?"; cat gpurun_out/r02f_skinny.log
+timeout 600 python scripts/bench_gemm.py > gpurun_out/r02f_gemm.log 2>&1; echo "gemm exit=$?"; cat gpurun_out/r02f_gemm.log
+timeout 900 python -m pytest tests/test_gpu_vlm.py tests/test_gpu_read_path.py tests/test_gpu_folder.py tests/test_gpu_text_image.py -x -q -m gpu > gpurun_out/r02f_vlm.log 2>&1
+echo "vlm exit=$?"; tail -n 15 gpurun_out/r02f_vlm.log
+for P in 1 32; do
+timeout 600 python bench.py --pages $P --steps 2 --warmup 1 --no-cpu --no-extra > gpurun_out/r02f_p$P.json 2> gpurun_out/r02f_p$P.err
+echo "P=$P exit=$?"; tail -c 300 gpurun_out/r02f_p$P.err; python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/r02f_p$P.json").read().strip().splitlines()[-1])
+    print({k:d[k] for k in ("value","ms_per_step","decode_tok_per_s","phase_ms_per_step")}, d["roofline"]["frac"], d["roofline"]["decode_step_ms"], d["roofline_tensor"]["frac"], d["roofline_tensor"]["vision"], d["roofline_tensor"]["prefill"], d["e2e"]["value"], d["e2e"]["seconds"])
+except Exception as e:
+    print("no json", e)
+PY
+done

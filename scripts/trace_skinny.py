@@ -7,11 +7,14 @@ from handwritten_ocr_b200 import _lib, vlm
 BF = torch.bfloat16; dev = torch.device("cuda")
 L = _lib.load()
 L.ocrb_skinny_set_trace.argtypes = [ctypes.c_void_p]; L.ocrb_skinny_set_trace.restype = None
-names = ["start", "setup_done", "wait_ret", "w_first", "x_first", "seg0_acc", "last_acc", "published", "fixup_done", "end"]
-for name, N, K, epi, norm in [("o_proj+res", 3584, 3584, 1, False)]:
+names = ["start", "setup_done", "wait_ret", "w_first", "x_first", "seg0_acc", "last_acc", "published", "fixup_done", "end", "fix_in_smem", "epi_stored"]
+BATCH = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+SHAPES = {"o": ("o_proj+res", 3584, 3584, 1, False), "qkv": ("qkv+norm", 4608, 3584, 0, True), "gu": ("gate_up", 37888, 3584, 2, True),
+          "down": ("down+res", 3584, 18944, 1, False)}
+for name, N, K, epi, norm in [SHAPES[k] for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["o"])]:
     Ws = [(torch.randn(N, K, device=dev) * K ** -0.5).to(BF) for _ in range(12)]
-    nw = torch.ones(K, device=dev, dtype=BF); B = 3
-    X = torch.randn(B, K, device=dev).to(BF); D = torch.empty(B, N, device=dev, dtype=BF); R = torch.randn(B, N, device=dev).to(BF)
+    nw = torch.ones(K, device=dev, dtype=BF); B = BATCH
+    X = torch.randn(B, K, device=dev).to(BF); D = torch.empty(B, N // 2 if epi == 2 else N, device=dev, dtype=BF); R = torch.randn(B, N, device=dev).to(BF)
     traces = [torch.zeros(296 * 64, dtype=torch.int64, device=dev) for _ in range(12)]
     def run(i):
         L.ocrb_skinny_set_trace(traces[i % 12].data_ptr())
@@ -32,7 +35,7 @@ for name, N, K, epi, norm in [("o_proj+res", 3584, 3584, 1, False)]:
         cur[t[i] == 0] = np.nan
         rows.append(cur)
     cur = np.stack(rows)   # [kernels, ctas, stamps]
-    print(f"== {name} N={N} K={K}: ns relative to the end of the previous kernel in the chain (median over kernels; min / median / max over CTAs)")
+    print(f"== {name} N={N} K={K} B={B}: ns relative to the end of the previous kernel in the chain (median over kernels; min / median / max over CTAs)")
     for s, nm in enumerate(names):
         v = cur[:, :, s]
         if np.all(np.isnan(v)): continue
@@ -41,4 +44,7 @@ for name, N, K, epi, norm in [("o_proj+res", 3584, 3584, 1, False)]:
     k = cur[4]          # one kernel of the chain, CTA 5 and CTA 100: per-unit (w_ready, x_ready) in the first segment
     for cta in (5, 100):
         print(f"   CTA {cta} units (w_ready, x_ready):", " ".join(f"({k[cta, 16 + 2 * i]:.0f},{k[cta, 17 + 2 * i]:.0f})" for i in range(12) if not np.isnan(k[cta, 16 + 2 * i])))
-        print(f"   CTA {cta} producer arrive:", " ".join(f"{k[cta, 40 + i]:.0f}" for i in range(12) if not np.isnan(k[cta, 40 + i])))
+        print(f"   CTA {cta} epilogue chunk starts:", " ".join(f"{k[cta, 40 + i]:.0f}" for i in range(12) if not np.isnan(k[cta, 40 + i])))
+    own = [c for c in range(148) if not np.isnan(k[c, 8])][:3]
+    for cta in own:
+        print(f"   owner CTA {cta}: last_acc {k[cta, 6]:.0f} fix_in_smem {k[cta, 10]:.0f} chunk starts", " ".join(f"{k[cta, 40 + i]:.0f}" for i in range(12) if not np.isnan(k[cta, 40 + i])), f"epi_stored {k[cta, 11]:.0f} fixup_done {k[cta, 8]:.0f} end {k[cta, 9]:.0f}")

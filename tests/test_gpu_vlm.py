@@ -121,19 +121,37 @@ def test_batch_invariance_and_graph(ctx):
 
 
 def test_eos_stops_and_pads(ctx):
-    """Force EOS: a huge lm_head row for the eos id makes every sequence stop at once."""
-    cfg, hf, eng = ctx["default"]
+    """EOS semantics of HF's greedy loop (generation/utils.py:2743-2806): a sequence stops at its first <|im_end|>, a
+    finished row of a batch is padded with pad = eos while the others continue, the batch ends when every row is done.
+    The EOS is forced with a wide margin: its lm_head row becomes 4x the row of the token HF picks at step k, so at
+    step k the EOS logit is 4x the winning logit (rounding cannot flip that) -- our tokens must EQUAL HF's."""
+    from handwritten_ocr_b200.vlm_config import EOS
+    cfg, hf, eng = ctx["peaked"]
     pp = ctx["pp"]
-    row = eng.w.lm_head[151645].clone()
+    pages = ctx["pages"][:2]
+    inputs = [hf_inputs(eng, pp, pg)[0] for pg in pages]
+    n_new = 16
+    with torch.no_grad():
+        free = [hf.generate(**inp, max_new_tokens=n_new, do_sample=False)[0, inp["input_ids"].shape[1]:].tolist() for inp in inputs]
+    k = 6
+    tok_k = free[0][k]
+    assert tok_k != EOS
+    row_ours, row_hf = eng.w.lm_head[EOS].clone(), hf.lm_head.weight.data[EOS].clone()
     try:
-        eng.w.lm_head[151645] = eng.w.final_norm * 0 + 1.0
-        # eos logit = sum(normed hidden) may not dominate for every state; only require HF-equal behaviour
-        hf.lm_head.weight.data[151645] = eng.w.lm_head[151645]
-        inp, _ = hf_inputs(eng, pp, ctx["pages"][0])
+        eng.w.lm_head[EOS] = 4.0 * eng.w.lm_head[tok_k]
+        hf.lm_head.weight.data[EOS] = 4.0 * hf.lm_head.weight.data[tok_k]
         with torch.no_grad():
-            want = hf.generate(**inp, max_new_tokens=16, do_sample=False)[0, inp["input_ids"].shape[1]:].tolist()
-        got = eng.read_batch(pp.to_device(ctx["pages"][0]), max_new_tokens=16)[0]
-        assert got[: len(want)] == want or got == want[: len(got)]
+            want = [hf.generate(**inp, max_new_tokens=n_new, do_sample=False)[0, inp["input_ids"].shape[1]:].tolist() for inp in inputs]
+        assert want[0][-1] == EOS and len(want[0]) <= k + 1, "the forced EOS must end page 0 by step k"
+        # one page alone: exactly HF's tokens, EOS included, nothing after it
+        got0 = eng.read_batch(pp.to_device(pages[0]), max_new_tokens=n_new)[0]
+        assert got0 == want[0]
+        # both pages in one batch: each row = HF's tokens, then eos padding up to the longest row of the batch
+        got = eng.read_batch(pp.to_device(pages), max_new_tokens=n_new)
+        longest = max(len(w_) for w_ in want)
+        for g_, w_ in zip(got, want):
+            assert len(g_) == longest
+            assert g_[: len(w_)] == w_ and all(t_ == EOS for t_ in g_[len(w_):])
     finally:
-        eng.w.lm_head[151645] = row
-        hf.lm_head.weight.data[151645] = row
+        eng.w.lm_head[EOS] = row_ours
+        hf.lm_head.weight.data[EOS] = row_hf
