@@ -18,6 +18,13 @@ class OcrbError(RuntimeError):
 
 _lib = None
 
+class ChainLinear(ctypes.Structure):
+    """`ocrb_chain_linear` of include/ocrb200.h: one linear of an ocrb_skinny_chain_bf16 call."""
+    _fields_ = [("X", c_void_p), ("ldx", c_int64), ("W", c_void_p), ("ldw", c_int64), ("D", c_void_p), ("ldd", c_int64),
+                ("N", c_int32), ("K", c_int32), ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int64),
+                ("epilogue", c_int32), ("eps", c_float), ("norm_w", c_void_p)]
+
+
 _P = c_void_p
 _I = c_int32
 _L = c_int64
@@ -42,6 +49,7 @@ _SIGS = {
     "ocrb_normalize_patchify": [_P, _P, _I, _I, _I, _I, _P, _I, _P],
     "ocrb_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P],
     "ocrb_skinny_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P, _F, _P, _P],
+    "ocrb_skinny_chain_bf16": [_P, _I, _I, _P, _P],
     "ocrb_rmsnorm_bf16": [_P, _L, _P, _P, _L, _I, _I, _F, _P],
     "ocrb_rope_vision": [_P, _I, _I, _I, _P, _P, _P],
     "ocrb_rope_text": [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _P],
@@ -60,7 +68,7 @@ _SIGS = {
 }
 
 EXPORTS = ["ocrb_version", "ocrb_last_error", "ocrb_launch_count", "ocrb_launch_count_reset",
-           "ocrb_skinny_workspace_bytes", "ocrb_inpaint_workspace_bytes"] + list(_SIGS)
+           "ocrb_skinny_workspace_bytes", "ocrb_chain_workspace_bytes", "ocrb_inpaint_workspace_bytes"] + list(_SIGS)
 
 
 def load():
@@ -78,6 +86,7 @@ def load():
     L.ocrb_launch_count.restype = c_uint64
     L.ocrb_launch_count_reset.restype = None
     L.ocrb_skinny_workspace_bytes.restype = c_int64
+    L.ocrb_chain_workspace_bytes.restype = c_int64
     L.ocrb_inpaint_workspace_bytes.restype = c_int64
     L.ocrb_inpaint_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
     for name, args in _SIGS.items():

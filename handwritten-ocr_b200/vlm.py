@@ -10,6 +10,7 @@ Reference semantics: HF transformers modeling_qwen2_5_vl.py (vision tower :345-5
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
 
@@ -65,6 +66,41 @@ def skinny(X, W, out, *, bias=None, residual=None, epilogue=EPI_NONE, norm_w=Non
               residual.stride(0) if residual is not None else 0, epilogue, _lib.ptr(norm_w), float(eps),
               skinny_workspace(X.device).data_ptr(), _sp())
     return out
+
+
+_CHAIN_WS = {}
+CHAIN_MAX_B = int(os.environ.get("OCRB_CHAIN_MAX_B", "128"))     # 0: one launch per linear (skinny / cluster kernels)
+
+
+CHAIN_TRACE = None        # debugging: a list collects one timestamp buffer per chain launch
+
+
+def chain_workspace(device) -> torch.Tensor:
+    """Per-device workspace of ocrb_skinny_chain_bf16 (zeroed once; the kernel returns its counters to zero)."""
+    key = torch.device(device).index or 0
+    ws = _CHAIN_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_lib.load().ocrb_chain_workspace_bytes()), dtype=torch.uint8, device=device)
+        _CHAIN_WS[key] = ws
+    return ws
+
+
+def chain_linear(X, W, out, *, bias=None, residual=None, epilogue=EPI_NONE, norm_w=None, eps=1e-6):
+    """One linear of a `skinny_chain` call: same arguments and meaning as `skinny`."""
+    return _lib.ChainLinear(X.data_ptr(), X.stride(0), W.data_ptr(), W.stride(0), out.data_ptr(), out.stride(0),
+                            W.shape[0], X.shape[1], _lib.ptr(bias), _lib.ptr(residual),
+                            residual.stride(0) if residual is not None else 0, epilogue, float(eps), _lib.ptr(norm_w))
+
+
+def skinny_chain(linears, B: int, device):
+    """Dependent skinny linears (each may read what the earlier ones wrote) in ONE persistent launch: the weight stream
+    of the whole chain keeps HBM busy across the dependencies (csrc/chain.cu)."""
+    arr = (_lib.ChainLinear * len(linears))(*linears)
+    if CHAIN_TRACE is not None:       # scripts/trace_chain.py: one [grid][64] globaltimer buffer per launch
+        buf = torch.zeros(296 * 64, dtype=torch.int64, device=device)
+        CHAIN_TRACE.append(buf)
+        _lib.load().ocrb_chain_set_trace(ctypes.c_void_p(buf.data_ptr()))
+    _lib.call("ocrb_skinny_chain_bf16", ctypes.addressof(arr), len(linears), B, chain_workspace(device).data_ptr(), _sp())
 
 
 def linear_small_or_big(X, W, out, **kw):
@@ -496,10 +532,45 @@ class Decoder:
         return out
 
     # ---- one decode step for B sequences (all state on the device) ----
+    def _step_chained(self, st: "DecodeState"):
+        """The step as 1 + layers persistent chain launches: [qkv 0] attn [o, gate/up, down, qkv 1] attn ... [o, gate/up,
+        down, lm_head] argmax.  The RMSNorms run inside the chains; only the attention sits between two launches."""
+        t = self.cfg.text
+        nq, nkv, hd = t.heads, t.kv_heads, t.head_dim
+        B, dev, eps = st.B, st.x.device, t.rms_eps
+        L = self.w.layers
+        _lib.call("ocrb_embed_gather", self.w.embed.data_ptr(), st.next_ids.data_ptr(), st.x.data_ptr(), B, t.hidden, _sp())
+        _lib.call("ocrb_decode_rope_table", st.ctx_len.data_ptr(), st.rope_delta.data_ptr(), st.inv_freq.data_ptr(), B, hd,
+                  st.cos.data_ptr(), st.sin.data_ptr(), _sp())
+        max_pages = st.block_table.shape[1]
+
+        def qkv_of(lay):
+            return chain_linear(st.x, lay["qkv_w"], st.qkv, bias=lay["qkv_b"], norm_w=lay["ln1"], eps=eps)
+
+        skinny_chain([qkv_of(L[0])], B, dev)
+        for li, lay in enumerate(L):
+            _lib.call("ocrb_decode_attention", st.qkv.data_ptr(), st.qkv.stride(0), self.kv.k[li].data_ptr(),
+                      self.kv.v[li].data_ptr(), self.kv.n_pages, st.block_table.data_ptr(), max_pages, st.ctx_len.data_ptr(), B,
+                      self.kv.page, nq, nkv, hd, st.cos.data_ptr(), st.sin.data_ptr(), float(hd ** -0.5),
+                      st.att.data_ptr(), st.att.stride(0), st.split_ws.data_ptr(), st.n_splits, _sp())
+            lins = [chain_linear(st.att, lay["o_w"], st.x, residual=st.x, epilogue=EPI_RESIDUAL),
+                    chain_linear(st.x, lay["gu_w"], st.act, epilogue=EPI_SWIGLU, norm_w=lay["ln2"], eps=eps),
+                    chain_linear(st.act, lay["down_w"], st.x, residual=st.x, epilogue=EPI_RESIDUAL)]
+            if li + 1 < len(L):
+                lins.append(qkv_of(L[li + 1]))
+            else:
+                lins.append(chain_linear(st.x, self.w.lm_head, st.logits_local, norm_w=self.w.final_norm, eps=eps))
+            skinny_chain(lins, B, dev)
+        _lib.call("ocrb_argmax_step", st.logits.data_ptr(), st.logits.stride(0), B, t.vocab, EOS, EOS, st.max_new,
+                  st.out_tokens.data_ptr(), st.next_ids.data_ptr(), st.finished.data_ptr(), st.ctx_len.data_ptr(),
+                  st.step.data_ptr(), 1, _sp())
+
     def _step(self, st: "DecodeState"):
         t = self.cfg.text
         nq, nkv, hd = t.heads, t.kv_heads, t.head_dim
         B = st.B
+        if self.tp is None and B <= CHAIN_MAX_B and t.hidden <= 8192:
+            return self._step_chained(st)
         _lib.call("ocrb_embed_gather", self.w.embed.data_ptr(), st.next_ids.data_ptr(), st.x.data_ptr(), B, t.hidden, _sp())
         _lib.call("ocrb_decode_rope_table", st.ctx_len.data_ptr(), st.rope_delta.data_ptr(), st.inv_freq.data_ptr(), B, hd,
                   st.cos.data_ptr(), st.sin.data_ptr(), _sp())

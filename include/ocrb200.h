@@ -157,6 +157,29 @@ int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, int64_t ldw
                           int64_t ldr, int32_t epilogue, const void *norm_w, float eps, void *workspace,
                           void *stream);
 
+/* A chain of up to OCRB_CHAIN_MAX dependent skinny linears in ONE persistent launch (one decode step's
+ * o_proj -> [RMSNorm] gate/up+SwiGLU -> down_proj -> [RMSNorm] qkv of the next layer / lm_head; HF decoder layer
+ * modeling_qwen2_5_vl.py:839-879 inside the generation loop utils.py:2743-2806).  Linear g+1 may read what linear g
+ * (or any earlier one) wrote: the kernel orders them with device-side counters while the weight stream of the whole
+ * chain keeps HBM busy.  Each linear has the meaning of one ocrb_skinny_gemm_bf16 call with the same arguments and
+ * produces the same bits.  `residual` may equal `D` (in-place update).  norm_w != NULL: K <= 8192.
+ * workspace: ocrb_chain_workspace_bytes() bytes, ZERO-initialised once by the caller, then owned by this entry point
+ * (counters are returned to zero by every launch); not shared by launches that can run concurrently. */
+#define OCRB_CHAIN_MAX 5
+typedef struct ocrb_chain_linear {
+  const void *X; int64_t ldx;          /* [B, K] activations (row stride in elements) */
+  const void *W; int64_t ldw;          /* [N, K] weights */
+  void *D; int64_t ldd;                /* [B, N'] output */
+  int32_t N, K;
+  const void *bias;                    /* [N] or NULL */
+  const void *residual; int64_t ldr;   /* OCRB_EPI_RESIDUAL */
+  int32_t epilogue;
+  float eps;
+  const void *norm_w;                  /* [K] RMSNorm weight applied to X first, or NULL */
+} ocrb_chain_linear;
+int64_t ocrb_chain_workspace_bytes(void);
+int ocrb_skinny_chain_bf16(const ocrb_chain_linear *lin, int32_t n, int32_t B, void *workspace, void *stream);
+
 /* HF Qwen2_5_VLRMSNorm (modeling:66-71): y = w * bf16( x_f32 * rsqrt(mean(x^2)+eps) ) */
 int ocrb_rmsnorm_bf16(const void *x, int64_t ldx, const void *w, void *y, int64_t ldy, int32_t rows,
                       int32_t dim, float eps, void *stream);

@@ -209,6 +209,99 @@ def test_skinny_batch_invariance(L, skws):
     assert torch.equal(D_a, D_b)
 
 
+# ───────────── chain of dependent skinny linears in one persistent launch (csrc/chain.cu) ─────────────
+@pytest.fixture(scope="module")
+def chws(L):
+    return torch.zeros(int(L.load().ocrb_chain_workspace_bytes()), dtype=torch.uint8, device="cuda")
+
+
+def chain_call(L, ws, lins, B):
+    import ctypes
+    arr = (L.ChainLinear * len(lins))(*lins)
+    L.call("ocrb_skinny_chain_bf16", ctypes.addressof(arr), len(lins), B, ws.data_ptr(), sp())
+
+
+def chain_lin(L, X, W, D, bias=None, res=None, epi=0, norm_w=None, eps=1e-6):
+    return L.ChainLinear(X.data_ptr(), X.stride(0), W.data_ptr(), W.stride(0), D.data_ptr(), D.stride(0), W.shape[0],
+                         X.shape[1], L.ptr(bias), L.ptr(res), res.stride(0) if res is not None else 0, epi, eps, L.ptr(norm_w))
+
+
+def layer_tensors(B, H, I, Q, seed):
+    t = {"att": rnd(B, H, seed=seed), "x": rnd(B, H, seed=seed + 1),
+         "o_w": rnd(H, H, scale=H ** -0.5, seed=seed + 2), "ln2": (1 + 0.1 * rnd(H, seed=seed + 3).float()).to(BF),
+         "gu_w": pack_swiglu(rnd(I, H, scale=H ** -0.5, seed=seed + 4), rnd(I, H, scale=H ** -0.5, seed=seed + 5)),
+         "down_w": rnd(H, I, scale=I ** -0.5, seed=seed + 6), "ln1": (1 + 0.1 * rnd(H, seed=seed + 7).float()).to(BF),
+         "qkv_w": rnd(Q, H, scale=H ** -0.5, seed=seed + 8), "qkv_b": rnd(Q, seed=seed + 9)}
+    return t
+
+
+def run_layer_chain(L, ws, t, B, I, Q):
+    x = t["x"][:B].clone()
+    act = torch.full((B, I), float("nan"), device="cuda", dtype=BF)
+    qkv = torch.full((B, Q), float("nan"), device="cuda", dtype=BF)
+    att = t["att"][:B]
+    chain_call(L, ws, [chain_lin(L, att, t["o_w"], x, res=x, epi=1),
+                       chain_lin(L, x, t["gu_w"], act, epi=2, norm_w=t["ln2"]),
+                       chain_lin(L, act, t["down_w"], x, res=x, epi=1),
+                       chain_lin(L, x, t["qkv_w"], qkv, bias=t["qkv_b"], norm_w=t["ln1"])], B)
+    torch.cuda.synchronize()
+    return x, act, qkv
+
+
+@pytest.mark.parametrize("B", [1, 3, 8, 16, 24, 48, 64, 96, 128])
+@pytest.mark.parametrize("H,I,Q", [(3584, 18944, 4608), (1024, 2816, 1536)])
+def test_chain_layer_matches_reference(L, chws, B, H, I, Q):
+    """o_proj + residual -> RMSNorm -> gate/up + SwiGLU -> down_proj + residual -> RMSNorm -> qkv + bias in one launch."""
+    t = layer_tensors(B, H, I, Q, seed=100)
+    x, act, qkv = run_layer_chain(L, chws, t, B, I, Q)
+    # the first linear alone (a chain of one gives the bits it gives inside the longer chain): every later check then
+    # starts from the kernel's own activations and isolates one linear
+    x1 = t["x"][:B].clone()
+    chain_call(L, chws, [chain_lin(L, t["att"][:B], t["o_w"], x1, res=x1, epi=1)], B)
+    torch.cuda.synchronize()
+    lin_o = ref_linear(t["att"][:B], t["o_w"])
+    close_bf16(x1, (lin_o.float() + t["x"][:B].float()).to(BF), "chain o_proj + residual", mag=lin_o)
+    xn = hf_rmsnorm(x1, t["ln2"], 1e-6)
+    Wg = t["gu_w"].view(I // 64, 2, 64, H)[:, 0].reshape(I, H)
+    Wu = t["gu_w"].view(I // 64, 2, 64, H)[:, 1].reshape(I, H)
+    g, u = ref_linear(xn, Wg), ref_linear(xn, Wu)
+    close_bf16(act, torch.nn.functional.silu(g) * u, "chain norm + gate/up + swiglu", ulps=8.0, frac_exact=0.9,
+               mag=g.float().abs() * u.float().abs())
+    lin_d = ref_linear(act, t["down_w"])                       # from the kernel's own activations: isolates each linear
+    x2 = (lin_d.float() + x1.float()).to(BF)
+    close_bf16(x, x2, "chain down + residual (after o_proj + residual)", ulps=3.0, frac_exact=0.9, mag=lin_d)
+    qkv_ref = ref_linear(hf_rmsnorm(x, t["ln1"], 1e-6), t["qkv_w"], t["qkv_b"])
+    close_bf16(qkv, qkv_ref, "chain qkv", mag=qkv_ref)
+    ctr_at = 296 * 128 * 128 * 4
+    n_ctr = 5 * 296 + 48
+    assert int(chws[ctr_at:ctr_at + 4 * n_ctr].view(torch.int32).abs().sum()) == 0, "chain counters must return to zero"
+
+
+def test_chain_batch_invariance_and_determinism(L, chws):
+    H, I, Q = 3584, 18944, 4608
+    t = layer_tensors(128, H, I, Q, seed=200)
+    alone = [run_layer_chain(L, chws, {**t, "att": t["att"][b:b + 1], "x": t["x"][b:b + 1]}, 1, I, Q) for b in range(3)]
+    for Bb in (3, 16, 17, 64, 96, 128):
+        x, act, qkv = run_layer_chain(L, chws, t, Bb, I, Q)
+        x_b, act_b, qkv_b = run_layer_chain(L, chws, t, Bb, I, Q)
+        assert torch.equal(x, x_b) and torch.equal(act, act_b) and torch.equal(qkv, qkv_b), f"run-to-run difference at B={Bb}"
+        for b in range(3):
+            assert torch.equal(alone[b][0][0], x[b]) and torch.equal(alone[b][1][0], act[b]) and \
+                torch.equal(alone[b][2][0], qkv[b]), f"row {b} differs between B=1 and B={Bb}"
+
+
+def test_chain_of_one_equals_skinny_stream_k(L, skws, chws):
+    """A linear wide enough for the stream-K skinny kernel (more than 74 tiles) gives the same bits through the chain."""
+    B, N, K = 5, 152064, 3584
+    X, W, nw = rnd(B, K, seed=50), rnd(N, K, scale=K ** -0.5, seed=51), (1 + 0.1 * rnd(K, seed=52).float()).to(BF)
+    D1 = torch.empty((B, N), device="cuda", dtype=BF)
+    D2 = torch.empty((B, N), device="cuda", dtype=BF)
+    skinny_call(L, skws, X, W, D1, B, N, K, norm_w=nw, eps=1e-6)
+    chain_call(L, chws, [chain_lin(L, X, W, D2, norm_w=nw)], B)
+    torch.cuda.synchronize()
+    assert torch.equal(D1, D2)
+
+
 @pytest.mark.parametrize("rows,dim", [(7, 1280), (3, 3584), (999, 5120)])
 def test_rmsnorm(L, rows, dim):
     x, w = rnd(rows, dim, seed=50), (1 + 0.1 * rnd(dim, seed=51).float()).to(BF)
