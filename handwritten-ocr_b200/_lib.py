@@ -25,6 +25,19 @@ class ChainLinear(ctypes.Structure):
                 ("epilogue", c_int32), ("eps", c_float), ("norm_w", c_void_p)]
 
 
+class ChainAttention(ctypes.Structure):
+    """`ocrb_chain_attention`: one layer's paged decode attention inside a plan."""
+    _fields_ = [("qkv", c_void_p), ("ldqkv", c_int64), ("k_cache", c_void_p), ("v_cache", c_void_p), ("n_cache_pages", c_int32),
+                ("block_table", c_void_p), ("max_pages", c_int32), ("ctx_len", c_void_p), ("page_size", c_int32),
+                ("n_q", c_int32), ("n_kv", c_int32), ("hd", c_int32), ("cosT", c_void_p), ("sinT", c_void_p),
+                ("scale", c_float), ("out", c_void_p), ("ldo", c_int64), ("split_ws", c_void_p), ("n_splits", c_int32)]
+
+
+class ChainOp(ctypes.Structure):
+    """`ocrb_chain_op`: kind 0 = linear (`lin`), 1 = attention (`att`)."""
+    _fields_ = [("kind", c_int32), ("reserved", c_int32), ("lin", ChainLinear), ("att", ChainAttention)]
+
+
 _P = c_void_p
 _I = c_int32
 _L = c_int64
@@ -50,6 +63,8 @@ _SIGS = {
     "ocrb_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P],
     "ocrb_skinny_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P, _F, _P, _P],
     "ocrb_skinny_chain_bf16": [_P, _I, _I, _P, _P],
+    "ocrb_chain_plan_build": [_P, _I, _I, _P, _P, _P],
+    "ocrb_chain_plan_run": [_P, _I, _I, _P, _P],
     "ocrb_rmsnorm_bf16": [_P, _L, _P, _P, _L, _I, _I, _F, _P],
     "ocrb_rope_vision": [_P, _I, _I, _I, _P, _P, _P],
     "ocrb_rope_text": [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _P],
@@ -68,7 +83,7 @@ _SIGS = {
 }
 
 EXPORTS = ["ocrb_version", "ocrb_last_error", "ocrb_launch_count", "ocrb_launch_count_reset",
-           "ocrb_skinny_workspace_bytes", "ocrb_chain_workspace_bytes", "ocrb_inpaint_workspace_bytes"] + list(_SIGS)
+           "ocrb_skinny_workspace_bytes", "ocrb_chain_workspace_bytes", "ocrb_chain_plan_bytes", "ocrb_inpaint_workspace_bytes"] + list(_SIGS)
 
 
 def load():
@@ -87,6 +102,8 @@ def load():
     L.ocrb_launch_count_reset.restype = None
     L.ocrb_skinny_workspace_bytes.restype = c_int64
     L.ocrb_chain_workspace_bytes.restype = c_int64
+    L.ocrb_chain_plan_bytes.restype = c_int64
+    L.ocrb_chain_plan_bytes.argtypes = [c_int32]
     L.ocrb_inpaint_workspace_bytes.restype = c_int64
     L.ocrb_inpaint_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
     for name, args in _SIGS.items():

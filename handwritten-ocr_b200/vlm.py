@@ -69,7 +69,10 @@ def skinny(X, W, out, *, bias=None, residual=None, epilogue=EPI_NONE, norm_w=Non
 
 
 _CHAIN_WS = {}
-CHAIN_MAX_B = int(os.environ.get("OCRB_CHAIN_MAX_B", "128"))     # 0: one launch per linear (skinny / cluster kernels)
+# Largest batch decoded through the persistent chain / plan kernels (csrc/chain.cu).  Default 0: one launch per op (skinny /
+# cluster GEMMs + attention kernels under PDL) -- measured equal at B = 3 and faster above (profiles/r02_notes.md).
+CHAIN_MAX_B = int(os.environ.get("OCRB_CHAIN_MAX_B", "0"))
+CHAIN_FUSE_ATTN = os.environ.get("OCRB_CHAIN_ATTN", "1") == "1"   # the whole step (attention included) as one plan launch
 
 
 CHAIN_TRACE = None        # debugging: a list collects one timestamp buffer per chain launch
@@ -99,7 +102,7 @@ def skinny_chain(linears, B: int, device):
     if CHAIN_TRACE is not None:       # scripts/trace_chain.py: one [grid][64] globaltimer buffer per launch
         buf = torch.zeros(296 * 64, dtype=torch.int64, device=device)
         CHAIN_TRACE.append(buf)
-        _lib.load().ocrb_chain_set_trace(ctypes.c_void_p(buf.data_ptr()))
+        _lib.load().ocrb_chain_set_trace(ctypes.c_void_p(buf.data_ptr()), 64)
     _lib.call("ocrb_skinny_chain_bf16", ctypes.addressof(arr), len(linears), B, chain_workspace(device).data_ptr(), _sp())
 
 
@@ -565,11 +568,69 @@ class Decoder:
                   st.out_tokens.data_ptr(), st.next_ids.data_ptr(), st.finished.data_ptr(), st.ctx_len.data_ptr(),
                   st.step.data_ptr(), 1, _sp())
 
+    def _build_plan(self, st: "DecodeState"):
+        """The whole step as one plan: per layer [RMSNorm + qkv, attention, o_proj + residual, RMSNorm + gate/up + SwiGLU,
+        down_proj + residual], then final norm + lm_head.  Every pointer is baked into the device-side plan."""
+        t = self.cfg.text
+        nq, nkv, hd = t.heads, t.kv_heads, t.head_dim
+        B, eps = st.B, t.rms_eps
+        max_pages = st.block_table.shape[1]
+        ops = []
+
+        def lin(*a, **kw):
+            op = _lib.ChainOp()
+            op.kind = 0
+            op.lin = chain_linear(*a, **kw)
+            ops.append(op)
+
+        for li, lay in enumerate(self.w.layers):
+            lin(st.x, lay["qkv_w"], st.qkv, bias=lay["qkv_b"], norm_w=lay["ln1"], eps=eps)
+            op = _lib.ChainOp()
+            op.kind = 1
+            op.att = _lib.ChainAttention(st.qkv.data_ptr(), st.qkv.stride(0), self.kv.k[li].data_ptr(), self.kv.v[li].data_ptr(),
+                                         self.kv.n_pages, st.block_table.data_ptr(), max_pages, st.ctx_len.data_ptr(),
+                                         self.kv.page, nq, nkv, hd, st.cos.data_ptr(), st.sin.data_ptr(), float(hd ** -0.5),
+                                         st.att.data_ptr(), st.att.stride(0), st.split_ws.data_ptr(), st.n_splits)
+            ops.append(op)
+            lin(st.att, lay["o_w"], st.x, residual=st.x, epilogue=EPI_RESIDUAL)
+            lin(st.x, lay["gu_w"], st.act, epilogue=EPI_SWIGLU, norm_w=lay["ln2"], eps=eps)
+            lin(st.act, lay["down_w"], st.x, residual=st.x, epilogue=EPI_RESIDUAL)
+        lin(st.x, self.w.lm_head, st.logits_local, norm_w=self.w.final_norm, eps=eps)
+        n = len(ops)
+        arr = (_lib.ChainOp * n)(*ops)
+        plan = torch.zeros(int(_lib.load().ocrb_chain_plan_bytes(n)) + 64, dtype=torch.uint8, device=st.x.device)
+        off = (-plan.data_ptr()) % 64
+        _lib.call("ocrb_chain_plan_build", ctypes.addressof(arr), n, B, chain_workspace(st.x.device).data_ptr(),
+                  plan.data_ptr() + off, _sp())
+        st.plan, st.plan_ptr, st.plan_ops = plan, plan.data_ptr() + off, n
+
+    def _step_fused(self, st: "DecodeState"):
+        """One decode step = embedding gather, rope table, ONE persistent plan launch, argmax."""
+        t = self.cfg.text
+        B = st.B
+        if st.plan is None:
+            self._build_plan(st)
+        _lib.call("ocrb_embed_gather", self.w.embed.data_ptr(), st.next_ids.data_ptr(), st.x.data_ptr(), B, t.hidden, _sp())
+        _lib.call("ocrb_decode_rope_table", st.ctx_len.data_ptr(), st.rope_delta.data_ptr(), st.inv_freq.data_ptr(), B, t.head_dim,
+                  st.cos.data_ptr(), st.sin.data_ptr(), _sp())
+        dev = st.x.device
+        if CHAIN_TRACE is not None:
+            slots = 8 + 8 * st.plan_ops
+            buf = torch.zeros(296 * slots, dtype=torch.int64, device=dev)
+            CHAIN_TRACE.append(buf)
+            _lib.load().ocrb_chain_set_trace(ctypes.c_void_p(buf.data_ptr()), slots)
+        _lib.call("ocrb_chain_plan_run", st.plan_ptr, st.plan_ops, B, chain_workspace(dev).data_ptr(), _sp())
+        _lib.call("ocrb_argmax_step", st.logits.data_ptr(), st.logits.stride(0), B, t.vocab, EOS, EOS, st.max_new,
+                  st.out_tokens.data_ptr(), st.next_ids.data_ptr(), st.finished.data_ptr(), st.ctx_len.data_ptr(),
+                  st.step.data_ptr(), 1, _sp())
+
     def _step(self, st: "DecodeState"):
         t = self.cfg.text
         nq, nkv, hd = t.heads, t.kv_heads, t.head_dim
         B = st.B
         if self.tp is None and B <= CHAIN_MAX_B and t.hidden <= 8192:
+            if CHAIN_FUSE_ATTN and hd == 128 and 1 + 5 * len(self.w.layers) <= 192:
+                return self._step_fused(st)
             return self._step_chained(st)
         _lib.call("ocrb_embed_gather", self.w.embed.data_ptr(), st.next_ids.data_ptr(), st.x.data_ptr(), B, t.hidden, _sp())
         _lib.call("ocrb_decode_rope_table", st.ctx_len.data_ptr(), st.rope_delta.data_ptr(), st.inv_freq.data_ptr(), B, hd,
@@ -701,6 +762,8 @@ class DecodeState:
         self.split_ws = torch.empty(B * t.heads * self.n_splits * (t.head_dim + 2), dtype=torch.float32, device=dev)
         self.graph = None
         self.graph_launches = 0
+        self.plan = None               # device-side plan of the fused step (built at the first step)
+        self.plan_ptr, self.plan_ops = 0, 0
 
     def snapshot(self):
         return [x.clone() for x in (self.ctx_len, self.next_ids, self.finished, self.step, self.out_tokens)]

@@ -161,9 +161,9 @@ int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, int64_t ldw
  * o_proj -> [RMSNorm] gate/up+SwiGLU -> down_proj -> [RMSNorm] qkv of the next layer / lm_head; HF decoder layer
  * modeling_qwen2_5_vl.py:839-879 inside the generation loop utils.py:2743-2806).  Linear g+1 may read what linear g
  * (or any earlier one) wrote: the kernel orders them with device-side counters while the weight stream of the whole
- * chain keeps HBM busy.  Each linear has the meaning of one ocrb_skinny_gemm_bf16 call with the same arguments and
- * produces the same bits.  `residual` may equal `D` (in-place update).  norm_w != NULL: K <= 8192.
- * workspace: ocrb_chain_workspace_bytes() bytes, ZERO-initialised once by the caller, then owned by this entry point
+ * chain keeps HBM busy.  Each linear has the meaning of one ocrb_skinny_gemm_bf16 call with the same arguments.
+ * `residual` may equal `D` (in-place update).  norm_w != NULL: K <= 8192.
+ * workspace: ocrb_chain_workspace_bytes() bytes, ZERO-initialised once by the caller, then owned by these entry points
  * (counters are returned to zero by every launch); not shared by launches that can run concurrently. */
 #define OCRB_CHAIN_MAX 5
 typedef struct ocrb_chain_linear {
@@ -179,6 +179,36 @@ typedef struct ocrb_chain_linear {
 } ocrb_chain_linear;
 int64_t ocrb_chain_workspace_bytes(void);
 int ocrb_skinny_chain_bf16(const ocrb_chain_linear *lin, int32_t n, int32_t B, void *workspace, void *stream);
+
+/* A whole decode step as ONE persistent launch: a plan of up to OCRB_CHAIN_PLAN_MAX_OPS ops, each a skinny linear
+ * (above) or one layer's paged decode attention with the meaning of ocrb_decode_attention (mRoPE of the new token's
+ * q / k, KV append, split-KV attention, combine).  Op g+1 may read what op g wrote.  The attention ops of a plan share
+ * block table, context lengths and geometry (one per layer: only the caches differ); hd must be 128.
+ * ocrb_chain_plan_build writes the plan (ocrb_chain_plan_bytes(n) bytes of DEVICE memory, 64-byte aligned) and
+ * synchronises `stream`; ocrb_chain_plan_run only launches (CUDA-graph capturable).  The plan bakes in every pointer. */
+#define OCRB_CHAIN_PLAN_MAX_OPS 192
+#define OCRB_CHAIN_OP_LINEAR 0
+#define OCRB_CHAIN_OP_ATTENTION 1
+typedef struct ocrb_chain_attention {
+  const void *qkv; int64_t ldqkv;      /* [B, (n_q + 2 n_kv) * hd] fused q|k|v of the step (pre-RoPE) */
+  void *k_cache; void *v_cache;        /* the layer's paged cache [n_cache_pages][n_kv][page_size][hd] */
+  int32_t n_cache_pages;
+  const int32_t *block_table; int32_t max_pages;
+  const int32_t *ctx_len;              /* [B] cached tokens per sequence (the new token goes to position ctx_len) */
+  int32_t page_size, n_q, n_kv, hd;
+  const void *cosT; const void *sinT;  /* [B, hd] bf16 mRoPE tables of the new position */
+  float scale;
+  void *out; int64_t ldo;              /* [B, n_q * hd] */
+  float *split_ws; int32_t n_splits;   /* as ocrb_decode_attention */
+} ocrb_chain_attention;
+typedef struct ocrb_chain_op {
+  int32_t kind; int32_t reserved;
+  ocrb_chain_linear lin;
+  ocrb_chain_attention att;
+} ocrb_chain_op;
+int64_t ocrb_chain_plan_bytes(int32_t n_ops);
+int ocrb_chain_plan_build(const ocrb_chain_op *ops, int32_t n, int32_t B, void *workspace, void *plan, void *stream);
+int ocrb_chain_plan_run(const void *plan, int32_t n, int32_t B, void *workspace, void *stream);
 
 /* HF Qwen2_5_VLRMSNorm (modeling:66-71): y = w * bf16( x_f32 * rsqrt(mean(x^2)+eps) ) */
 int ocrb_rmsnorm_bf16(const void *x, int64_t ldx, const void *w, void *y, int64_t ldy, int32_t rows,

@@ -272,9 +272,8 @@ def test_chain_layer_matches_reference(L, chws, B, H, I, Q):
     close_bf16(x, x2, "chain down + residual (after o_proj + residual)", ulps=3.0, frac_exact=0.9, mag=lin_d)
     qkv_ref = ref_linear(hf_rmsnorm(x, t["ln1"], 1e-6), t["qkv_w"], t["qkv_b"])
     close_bf16(qkv, qkv_ref, "chain qkv", mag=qkv_ref)
-    ctr_at = 296 * 128 * 128 * 4
-    n_ctr = 5 * 296 + 48
-    assert int(chws[ctr_at:ctr_at + 4 * n_ctr].view(torch.int32).abs().sum()) == 0, "chain counters must return to zero"
+    ctr_at = 296 * 128 * 128 * 4 + 192 * 296 * 4          # done / stage2 / exit counters follow the epoch-valued flags (chain.cu)
+    assert int(chws[ctr_at:ctr_at + 4 * (2 * 192 + 1)].view(torch.int32).abs().sum()) == 0, "chain counters must return to zero"
 
 
 def test_chain_batch_invariance_and_determinism(L, chws):
@@ -470,6 +469,52 @@ def test_decode_attention_paged(L, n_splits, max_pages, nq, nkv, hd, ctx):
         p_new = bt[b, ctx[b] // page].long()
         assert torch.equal(kc[p_new, :, ctx[b] % page], kr)
         assert torch.equal(vc[p_new, :, ctx[b] % page], vn)
+
+
+@pytest.mark.parametrize("n_splits,max_pages,nq,nkv,ctx", [
+    (6, 20, 28, 4, [100, 37, 250]), (1, 20, 28, 4, [100, 37, 250]), (3, 24, 28, 4, [100, 37, 250]), (4, 20, 4, 2, [100, 37, 250]),
+    (20, 20, 28, 4, [0, 15, 16, 17, 319]), (17, 132, 28, 4, [1036, 1547, 2111, 127, 128]), (9, 132, 64, 8, [1036, 2000]),
+    (5, 40, 16, 1, [639, 1, 63, 64, 65, 300, 301]), (13, 97, 28, 4, [1036 + 7 * i for i in range(24)]),
+    (13, 97, 28, 4, [1100 + 3 * i for i in range(96)])])
+def test_plan_attention_equals_decode_attention(L, chws, n_splits, max_pages, nq, nkv, ctx):
+    """The attention op of a plan (csrc/chain.cu) = ocrb_decode_attention bit for bit: output, cache append and all."""
+    import ctypes
+    hd, B, page = 128, len(ctx), 16
+    n_pages = B * max_pages
+    kc = rnd(n_pages, nkv, page, hd, seed=80)
+    vc = rnd(n_pages, nkv, page, hd, seed=81)
+    perm = torch.randperm(n_pages, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    bt = perm.view(B, max_pages).to(torch.int32).contiguous()
+    qkv = rnd(B, (nq + 2 * nkv) * hd, seed=82)
+    ang = torch.rand(B, hd // 2, device="cuda") * 100
+    emb = torch.cat((ang, ang), -1)
+    cos, sin = emb.cos().to(BF).contiguous(), emb.sin().to(BF).contiguous()
+    ctx_d = torch.tensor(ctx, dtype=torch.int32, device="cuda")
+    res = []
+    for fused in (False, True):
+        k, v = kc.clone(), vc.clone()
+        ws = torch.zeros(B * nq * n_splits * (hd + 2), device="cuda", dtype=torch.float32)
+        out = torch.full((B, nq * hd), float("nan"), device="cuda", dtype=BF)
+        if not fused:
+            L.call("ocrb_decode_attention", qkv.data_ptr(), qkv.stride(0), k.data_ptr(), v.data_ptr(), n_pages, bt.data_ptr(),
+                   max_pages, ctx_d.data_ptr(), B, page, nq, nkv, hd, cos.data_ptr(), sin.data_ptr(), hd ** -0.5, out.data_ptr(),
+                   nq * hd, ws.data_ptr(), n_splits, sp())
+        else:
+            op = L.ChainOp()
+            op.kind = 1
+            op.att = L.ChainAttention(qkv.data_ptr(), qkv.stride(0), k.data_ptr(), v.data_ptr(), n_pages, bt.data_ptr(), max_pages,
+                                      ctx_d.data_ptr(), page, nq, nkv, hd, cos.data_ptr(), sin.data_ptr(), hd ** -0.5,
+                                      out.data_ptr(), nq * hd, ws.data_ptr(), n_splits)
+            arr = (L.ChainOp * 1)(op)
+            plan = torch.zeros(int(L.load().ocrb_chain_plan_bytes(1)) + 64, dtype=torch.uint8, device="cuda")
+            pp = plan.data_ptr() + (-plan.data_ptr()) % 64
+            L.call("ocrb_chain_plan_build", ctypes.addressof(arr), 1, B, chws.data_ptr(), pp, sp())
+            for _ in range(2):          # twice: the counters must come back to zero, the second run sees the appended row again
+                L.call("ocrb_chain_plan_run", pp, 1, B, chws.data_ptr(), sp())
+        torch.cuda.synchronize()
+        res.append((out, k, v))
+    assert torch.equal(res[0][0], res[1][0]), "attention output differs"
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2]), "KV append differs"
 
 
 def test_argmax_step_first_index_and_eos(L):

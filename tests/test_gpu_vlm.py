@@ -120,6 +120,34 @@ def test_batch_invariance_and_graph(ctx):
     assert again == batch
 
 
+@pytest.mark.parametrize("fuse_attention", [True, False])
+def test_fused_step_plan_reads_the_same_text(ctx, monkeypatch, fuse_attention):
+    """The decode step as ONE persistent plan launch (csrc/chain.cu; opt-in, OCRB_CHAIN_MAX_B) against the default
+    one-launch-per-op step: the narrow linears add their split-K partials in a different (fixed) order, so tokens are
+    compared up to the first step where the default path's own top-2 margin is a rounding tie; the fused path must be
+    batch-invariant bit for bit like the default one."""
+    from handwritten_ocr_b200 import vlm
+    cfg, hf, eng = ctx["default"]
+    pp, pages = ctx["pp"], ctx["pages"]
+    base = eng.read_batch(pp.to_device(pages), max_new_tokens=24)
+    monkeypatch.setattr(vlm, "CHAIN_MAX_B", 128)
+    monkeypatch.setattr(vlm, "CHAIN_FUSE_ATTN", fuse_attention)
+    eng._states.clear()                  # cached decode states carry a CUDA graph of the default step
+    try:
+        before = vlm._lib.launch_count()
+        fused = eng.read_batch(pp.to_device(pages), max_new_tokens=24)
+        singles = [eng.read_batch(pp.to_device(p), max_new_tokens=24)[0] for p in pages]
+        assert fused == singles, "fused step is not batch-invariant"
+        nograph = eng.read_batch(pp.to_device(pages), max_new_tokens=24, use_graph=False)
+        assert nograph == fused
+        assert vlm._lib.launch_count() > before
+    finally:
+        eng._states.clear()
+    for a, b in zip(base, fused):
+        same = next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), len(a))
+        assert same >= 4, f"fused step diverges from the default step at token {same}"
+
+
 def test_eos_stops_and_pads(ctx):
     """EOS semantics of HF's greedy loop (generation/utils.py:2743-2806): a sequence stops at its first <|im_end|>, a
     finished row of a batch is padded with pad = eos while the others continue, the batch ends when every row is done.
