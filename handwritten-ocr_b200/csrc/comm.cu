@@ -48,7 +48,7 @@ allreduce_residual_kernel(ArPeers peers, int world, int rank, int *__restrict__ 
     const long long t0 = clock64();
     do {
       asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-      if (v < k && clock64() - t0 > 6000000000LL) {
+      if (v < k && clock64() - t0 > 60000000000LL) {
         printf("ocrb all-reduce: rank %d never saw rank %d announce call %d (flag %d)\n", rank, tid, k, v);
         __trap();
       }

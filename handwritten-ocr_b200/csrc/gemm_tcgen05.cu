@@ -3,13 +3,16 @@
 // (HF modeling_qwen2_5_vl.py: patch_embed :99-111, qkv/proj :214-283, MLPs :76-88 / :607-622,
 // merger :133-146, q/k/v/o :704-760).
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (one 128 x BN output tile per CTA, 64 + 32 * GM_EPI_WARPS threads):
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor 128x64 (A) and BNx64 (W) bf16 boxes, 128B swizzle,
 //              into a 4-stage shared-memory ring, completion on mbarriers (expect_tx)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32 in TMEM),
 //              tcgen05.commit frees ring slots / signals the accumulator
-//   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns -> registers -> bias / residual / SwiGLU / GELU with
-//              HF's bf16 rounding points -> 16-byte global stores
+//   warps 2.. : epilogue -- tcgen05.ld 32 lanes x 32 columns -> registers -> bias / residual / SwiGLU / GELU with
+//              HF's bf16 rounding points -> 16-byte global stores.  Two warps per TMEM lane quadrant (warp % 4), each
+//              half of the tile's columns: one warp per scheduler is issue-latency bound (~400 dependent instructions per
+//              32-column chunk) and took 12-17 us per 128 x 256 tile -- longer than the 7.5 us of MMAs of a K = 1280
+//              tile, so the vision tower's GEMMs waited for their own epilogue (profiles/r02_summary.md)
 // M/N/K tails are handled by TMA zero fill on loads and predicated stores.
 #include "tc_common.cuh"
 #include <math.h>
@@ -20,7 +23,12 @@ namespace ocrb {
 constexpr int GM_BM = 128;
 constexpr int GM_BK = 64;          // 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int GM_STAGES = 4;
-constexpr int GM_THREADS = 192;
+#ifndef GM_EPI_WARPS_N
+#define GM_EPI_WARPS_N 8
+#endif
+constexpr int GM_EPI_WARPS = GM_EPI_WARPS_N;   // epilogue warps: GM_EPI_WARPS / 4 per TMEM lane quadrant, each a share of the columns
+constexpr int GM_NPART = GM_EPI_WARPS / 4;
+constexpr int GM_THREADS = 64 + 32 * GM_EPI_WARPS;
 
 __device__ __forceinline__ float silu_bf16r(float g) { return bf16_round(g / (1.0f + expf(-g))); }
 __device__ __forceinline__ float gelu_bf16r(float x) { return bf16_round(0.5f * x * (1.0f + erff(x * 0.70710678118654752440f))); }
@@ -84,7 +92,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], 32 * GM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -143,8 +151,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
     }
   } else {
-    // ───────────── epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) ─────────────
+    // ───────────── epilogue: warp w owns TMEM lane quadrant w % 4 and column share (w - 2) / 4 ─────────────
     const int quad = warp & 3;
+    const int part = (warp - 2) >> 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int n0, m0;
@@ -157,15 +166,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const bool row_ok = row < p.M;
       if (p.epilogue == OCRB_EPI_SWIGLU) {
         // weight rows are packed per 128 as [gate 64 | up 64]; output column block = n0/2
+        constexpr int ITEMS = BN / 64;              // (128-column block, 32-column chunk of its gate / up halves)
+        constexpr int PER = ITEMS / GM_NPART;
+        static_assert(ITEMS % GM_NPART == 0, "epilogue warps must divide the SwiGLU chunks");
 #pragma unroll 1
-        for (int blk = 0; blk < BN / 128; ++blk) {
-#pragma unroll 1
-          for (int c = 0; c < 64; c += 32) {
+        for (int item = part * PER; item < (part + 1) * PER; ++item) {
+          {
+            const int blk = item >> 1, c = (item & 1) * 32;
             uint32_t g[32], u[32];
             tmem_ld32(lane_addr + blk * 128 + c, g);
             tmem_ld32(lane_addr + blk * 128 + 64 + c, u);
             tmem_ld_wait();
-            if (blk == BN / 128 - 1 && c == 32) {   // last TMEM read of this tile: hand the accumulator back
+            if (item == (part + 1) * PER - 1) {     // this warp's last TMEM read of the tile: hand the accumulator back
               tcgen05_fence_before();
               mbar_arrive_cta(&tmem_empty[acc]);
             }
@@ -205,12 +217,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         }
       } else {
+        constexpr int CPW = BN / GM_NPART;          // columns per epilogue warp
+        static_assert(CPW % 32 == 0, "epilogue warps must divide the 32-column chunks");
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = part * CPW; c < (part + 1) * CPW; c += 32) {
           uint32_t r[32];
           tmem_ld32(lane_addr + c, r);
           tmem_ld_wait();
-          if (c == BN - 32) {                        // last TMEM read of this tile
+          if (c == (part + 1) * CPW - 32) {          // this warp's last TMEM read of the tile
             tcgen05_fence_before();
             mbar_arrive_cta(&tmem_empty[acc]);
           }

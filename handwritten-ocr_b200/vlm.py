@@ -722,6 +722,10 @@ class Decoder:
             st.graph_launches = _lib.launch_count() - before
             st.restore(snap)
             st.graph = g
+            if self.tp is not None:
+                # a rank that is still capturing must not be waited for inside the peer all-reduce of a replaying rank
+                torch.cuda.synchronize()
+                self.tp.dist.barrier(group=self.tp.group)
         for i in range(n_steps):
             g.replay()
             self.replayed_launches += st.graph_launches
