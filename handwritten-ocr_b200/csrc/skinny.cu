@@ -29,6 +29,14 @@
 
 namespace ocrb {
 
+// 65..128 activation rows: ring depth and CTAs per SM (two CTAs of consecutive launches on one SM = PDL overlap)
+#ifndef SK_ST_BIG
+#define SK_ST_BIG 6
+#endif
+#ifndef SK_OCC_BIG
+#define SK_OCC_BIG 1
+#endif
+
 
 struct SkinnyParams {
   const bf16 *X; long long ldx;
@@ -130,10 +138,10 @@ skinny_norm_rows_kernel(SkinnyParams p, bf16 *__restrict__ xn) {
 // BP = MMA N (activation rows staged per k-block: 16/32/64); BC = accumulator columns the epilogue actually reads,
 // publishes and stores (4/8/16/32/64 >= B): with B = 3 sequences the fix-up moves 4 columns, not 16.
 template <int BP, int BC>
-__global__ void __launch_bounds__(SK_THREADS, (BP > 64) ? 1 : 2)
+__global__ void __launch_bounds__(SK_THREADS, (BP > 64) ? SK_OCC_BIG : 2)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, SkinnyParams p) {
   // ring depth: 4 x 24 KiB at BP = 64 keeps two CTAs per SM; above that one CTA per SM with 6 stages (96 KiB of weights in flight)
-  constexpr int ST = (BP > 64) ? 6 : ((BP >= 64) ? 4 : SK_STAGES);
+  constexpr int ST = (BP > 64) ? SK_ST_BIG : ((BP >= 64) ? 4 : SK_STAGES);
   constexpr uint32_t X_BYTES = BP * SK_BK * 2;
   constexpr uint32_t STAGE_BYTES = SK_W_BYTES + X_BYTES;
   constexpr int ACC_STRIDE = (BP <= 16) ? 16 : (BP <= 32 ? 32 : (BP <= 64 ? 64 : 128));   // TMEM columns between the two accumulators
@@ -493,9 +501,9 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t local_saddr, uint32_t ra
 }
 
 template <int BP, int BC, int SKC_CS>
-__global__ void __launch_bounds__(SK_THREADS, (BP > 64) ? 1 : 2)
+__global__ void __launch_bounds__(SK_THREADS, (BP > 64) ? SK_OCC_BIG : 2)
 skinny_cluster_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, SkinnyParams p) {
-  constexpr int ST = (BP > 64) ? 6 : ((BP >= 64) ? 4 : SK_STAGES);
+  constexpr int ST = (BP > 64) ? SK_ST_BIG : ((BP >= 64) ? 4 : SK_STAGES);
   constexpr uint32_t X_BYTES = BP * SK_BK * 2;
   constexpr uint32_t STAGE_BYTES = SK_W_BYTES + X_BYTES;
   constexpr int TMEM_COLS = (BP < 32) ? 32 : ((BP <= 32) ? 32 : (BP <= 64 ? 64 : 128));
@@ -673,7 +681,7 @@ skinny_cluster_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
 
 template <int BP, int BC, int CS>
 static int launch_skinny_cluster(const CUtensorMap &mw, const CUtensorMap &mx, const SkinnyParams &p, cudaStream_t st) {
-  constexpr int ST = (BP > 64) ? 6 : ((BP >= 64) ? 4 : SK_STAGES);
+  constexpr int ST = (BP > 64) ? SK_ST_BIG : ((BP >= 64) ? 4 : SK_STAGES);
   constexpr size_t smem = (size_t)ST * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 320 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
@@ -705,7 +713,7 @@ template <int CS>
 static int cluster_cap() {
   static int n = -1;
   if (n < 0) {
-    constexpr size_t smem = (size_t)6 * (SK_W_BYTES + 128 * SK_BK * 2) + 1024 + 320;
+    constexpr size_t smem = (size_t)SK_ST_BIG * (SK_W_BYTES + 128 * SK_BK * 2) + 1024 + 320;
     n = 0;
     if (cudaFuncSetAttribute(skinny_cluster_kernel<128, 128, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
       cudaLaunchConfig_t cfg = {};
@@ -747,7 +755,7 @@ static int launch_skinny_cluster_cs(int cs, const CUtensorMap &mw, const CUtenso
 
 template <int BP, int BC>
 static int launch_skinny(const CUtensorMap &mw, const CUtensorMap &mx, const SkinnyParams &p, int grid, cudaStream_t st) {
-  constexpr int ST = (BP > 64) ? 6 : ((BP >= 64) ? 4 : SK_STAGES);
+  constexpr int ST = (BP > 64) ? SK_ST_BIG : ((BP >= 64) ? 4 : SK_STAGES);
   constexpr int CC = (BC < 16) ? BC : 16;
   constexpr size_t smem = (size_t)ST * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 320 /*barriers*/ +
                           64 * CC * sizeof(float) + 64;

@@ -384,6 +384,27 @@ def test_attention_varlen(L, hd, nq, nkv, causal, lens):
         off += n
 
 
+@pytest.mark.parametrize("hd", [80, 64])
+def test_window_attention_equals_general_kernel(L, hd):
+    """Sequences of <= 64 tokens (the vision tower's windows) go through the persistent double-buffered window kernel:
+    bit-equal to the general one-CTA-per-tile kernel (reached by declaring max_seqlen = 65) on 630 windows of mixed length."""
+    nq = 16
+    g = torch.Generator().manual_seed(3)
+    lens = [64] * 500 + [int(x) for x in torch.randint(1, 65, (130,), generator=g)]
+    T = sum(lens)
+    q, k, v = rnd(T, nq * hd, seed=73), rnd(T, nq * hd, seed=74), rnd(T, nq * hd, seed=75)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    outs = []
+    for max_len in (64, 65):
+        out = torch.full((T, nq * hd), float("nan"), device="cuda", dtype=BF)
+        L.call("ocrb_attention_varlen", q.data_ptr(), nq * hd, k.data_ptr(), nq * hd, v.data_ptr(), nq * hd, out.data_ptr(),
+               nq * hd, cu.data_ptr(), len(lens), max_len, nq, nq, hd, hd ** -0.5, 0, sp())
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert not torch.isnan(outs[0].float()).any()
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("hd,nq,nkv,causal,lens", [
     (80, 16, 16, 0, [700]),
     (80, 16, 16, 0, [256, 257, 511, 64, 1]),

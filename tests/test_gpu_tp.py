@@ -71,6 +71,8 @@ def _worker(rank, world, port, q):
         ref.close()
     eng.close()
     q.put(res)
+    q.close()
+    q.join_thread()  # os._exit below does not run the queue's feeder thread to completion: flush the result first
     dist.barrier()
     torch.cuda.synchronize()
     os._exit(0)      # skip NCCL communicator teardown (can hang after graph-captured collectives)
@@ -87,7 +89,7 @@ def test_tp2_matches_single_gpu():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = sorted((q.get(timeout=600) for _ in range(2)), key=lambda r: r["rank"])
+    got = sorted((q.get(timeout=300) for _ in range(2)), key=lambda r: r["rank"])
     for p in procs:
         p.join(timeout=60)
         if p.is_alive():
