@@ -363,8 +363,9 @@ def run_b200(args):
     iso = eng.dec.time_weight_stream(B, reps=3)
     traffic = None
     if not args.tiny and B == 3:
-        # dram read+write of the launches of ONE decode step from the `ncu --set full` captures (profiles/r02*_summary.md)
-        traffic = 14_368_000_000
+        # dram__bytes_read + dram__bytes_write of the launches of ONE decode step from the `ncu --set full` capture of a decode
+        # layer (profiles/r02_summary.md): 28 x (qkv 33.1 + attention 6.5 + o_proj 25.8 + gate/up 276.2 + down 141.2 MB) + lm_head
+        traffic = 14_610_000_000
     roofline = {"bound": "hbm", "kernel": "skinny_gemm_kernel (tcgen05 swap-AB weight streaming) + decode_attn_kernel (paged KV); "
                                           "whole decode step timed in situ",
                 "achieved": dr["achieved"], "peak": pk["hbm"], "unit": "GB/s", "frac": dr["frac"], "peak_source": pk["source"],
