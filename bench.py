@@ -146,10 +146,11 @@ class Workload:
         batch = self.torch.stack(cands, 1).reshape((P * ns,) + tuple(cands[0].shape[1:]))   # page-major: p0s0,p0s1,...
         toks = self.eng.read_batch(batch, prompt=PROMPT, max_new_tokens=NEW_TOKENS)
         texts = [self.eng.detokenize(t) for t in toks]
-        res = []
-        for p in range(P):
-            tp = texts[ns * p: ns * (p + 1)]
-            res.append((textops.compare_versions(tp[0], tp[1]), textops.merge_versions(tp)))
+        # agreement + majority-vote merge of every page of the batch: one Levenshtein launch, one LCS launch
+        per_page = [texts[ns * p: ns * (p + 1)] for p in range(P)]
+        cmps = textops.compare_versions_batch([(tp[0], tp[1]) for tp in per_page])
+        merged = textops.merge_versions_batch(per_page)
+        res = list(zip(cmps, merged))
         return toks, texts, res
 
     def account(self, B: int):

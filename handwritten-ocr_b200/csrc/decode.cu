@@ -348,11 +348,15 @@ extern "C" int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cac
   if (rc) return rc;
   rc = make_cache_map(&mv, v_cache, rows, hd);
   if (rc) return rc;
-  static int cfg = -1;
-  if (cfg < 0) {
+  // workers per CTA x ring depth: 6 x 4 while a worker has one or two items (small batches: latency of the ring), 8 x 2 once
+  // every worker has several (B = 96: 225 vs 231 us per layer -- more warps hide the serial mma / softmax chain of a tile).
+  // A sequence's arithmetic does not depend on the choice.
+  static int cfg_env = -1;
+  if (cfg_env < 0) {
     const char *e = getenv("OCRB_ATTN_CFG");
-    cfg = e ? atoi(e) : 64;
+    cfg_env = e ? atoi(e) : 0;
   }
+  const int cfg = cfg_env ? cfg_env : (((long long)B * n_kv * n_splits >= 3LL * 148 * 6) ? 82 : 64);
 #define DA_LAUNCH(HD_, W_, S_)                                                                                              \
   launch_decode_attn<HD_, W_, S_>(mk, mv, (const bf16 *)qkv, (long long)ldqkv, (bf16 *)k_cache, (bf16 *)v_cache, block_table, \
                                   (int)max_pages, ctx_len, (int)B, (int)page_size, (int)n_q, (int)n_kv, (const bf16 *)cosT,    \

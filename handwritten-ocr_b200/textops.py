@@ -173,70 +173,109 @@ def _find_differing_segments(w1: list, w2: list) -> list:
     return segs
 
 
+def compare_versions_batch(pairs: Sequence[tuple]) -> list:
+    """[(v1, v2), ...] -> list of tools.py:326-350 dicts; the 2 * len(pairs) char and word distances share ONE launch
+    (a folder batch compares the candidates of all its pages at once)."""
+    prep, lev = [], []
+    for v1, v2 in pairs:
+        n1, n2 = normalize_text(v1), normalize_text(v2)
+        w1, w2 = n1.split(), n2.split()
+        i1, i2 = _ids(w1, w2)
+        lev += [(_codes(n1), _codes(n2)), (i1, i2)]
+        prep.append((n1, n2, w1, w2))
+    d = levenshtein_ids_batch(lev)
+    out = []
+    for k, (n1, n2, w1, w2) in enumerate(prep):
+        dc, dw = d[2 * k], d[2 * k + 1]
+        out.append({
+            "agreement_rate": round((1 - dc / max(len(n1), len(n2), 1)) * 100, 1),
+            "char_edit_distance": dc,
+            "word_edit_distance": dw,
+            "differing_segments": _find_differing_segments(w1, w2),
+        })
+    return out
+
+
 def compare_versions(v1: str, v2: str) -> dict:
     """tools.py:326-350; char and word distances share one launch."""
-    n1, n2 = normalize_text(v1), normalize_text(v2)
-    w1, w2 = n1.split(), n2.split()
-    i1, i2 = _ids(w1, w2)
-    dc, dw = levenshtein_ids_batch([(_codes(n1), _codes(n2)), (i1, i2)])
-    return {
-        "agreement_rate": round((1 - dc / max(len(n1), len(n2), 1)) * 100, 1),
-        "char_edit_distance": dc,
-        "word_edit_distance": dw,
-        "differing_segments": _find_differing_segments(w1, w2),
-    }
+    return compare_versions_batch([(v1, v2)])[0]
 
 
-def lcs_align_batch(backbone_ids: np.ndarray, version_ids: Sequence[np.ndarray]) -> list:
-    """Align every version to the backbone (tools.py:465-493) in one launch.
-    Returns, per version, an int32 array [len(backbone)] of indices into that version (-1 = gap)."""
+def lcs_align_pairs(pairs: Sequence[tuple]) -> list:
+    """[(backbone ids, version ids), ...] -> per pair an int32 array [len(backbone)] of indices into the version (-1 = gap):
+    tools.py:465-493 for every pair in ONE launch (one CTA per pair)."""
     dev = _dev()
-    n = len(backbone_ids)
-    nv = len(version_ids)
-    if n == 0 or nv == 0:
-        return [np.full(n, -1, np.int32) for _ in range(nv)]
-    fb, ob = _pack([backbone_ids] * nv)
-    fw, ow = _pack(list(version_ids))
-    sizes = np.array([n * len(v) for v in version_ids], np.int64)
-    ws_off = np.zeros(nv, np.int64)
+    out = [np.full(len(b), -1, np.int32) for b, _ in pairs]
+    live = [k for k, (b, v) in enumerate(pairs) if len(b) and len(v)]
+    if not live:
+        return out
+    fb, ob = _pack([pairs[k][0] for k in live])
+    fw, ow = _pack([pairs[k][1] for k in live])
+    sizes = np.array([len(pairs[k][0]) * len(pairs[k][1]) for k in live], np.int64)
+    ws_off = np.zeros(len(live), np.int64)
     ws_off[1:] = np.cumsum(sizes)[:-1]
     ints = torch.from_numpy(np.concatenate([fb, ob, fw, ow])).to(dev)
     b_, ob_, w_, ow_ = torch.split(ints, [len(fb), len(ob), len(fw), len(ow)])
     wsoff_d = torch.from_numpy(ws_off).to(dev)
     ws = torch.empty(max(int(sizes.sum()), 1), dtype=torch.uint8, device=dev)
-    aligned = torch.empty(n * nv, dtype=torch.int32, device=dev)
-    _lib.call("ocrb_lcs_align_batch", _lib.ptr(b_), _lib.ptr(ob_), _lib.ptr(w_), _lib.ptr(ow_), nv, n,
-              _lib.ptr(aligned), _lib.ptr(ws), _lib.ptr(wsoff_d), _lib.stream_ptr())
-    al = aligned.cpu().numpy().reshape(nv, n)
-    return [al[k] for k in range(nv)]
+    aligned = torch.empty(int(ob[-1]), dtype=torch.int32, device=dev)
+    _lib.call("ocrb_lcs_align_batch", _lib.ptr(b_), _lib.ptr(ob_), _lib.ptr(w_), _lib.ptr(ow_), len(live),
+              int(max(len(pairs[k][0]) for k in live)), _lib.ptr(aligned), _lib.ptr(ws), _lib.ptr(wsoff_d), _lib.stream_ptr())
+    al = aligned.cpu().numpy()
+    for j, k in enumerate(live):
+        out[k] = al[ob[j]:ob[j + 1]]
+    return out
+
+
+def lcs_align_batch(backbone_ids: np.ndarray, version_ids: Sequence[np.ndarray]) -> list:
+    """Align every version to the backbone (tools.py:465-493) in one launch.
+    Returns, per version, an int32 array [len(backbone)] of indices into that version (-1 = gap)."""
+    return lcs_align_pairs([(backbone_ids, v) for v in version_ids])
+
+
+def merge_versions_batch(version_lists: Sequence[list]) -> list:
+    """tools.py:411-462 for many pages at once: every candidate of every page is aligned to its page's first-longest one
+    (case-insensitive LCS) in ONE launch, then the per-position vote runs on the host; ties keep all variants as `[a|b]` in
+    candidate order."""
+    results = [None] * len(version_lists)
+    jobs, pairs = [], []
+    for p, versions in enumerate(version_lists):
+        if not versions:
+            results[p] = ""
+            continue
+        if len(versions) == 1:
+            results[p] = versions[0]
+            continue
+        word_lists = [normalize_text(v).split() for v in versions]
+        backbone_idx = max(range(len(word_lists)), key=lambda i: len(word_lists[i]))
+        backbone = word_lists[backbone_idx]
+        ids = _ids(backbone, *word_lists, key=str.lower)
+        jobs.append((p, word_lists, backbone, len(pairs)))
+        pairs += [(ids[0], v) for v in ids[1:]]
+    aligned_all = lcs_align_pairs(pairs) if pairs else []
+    for p, word_lists, backbone, first in jobs:
+        aligned = aligned_all[first:first + len(word_lists)]
+        merged = []
+        for pos, bw in enumerate(backbone):
+            cands = [wl[a[pos]] for wl, a in zip(word_lists, aligned) if a[pos] >= 0]
+            if not cands:
+                merged.append(bw)
+                continue
+            votes: dict = {}
+            for c in cands:
+                votes[c] = votes.get(c, 0) + 1
+            top = max(votes.values())
+            winners = [w for w, c in votes.items() if c == top]
+            if len(winners) == 1:
+                merged.append(winners[0])
+            else:
+                uniq = list(dict.fromkeys(cands))
+                merged.append(uniq[0] if len(uniq) == 1 else "[" + "|".join(uniq) + "]")
+        results[p] = " ".join(merged)
+    return results
 
 
 def merge_versions(versions: list) -> str:
     """tools.py:411-462: align every candidate to the first-longest one (case-insensitive LCS), then
     vote per backbone position; ties keep all variants as `[a|b]` in candidate order."""
-    if not versions:
-        return ""
-    if len(versions) == 1:
-        return versions[0]
-    word_lists = [normalize_text(v).split() for v in versions]
-    backbone_idx = max(range(len(word_lists)), key=lambda i: len(word_lists[i]))
-    backbone = word_lists[backbone_idx]
-    ids = _ids(backbone, *word_lists, key=str.lower)
-    aligned = lcs_align_batch(ids[0], ids[1:])
-    merged = []
-    for pos, bw in enumerate(backbone):
-        cands = [wl[a[pos]] for wl, a in zip(word_lists, aligned) if a[pos] >= 0]
-        if not cands:
-            merged.append(bw)
-            continue
-        votes: dict = {}
-        for c in cands:
-            votes[c] = votes.get(c, 0) + 1
-        top = max(votes.values())
-        winners = [w for w, c in votes.items() if c == top]
-        if len(winners) == 1:
-            merged.append(winners[0])
-        else:
-            uniq = list(dict.fromkeys(cands))
-            merged.append(uniq[0] if len(uniq) == 1 else "[" + "|".join(uniq) + "]")
-    return " ".join(merged)
+    return merge_versions_batch([versions])[0]

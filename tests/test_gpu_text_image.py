@@ -102,6 +102,25 @@ def test_merge_vs_oracle_large(tx, synth):
     assert tx.compare_versions(vs[0], vs[1]) == T.compare_versions(vs[0], vs[1])
 
 
+def test_compare_merge_batches_equal_singles_and_goldens(tx, synth, text_golden):
+    """A folder batch's agreement / merge step in two launches: the goldens of the unmodified reference, 32 synthetic pages
+    of ragged length (empty and single-candidate pages included), all equal to the one-page calls and the oracle."""
+    cmp_cases = text_golden["compare_versions"]
+    assert tx.compare_versions_batch([(c["v1"], c["v2"]) for c in cmp_cases]) == [c["out"] for c in cmp_cases]
+    mrg_cases = text_golden["merge_versions"]
+    assert tx.merge_versions_batch([c["versions"] for c in mrg_cases]) == [c["out"] for c in mrg_cases]
+    pages = []
+    for p in range(32):
+        base = synth.text(100 + p, 40 + 37 * (p % 9))
+        pages.append([synth.corrupt(base, 3 * p + k, 0.02 + 0.01 * k) for k in range(3)])
+    pages += [[], ["only one candidate"], ["", "two words"], ["same", "same", "same"]]
+    merged = tx.merge_versions_batch(pages)
+    assert merged == [T.merge_versions(v) for v in pages]
+    pairs = [(v[0], v[1]) for v in pages if len(v) >= 2]
+    assert tx.compare_versions_batch(pairs) == [T.compare_versions(a, b) for a, b in pairs]
+    assert tx.compare_versions_batch([]) == [] and tx.merge_versions_batch([]) == []
+
+
 # ───────────── image ─────────────
 @pytest.mark.parametrize("name", SMALL)
 def test_small_transforms_golden(pp, image_small, name):
