@@ -205,6 +205,11 @@ __device__ __forceinline__ void ch_ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t 
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
 }
+__device__ __forceinline__ uint32_t ch_movmatrix_trans(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
 __device__ __forceinline__ void ch_mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -605,19 +610,18 @@ __device__ __forceinline__ void chain_body(const ChainDesc *__restrict__ descs, 
           const int total = ctx + 1;
           const bf16 *row = d.qkv + (size_t)a.b * d.ldqkv;
           const bf16 *c = d.cosT + (size_t)a.b * CH_HD, *s_ = d.sinT + (size_t)a.b * CH_HD;
-          // Q fragments of the m16 tile (rows = the Gq query heads of this KV head, rows >= Gq zero), mRoPE applied.
+          // Q^T operand fragments (lane r0 = query head, heads >= Gq zero), mRoPE applied.
           // Element j of a lane = columns (j >> 1) * 16 + (j & 1) * 8 + cq, +1; its rotate-half partner (column +- 64) is
           // element j ^ 8 of the same lane, so one batch of independent loads (q rows, cos, sin) feeds the whole tile.
           uint32_t qf[CH_HD / 16][4];
           {
-            const bf16 *q0 = row + (size_t)(a.kvh * Gq + r0) * CH_HD, *q1 = q0 + (size_t)8 * CH_HD;
-            const bool v0 = r0 < Gq, v1 = r0 + 8 < Gq;
-            uint32_t x0[16], x1[16], cw[16], sw[16];
+            const bf16 *q0 = row + (size_t)(a.kvh * Gq + r0) * CH_HD;
+            const bool v0 = r0 < Gq;
+            uint32_t x0[16], cw[16], sw[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int col = (j >> 1) * 16 + (j & 1) * 8 + cq;
               x0[j] = v0 ? __ldcg(reinterpret_cast<const unsigned int *>(q0 + col)) : 0u;
-              x1[j] = v1 ? __ldcg(reinterpret_cast<const unsigned int *>(q1 + col)) : 0u;
               cw[j] = *reinterpret_cast<const unsigned int *>(c + col);
               sw[j] = *reinterpret_cast<const unsigned int *>(s_ + col);
             }
@@ -625,15 +629,16 @@ __device__ __forceinline__ void chain_body(const ChainDesc *__restrict__ descs, 
             for (int j = 0; j < 16; ++j) {
               const float sgn = (j < 8) ? -1.f : 1.f;
               qf[j >> 1][(j & 1) * 2] = ch_rope_math(x0[j], x0[j ^ 8], cw[j], sw[j], sgn);
-              qf[j >> 1][(j & 1) * 2 + 1] = ch_rope_math(x1[j], x1[j ^ 8], cw[j], sw[j], sgn);
+              qf[j >> 1][(j & 1) * 2 + 1] = 0u;              // rows 8-15 of the old head-major tile: unused (Gq <= 8)
             }
           }
           if (et == 0 && q == 0) ch_stamp(ctl, 8 + g * 8 + 1);   // Q fragments built
-          constexpr int NJ = CH_HD / 8;
-          float o[NJ][4];
+          // transposed products (decode.cu): S^T[key][head] = K . Q^T, O^T[dim][head] += V^T . P^T; heads on the N = 8 side
+          constexpr int KK = CH_HD / 16;
+          float o[KK][4];
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-          float run_m[2] = {-INFINITY, -INFINITY}, run_l[2] = {0.f, 0.f};
+          for (int mt = 0; mt < KK; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+          float run_m[2] = {-INFINITY, -INFINITY}, run_l[2] = {0.f, 0.f};     // heads cq, cq + 1
 
           for (int u = s_gstart[q]; u < s_gstart[q + 1]; ++u) {
             const AttnUnit e = s_units[u];
@@ -667,72 +672,55 @@ __device__ __forceinline__ void chain_body(const ChainDesc *__restrict__ descs, 
                 patched = true;
                 __syncwarp();
               }
-              // ---- S = Q.K^T for the 16 keys of the tile (two 8-key column tiles) ----
-              float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+              float acc[4] = {0.f, 0.f, 0.f, 0.f};
               {
                 const int kr = (m >> 1) * 8 + l8;                     // key row this lane addresses
 #pragma unroll
-                for (int kk = 0; kk < CH_HD / 16; ++kk) {
+                for (int kk = 0; kk < KK; ++kk) {
                   uint32_t bb[4];
                   const int ch = (kk & 3) * 2 + (m & 1);              // 16-byte chunk inside the 64-dim atom
                   ch_ldmatrix_x4(bb, sk + (kk >> 2) * 2048 + kr * 128 + ((ch ^ (kr & 7)) << 4));
-                  ch_mma_16816(acc[0], qf[kk], bb[0], bb[1]);
-                  ch_mma_16816(acc[1], qf[kk], bb[2], bb[3]);
+                  const uint32_t ka[4] = {bb[0], bb[2], bb[1], bb[3]};
+                  ch_mma_16816(acc, ka, qf[kk][0], qf[kk][2]);
                 }
               }
-              // ---- online softmax: this thread holds rows r0 (e = 0, 1) and r0 + 8 (e = 2, 3), keys j * 8 + cq + (e & 1) ----
-              float tmax[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-              for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int ee = 0; ee < 4; ++ee) {
-                  const bool ok = key0 + j * 8 + cq + (ee & 1) < total;
-                  acc[j][ee] = ok ? acc[j][ee] * d.scale : -INFINITY;
-                  tmax[ee >> 1] = fmaxf(tmax[ee >> 1], acc[j][ee]);
-                }
+              const bool ok0 = key0 + r0 < total, ok1 = key0 + r0 + 8 < total;
               float corr[2];
+              bool moved = false;
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                tmax[h] = fmaxf(tmax[h], __shfl_xor_sync(0xffffffffu, tmax[h], 1));
-                tmax[h] = fmaxf(tmax[h], __shfl_xor_sync(0xffffffffu, tmax[h], 2));
-                const float mn = fmaxf(run_m[h], tmax[h]);            // finite: every processed tile has a live key
-                corr[h] = __expf(run_m[h] - mn);                      // exp(-inf) = 0 on the first tile
-                run_m[h] = mn;
-                run_l[h] *= corr[h];
+              for (int j = 0; j < 2; ++j) {
+                acc[j] = ok0 ? acc[j] * d.scale : -INFINITY;
+                acc[2 + j] = ok1 ? acc[2 + j] * d.scale : -INFINITY;
+                float tmax = fmaxf(acc[j], acc[2 + j]);
+                tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 4));
+                tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 8));
+                tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 16));
+                const float mn = fmaxf(run_m[j], tmax);               // finite: every processed tile has a live key
+                corr[j] = __expf(run_m[j] - mn);                      // exp(-inf) = 0 on the first tile
+                run_m[j] = mn;
+                run_l[j] *= corr[j];
+                moved |= corr[j] != 1.0f;
               }
-              uint32_t pa[4];
-              {
-                float pv[2][4];
+              float pv[4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                  for (int ee = 0; ee < 4; ++ee) {
-                    pv[j][ee] = __expf(acc[j][ee] - run_m[ee >> 1]);
-                    run_l[ee >> 1] += pv[j][ee];
-                  }
-                pa[0] = ch_pack_bf16(pv[0][0], pv[0][1]);
-                pa[1] = ch_pack_bf16(pv[0][2], pv[0][3]);
-                pa[2] = ch_pack_bf16(pv[1][0], pv[1][1]);
-                pa[3] = ch_pack_bf16(pv[1][2], pv[1][3]);
+              for (int ee = 0; ee < 4; ++ee) {
+                pv[ee] = __expf(acc[ee] - run_m[ee & 1]);
+                run_l[ee & 1] += pv[ee];
               }
-              // ---- O = O * corr + P.V (the scaling is skipped when no row of the warp moved its maximum) ----
+              const uint32_t pb0 = ch_movmatrix_trans(ch_pack_bf16(pv[0], pv[1]));
+              const uint32_t pb1 = ch_movmatrix_trans(ch_pack_bf16(pv[2], pv[3]));
               {
-                const bool rescale = __any_sync(0xffffffffu, corr[0] != 1.0f || corr[1] != 1.0f);
+                const bool rescale = __any_sync(0xffffffffu, moved);
                 const int vr = (m & 1) * 8 + l8;                      // key row this lane addresses
 #pragma unroll
-                for (int jj = 0; jj < CH_HD / 16; ++jj) {
+                for (int jj = 0; jj < KK; ++jj) {
                   uint32_t bb[4];
                   const int ch = (jj & 3) * 2 + (m >> 1);
                   ch_ldmatrix_x4_trans(bb, sv + (jj >> 2) * 2048 + vr * 128 + ((ch ^ (vr & 7)) << 4));
-                  if (rescale) {
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                      float (&oo)[4] = o[jj * 2 + t];
-                      oo[0] *= corr[0]; oo[1] *= corr[0]; oo[2] *= corr[1]; oo[3] *= corr[1];
-                    }
-                  }
-                  ch_mma_16816(o[jj * 2], pa, bb[0], bb[1]);
-                  ch_mma_16816(o[jj * 2 + 1], pa, bb[2], bb[3]);
+                  const uint32_t va[4] = {bb[0], bb[2], bb[1], bb[3]};
+                  float (&oo)[4] = o[jj];
+                  if (rescale) { oo[0] *= corr[0]; oo[1] *= corr[1]; oo[2] *= corr[0]; oo[3] *= corr[1]; }
+                  ch_mma_16816(oo, va, pb0, pb1);
                 }
               }
             }
@@ -742,20 +730,25 @@ __device__ __forceinline__ void chain_body(const ChainDesc *__restrict__ descs, 
           }
           // ---- one fp32 partial (max, sum, o[hd]) per head of this item, straight from the registers ----
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            run_l[h] += __shfl_xor_sync(0xffffffffu, run_l[h], 1);
-            run_l[h] += __shfl_xor_sync(0xffffffffu, run_l[h], 2);
+          for (int j = 0; j < 2; ++j) {
+            run_l[j] += __shfl_xor_sync(0xffffffffu, run_l[j], 4);
+            run_l[j] += __shfl_xor_sync(0xffffffffu, run_l[j], 8);
+            run_l[j] += __shfl_xor_sync(0xffffffffu, run_l[j], 16);
           }
           float *ws = d.split_ws + (((size_t)a.b * d.n_q + (size_t)a.kvh * Gq) * d.n_splits + a.split) * (CH_HD + 2);
           const size_t ws_head = (size_t)d.n_splits * (CH_HD + 2);
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) {
-            if (r0 < Gq) *reinterpret_cast<float2 *>(ws + r0 * ws_head + 2 + j * 8 + cq) = make_float2(o[j][0], o[j][1]);
-            if (r0 + 8 < Gq) *reinterpret_cast<float2 *>(ws + (r0 + 8) * ws_head + 2 + j * 8 + cq) = make_float2(o[j][2], o[j][3]);
-          }
-          if ((lane & 3) == 0) {
-            if (r0 < Gq) { ws[r0 * ws_head] = run_m[0]; ws[r0 * ws_head + 1] = run_l[0]; }
-            if (r0 + 8 < Gq) { ws[(r0 + 8) * ws_head] = run_m[1]; ws[(r0 + 8) * ws_head + 1] = run_l[1]; }
+          for (int j = 0; j < 2; ++j) {
+            const int h = cq + j;
+            if (h < Gq) {
+              float *wh = ws + (size_t)h * ws_head;
+#pragma unroll
+              for (int mt = 0; mt < KK; ++mt) {
+                wh[2 + mt * 16 + r0] = o[mt][j];
+                wh[2 + mt * 16 + r0 + 8] = o[mt][2 + j];
+              }
+              if (r0 == 0) { wh[0] = run_m[j]; wh[1] = run_l[j]; }
+            }
           }
         }
         pos += n_units;
@@ -1228,8 +1221,8 @@ extern "C" int ocrb_chain_plan_build(const ocrb_chain_op *ops, int32_t n, int32_
       const ocrb_chain_attention &a = op.att;
       OCRB_REQUIRE(a.qkv && a.k_cache && a.v_cache && a.block_table && a.ctx_len && a.cosT && a.sinT && a.out && a.split_ws,
                    "chain_plan_build: null pointer in attention op %d", g);
-      OCRB_REQUIRE(a.hd == CH_HD && a.n_kv > 0 && a.n_q % a.n_kv == 0 && a.n_q / a.n_kv <= 16,
-                   "chain_plan_build: fused attention needs hd 128 and <= 16 query heads per KV head (op %d)", g);
+      OCRB_REQUIRE(a.hd == CH_HD && a.n_kv > 0 && a.n_q % a.n_kv == 0 && a.n_q / a.n_kv <= 8,
+                   "chain_plan_build: fused attention needs hd 128 and <= 8 query heads per KV head (op %d)", g);
       OCRB_REQUIRE(a.page_size > 0 && a.page_size % 16 == 0 && a.n_splits > 0 && a.n_cache_pages > 0,
                    "chain_plan_build: page_size must be a multiple of 16 (op %d)", g);
       OCRB_REQUIRE(a.ldqkv % 2 == 0 && a.ldo % 4 == 0 && ((uintptr_t)a.qkv & 3) == 0 && ((uintptr_t)a.out & 7) == 0 &&

@@ -5,8 +5,11 @@
 // config over 28 layers).  Layout and schedule:
 //   * cache layout [page][kv head][16 tokens][hd]: the K (or V) rows a 16-key tile needs are ONE contiguous 4 KiB block,
 //     fetched by the TMA unit (cp.async.bulk.tensor, two [16 x 64]-column boxes, 128B swizzle) straight into shared memory;
-//   * work item = (sequence, KV head, range of `chunk` keys); the G query heads that share the KV head are the 16 rows
-//     of mma.sync.m16n8k16 tiles (rows >= G are zero);
+//   * work item = (sequence, KV head, range of `chunk` keys).  The products are computed TRANSPOSED so that the wide side
+//     of mma.sync.m16n8k16 (M = 16) is the 16 keys of a tile and the narrow side (N = 8) the G <= 8 query heads that
+//     share the KV head: S^T[key][head] = K . Q^T and O^T[dim][head] += V^T . P^T -- 16 mma per 16-key tile for G <= 8
+//     (32 with the heads on the M side, 9 of 16 rows dead at G = 7); P^T reaches its operand layout through two
+//     movmatrix transposes;
 //   * every WARP is an independent flash-decoding worker: it owns whole work items (item = warp * grid + cta, then
 //     strided), streams their 16-key tiles through its private shared-memory ring (lane 0 issues the TMA loads, an
 //     mbarrier per slot counts the bytes), keeps the running (max, sum, O[16 x hd]) in registers and writes one fp32
@@ -67,7 +70,14 @@ struct DaSmem {
   static constexpr size_t BYTES = 1024 + RING_BYTES + DA_WARPS * Q_BYTES + DA_WARPS * DA_STAGES * 8;
 };
 
-template <int HD, int DA_WARPS, int DA_STAGES>
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
+// NT = 8-head column tiles of the transposed products (1: up to 8 query heads per KV head, 2: up to 16)
+template <int HD, int DA_WARPS, int DA_STAGES, int NT>
 __global__ void __launch_bounds__(DA_WARPS * 32, 1)
 decode_attn_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                    const bf16 *__restrict__ qkv, long long ldqkv, bf16 *__restrict__ k_cache, bf16 *__restrict__ v_cache,
@@ -76,7 +86,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
                    float scale, float *__restrict__ split_ws, int n_splits, int chunk) {
   using SM = DaSmem<HD, DA_WARPS, DA_STAGES>;
   constexpr int QP = SM::QPITCH;
-  constexpr int NJ = HD / 8;                                  // 8-wide output column tiles of O
+  constexpr int KK = HD / 16;                                 // k-steps of K . Q^T = 16-dim row tiles of O^T
   extern __shared__ uint8_t da_smem_raw[];
   uint8_t *smem = da_smem_raw + ((1024u - (smem_u32(da_smem_raw) & 1023u)) & 1023u);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -144,18 +154,60 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
     if (!waited) { pdl_wait(); waited = true; }               // qkv comes from the preceding skinny GEMM
     const bf16 *row = qkv + (size_t)b * ldqkv;
     const bf16 *c = cosT + (size_t)b * HD, *s_ = sinT + (size_t)b * HD;
-    for (int i = lane; i < G * HD; i += 32) {
-      const int g = i / HD, d = i % HD;
-      sQ[g * QP + d] = __float2bfloat16_rn(rope_elem_bf16(row + (size_t)(kvh * G + g) * HD, d, HD, c, s_));
+    // mRoPE of the G query heads into the staging tile, 8 elements (16 bytes) per lane and step: the element chunk, its
+    // rotate-half partner chunk (+- HD / 2) and the cos / sin chunks of up to 4 steps are fetched together -- one L2 round trip
+    // per item instead of one per element (the scalar loop cost ~3 us of a ~7 us item).  Same arithmetic as rope_elem_bf16.
+    {
+      constexpr int CH = HD / 8;                               // 16-byte chunks per head
+      for (int i0 = 0; i0 < G * CH; i0 += 4 * 32) {
+        uint4 xv[4], ov[4], cv[4], sv4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = i0 + u * 32 + lane;
+          if (idx < G * CH) {
+            const int g = idx / CH, ch = idx - g * CH;
+            const bf16 *qh = row + (size_t)(kvh * G + g) * HD;
+            xv[u] = __ldg(reinterpret_cast<const uint4 *>(qh + ch * 8));
+            ov[u] = __ldg(reinterpret_cast<const uint4 *>(qh + (ch ^ (CH / 2)) * 8));
+            cv[u] = __ldg(reinterpret_cast<const uint4 *>(c + ch * 8));
+            sv4[u] = __ldg(reinterpret_cast<const uint4 *>(s_ + ch * 8));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = i0 + u * 32 + lane;
+          if (idx < G * CH) {
+            const int g = idx / CH, ch = idx - g * CH;
+            const float sgn = (ch < CH / 2) ? -1.f : 1.f;
+            const bf16 *xe = reinterpret_cast<const bf16 *>(&xv[u]), *oe = reinterpret_cast<const bf16 *>(&ov[u]);
+            const bf16 *ce = reinterpret_cast<const bf16 *>(&cv[u]), *se = reinterpret_cast<const bf16 *>(&sv4[u]);
+            uint4 outv;
+            bf16 *re = reinterpret_cast<bf16 *>(&outv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float t = bf16_round(__bfloat162float(xe[e]) * __bfloat162float(ce[e]));
+              const float uu = bf16_round(sgn * __bfloat162float(oe[e]) * __bfloat162float(se[e]));
+              re[e] = __float2bfloat16_rn(bf16_round(t + uu));
+            }
+            *reinterpret_cast<uint4 *>(sQ + g * QP + ch * 8) = outv;
+          }
+        }
+      }
     }
     __syncwarp();
     uint32_t qf[HD / 16][4];
 #pragma unroll
     for (int kk = 0; kk < HD / 16; ++kk) ldmatrix_x4(qf[kk], smem_u32(sQ + ((m & 1) * 8 + l8) * QP + kk * 16 + (m >> 1) * 8));
-    float o[NJ][4];
+    // transposed accumulators: o[mt][nt] = O^T tile of dims mt*16 .. +15 x heads nt*8 .. +7
+    float o[KK][NT][4];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-    float run_m[2] = {-INFINITY, -INFINITY}, run_l[2] = {0.f, 0.f};
+    for (int mt = 0; mt < KK; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f;
+    // running max / sum of the heads this lane sees: head = nt * 8 + cq + j (replicated over the 8 lanes with the same cq)
+    float run_m[NT][2], run_l[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { run_m[nt][0] = run_m[nt][1] = -INFINITY; run_l[nt][0] = run_l[nt][1] = 0.f; }
 
     for (int i = 0; i < n_tiles; ++i) {
       const int s = i % DA_STAGES;
@@ -181,72 +233,73 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
         }
         __syncwarp();
       }
-      // ---- S = Q.K^T for the 16 keys of the tile (two 8-key column tiles) ----
-      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      // ---- S^T[16 keys][heads] = K . Q^T: the K tile is the M side, the heads the N side ----
+      float acc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
       {
         const int kr = (m >> 1) * 8 + l8;                     // key row this lane addresses
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
+        for (int kk = 0; kk < KK; ++kk) {
           uint32_t bb[4];
           const int ch = (kk & 3) * 2 + (m & 1);              // 16-byte chunk inside the 64-dim atom
           ldmatrix_x4(bb, sk + (kk >> 2) * SM::ATOM_BYTES + kr * 128 + ((ch ^ (kr & 7)) << 4));
-          mma_bf16_16816(acc[0], qf[kk], bb[0], bb[1]);
-          mma_bf16_16816(acc[1], qf[kk], bb[2], bb[3]);
+          // bb = (keys 0-7, dims 0-7), (keys 0-7, dims 8-15), (keys 8-15, dims 0-7), (keys 8-15, dims 8-15) of this k-step:
+          // as an A operand the middle two swap
+          const uint32_t ka[4] = {bb[0], bb[2], bb[1], bb[3]};
+          mma_bf16_16816(acc[0], ka, qf[kk][0], qf[kk][2]);   // heads 0-7: rows 0-7 of the Q tile
+          if (NT > 1) mma_bf16_16816(acc[NT - 1], ka, qf[kk][1], qf[kk][3]);
         }
       }
-      // ---- online softmax: this thread holds rows r0 (e = 0, 1) and r0 + 8 (e = 2, 3), keys j * 8 + cq + (e & 1) ----
-      float tmax[2] = {-INFINITY, -INFINITY};
+      // ---- online softmax per head: this thread holds keys r0 (e = 0, 1) and r0 + 8 (e = 2, 3) of heads nt*8 + cq + (e & 1) ----
+      const bool ok0 = key0 + r0 < total, ok1 = key0 + r0 + 8 < total;
+      uint32_t pb[NT][2];
+      bool moved = false;
+      float corr[NT][2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int nt = 0; nt < NT; ++nt) {
+        float tmax[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          acc[nt][j] = ok0 ? acc[nt][j] * scale : -INFINITY;
+          acc[nt][2 + j] = ok1 ? acc[nt][2 + j] * scale : -INFINITY;
+          tmax[j] = fmaxf(acc[nt][j], acc[nt][2 + j]);
+          tmax[j] = fmaxf(tmax[j], __shfl_xor_sync(0xffffffffu, tmax[j], 4));
+          tmax[j] = fmaxf(tmax[j], __shfl_xor_sync(0xffffffffu, tmax[j], 8));
+          tmax[j] = fmaxf(tmax[j], __shfl_xor_sync(0xffffffffu, tmax[j], 16));
+          const float mn = fmaxf(run_m[nt][j], tmax[j]);      // finite: every processed tile has a live key
+          corr[nt][j] = __expf(run_m[nt][j] - mn);            // exp(-inf) = 0 on the first tile
+          run_m[nt][j] = mn;
+          run_l[nt][j] *= corr[nt][j];
+          moved |= corr[nt][j] != 1.0f;
+        }
+        float pv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const bool ok = key0 + j * 8 + cq + (e & 1) < total;
-          acc[j][e] = ok ? acc[j][e] * scale : -INFINITY;
-          tmax[e >> 1] = fmaxf(tmax[e >> 1], acc[j][e]);
+          pv[e] = __expf(acc[nt][e] - run_m[nt][e & 1]);
+          run_l[nt][e & 1] += pv[e];
         }
-      float corr[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        tmax[h] = fmaxf(tmax[h], __shfl_xor_sync(0xffffffffu, tmax[h], 1));
-        tmax[h] = fmaxf(tmax[h], __shfl_xor_sync(0xffffffffu, tmax[h], 2));
-        const float mn = fmaxf(run_m[h], tmax[h]);            // finite: every processed tile has a live key
-        corr[h] = __expf(run_m[h] - mn);                      // exp(-inf) = 0 on the first tile
-        run_m[h] = mn;
-        run_l[h] *= corr[h];
+        // P^T as the B operand of O^T += V^T . P^T needs (key pair, head) per lane: transpose the two 8 x 8 blocks
+        pb[nt][0] = movmatrix_trans(pack_bf16(pv[0], pv[1]));
+        pb[nt][1] = movmatrix_trans(pack_bf16(pv[2], pv[3]));
       }
-      uint32_t pa[4];
+      // ---- O^T = O^T * corr + V^T . P^T (the scaling is skipped when no head of the warp moved its maximum) ----
       {
-        float pv[2][4];
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            pv[j][e] = __expf(acc[j][e] - run_m[e >> 1]);
-            run_l[e >> 1] += pv[j][e];
-          }
-        pa[0] = pack_bf16(pv[0][0], pv[0][1]);
-        pa[1] = pack_bf16(pv[0][2], pv[0][3]);
-        pa[2] = pack_bf16(pv[1][0], pv[1][1]);
-        pa[3] = pack_bf16(pv[1][2], pv[1][3]);
-      }
-      // ---- O = O * corr + P.V (the scaling is skipped when no row of the warp moved its maximum: corr == 1 exactly) ----
-      {
-        const bool rescale = __any_sync(0xffffffffu, corr[0] != 1.0f || corr[1] != 1.0f);
+        const bool rescale = __any_sync(0xffffffffu, moved);
         const int vr = (m & 1) * 8 + l8;                      // key row this lane addresses
 #pragma unroll
-        for (int jj = 0; jj < HD / 16; ++jj) {
+        for (int jj = 0; jj < KK; ++jj) {
           uint32_t bb[4];
           const int ch = (jj & 3) * 2 + (m >> 1);
           ldmatrix_x4_trans(bb, sv + (jj >> 2) * SM::ATOM_BYTES + vr * 128 + ((ch ^ (vr & 7)) << 4));
-          if (rescale) {
+          // transposed 8 x 8 blocks: (dims 0-7, keys 0-7), (dims 0-7, keys 8-15), (dims 8-15, keys 0-7), (dims 8-15, keys 8-15)
+          const uint32_t va[4] = {bb[0], bb[2], bb[1], bb[3]};
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              float (&oo)[4] = o[jj * 2 + t];
-              oo[0] *= corr[0]; oo[1] *= corr[0]; oo[2] *= corr[1]; oo[3] *= corr[1];
-            }
+          for (int nt = 0; nt < NT; ++nt) {
+            float (&oo)[4] = o[jj][nt];
+            if (rescale) { oo[0] *= corr[nt][0]; oo[1] *= corr[nt][1]; oo[2] *= corr[nt][0]; oo[3] *= corr[nt][1]; }
+            mma_bf16_16816(oo, va, pb[nt][0], pb[nt][1]);
           }
-          mma_bf16_16816(o[jj * 2], pa, bb[0], bb[1]);
-          mma_bf16_16816(o[jj * 2 + 1], pa, bb[2], bb[3]);
         }
       }
       __syncwarp();                      // every lane is done with this ring slot
@@ -254,19 +307,28 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
     }
     // ---- one fp32 partial (max, sum, o[hd]) per head of this item, straight from the registers ----
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      run_l[h] += __shfl_xor_sync(0xffffffffu, run_l[h], 1);
-      run_l[h] += __shfl_xor_sync(0xffffffffu, run_l[h], 2);
-    }
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      if (r0 < G) *reinterpret_cast<float2 *>(ws + r0 * ws_head + 2 + j * 8 + cq) = make_float2(o[j][0], o[j][1]);
-      if (r0 + 8 < G) *reinterpret_cast<float2 *>(ws + (r0 + 8) * ws_head + 2 + j * 8 + cq) = make_float2(o[j][2], o[j][3]);
-    }
-    if ((lane & 3) == 0) {
-      if (r0 < G) { ws[r0 * ws_head] = run_m[0]; ws[r0 * ws_head + 1] = run_l[0]; }
-      if (r0 + 8 < G) { ws[(r0 + 8) * ws_head] = run_m[1]; ws[(r0 + 8) * ws_head + 1] = run_l[1]; }
-    }
+      for (int j = 0; j < 2; ++j) {
+        run_l[nt][j] += __shfl_xor_sync(0xffffffffu, run_l[nt][j], 4);
+        run_l[nt][j] += __shfl_xor_sync(0xffffffffu, run_l[nt][j], 8);
+        run_l[nt][j] += __shfl_xor_sync(0xffffffffu, run_l[nt][j], 16);
+      }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int h = nt * 8 + cq + j;                        // head of this lane's columns
+        if (h < G) {
+          float *wh = ws + (size_t)h * ws_head;
+#pragma unroll
+          for (int mt = 0; mt < KK; ++mt) {
+            wh[2 + mt * 16 + r0] = o[mt][nt][j];
+            wh[2 + mt * 16 + r0 + 8] = o[mt][nt][2 + j];
+          }
+          if (r0 == 0) { wh[0] = run_m[nt][j]; wh[1] = run_l[nt][j]; }
+        }
+      }
     __syncwarp();                        // the Q staging rows are rewritten by the next item
   }
   if (!waited) pdl_wait();               // a worker without items still has to honour the dependency before it exits
@@ -299,7 +361,7 @@ static int make_cache_map(CUtensorMap *m, const void *cache, long long rows, int
   return make_tensor_map_bf16(m, cache, rows, hd, hd, DA_TILE);
 }
 
-template <int HD, int WARPS, int STAGES>
+template <int HD, int WARPS, int STAGES, int NT>
 static int launch_decode_attn(const CUtensorMap &mk, const CUtensorMap &mv, const bf16 *qkv, long long ldqkv, bf16 *kc, bf16 *vc,
                               const int32_t *bt, int max_pages, const int32_t *ctx_len, int B, int page_size, int n_q, int n_kv,
                               const bf16 *cosT, const bf16 *sinT, float scale, float *split_ws, int n_splits, int chunk,
@@ -309,7 +371,7 @@ static int launch_decode_attn(const CUtensorMap &mk, const CUtensorMap &mv, cons
   static bool attr_set = false;
   static int n_sm = 0;
   if (!attr_set) {
-    OCRB_CUDA(cudaFuncSetAttribute(decode_attn_kernel<HD, WARPS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OCRB_CUDA(cudaFuncSetAttribute(decode_attn_kernel<HD, WARPS, STAGES, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -318,7 +380,7 @@ static int launch_decode_attn(const CUtensorMap &mk, const CUtensorMap &mv, cons
   }
   const long long items = (long long)B * n_kv * n_splits;
   const int grid = (int)(items < n_sm ? items : n_sm);       // persistent: one CTA of independent warps per SM
-  OCRB_CUDA(launch_pdl_bit(2, decode_attn_kernel<HD, WARPS, STAGES>, dim3(grid), dim3(WARPS * 32), smem, st, mk, mv, qkv, ldqkv,
+  OCRB_CUDA(launch_pdl_bit(2, decode_attn_kernel<HD, WARPS, STAGES, NT>, dim3(grid), dim3(WARPS * 32), smem, st, mk, mv, qkv, ldqkv,
                            kc, vc, bt, max_pages, ctx_len, B, page_size, n_q, n_kv, cosT, sinT, scale, split_ws, n_splits, chunk));
   return check_launch("decode_attn_kernel");
 }
@@ -337,6 +399,8 @@ extern "C" int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cac
   OCRB_REQUIRE(B > 0 && n_kv > 0 && n_q % n_kv == 0 && n_q / n_kv <= DA_MAXG && (hd == 64 || hd == 128) && n_splits > 0,
                "decode_attention: needs n_q / n_kv <= 16 query heads per KV head and hd of 64 or 128");
   OCRB_REQUIRE(page_size > 0 && page_size % DA_TILE == 0, "decode_attention: page_size must be a multiple of 16");
+  OCRB_REQUIRE(((uintptr_t)qkv & 15) == 0 && ldqkv % 8 == 0 && ((uintptr_t)cosT & 15) == 0 && ((uintptr_t)sinT & 15) == 0,
+               "decode_attention: qkv rows and the rope tables must be 16-byte aligned");
   OCRB_REQUIRE(n_cache_pages > 0 && ((uintptr_t)k_cache & 15) == 0 && ((uintptr_t)v_cache & 15) == 0,
                "decode_attention: cache pointers must be 16-byte aligned, n_cache_pages > 0");
   const int max_ctx = max_pages * page_size;
@@ -358,14 +422,17 @@ extern "C" int ocrb_decode_attention(const void *qkv, int64_t ldqkv, void *k_cac
   }
   const int cfg = cfg_env ? cfg_env : (((long long)B * n_kv * n_splits >= 3LL * 148 * 6) ? 82 : 64);
 #define DA_LAUNCH(HD_, W_, S_)                                                                                              \
-  launch_decode_attn<HD_, W_, S_>(mk, mv, (const bf16 *)qkv, (long long)ldqkv, (bf16 *)k_cache, (bf16 *)v_cache, block_table, \
+  (n_q / n_kv > 8 ? DA_LAUNCH_NT(HD_, W_, S_, 2) : DA_LAUNCH_NT(HD_, W_, S_, 1))
+#define DA_LAUNCH_NT(HD_, W_, S_, NT_)                                                                                      \
+  launch_decode_attn<HD_, W_, S_, NT_>(mk, mv, (const bf16 *)qkv, (long long)ldqkv, (bf16 *)k_cache, (bf16 *)v_cache, block_table, \
                                   (int)max_pages, ctx_len, (int)B, (int)page_size, (int)n_q, (int)n_kv, (const bf16 *)cosT,    \
                                   (const bf16 *)sinT, scale, split_ws, (int)n_splits, chunk, st)
   if (hd == 128)
-    rc = (cfg == 82) ? DA_LAUNCH(128, 8, 2) : DA_LAUNCH(128, 6, 4);
+    rc = (cfg == 82) ? DA_LAUNCH(128, 8, 2) : ((cfg == 102) ? DA_LAUNCH(128, 10, 2) : DA_LAUNCH(128, 6, 4));
   else
     rc = DA_LAUNCH(64, 8, 4);
 #undef DA_LAUNCH
+#undef DA_LAUNCH_NT
   if (rc) return rc;
   OCRB_CUDA(launch_pdl_bit(4, decode_attn_combine_kernel, dim3(n_q, B), dim3(hd), 0, st, (const float *)split_ws, (int)n_q,
                            (int)n_splits, (int)hd, (bf16 *)out, (long long)ldo));

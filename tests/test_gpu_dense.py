@@ -495,7 +495,7 @@ def test_decode_attention_paged(L, n_splits, max_pages, nq, nkv, hd, ctx):
 @pytest.mark.parametrize("n_splits,max_pages,nq,nkv,ctx", [
     (6, 20, 28, 4, [100, 37, 250]), (1, 20, 28, 4, [100, 37, 250]), (3, 24, 28, 4, [100, 37, 250]), (4, 20, 4, 2, [100, 37, 250]),
     (20, 20, 28, 4, [0, 15, 16, 17, 319]), (17, 132, 28, 4, [1036, 1547, 2111, 127, 128]), (9, 132, 64, 8, [1036, 2000]),
-    (5, 40, 16, 1, [639, 1, 63, 64, 65, 300, 301]), (13, 97, 28, 4, [1036 + 7 * i for i in range(24)]),
+    (5, 40, 8, 1, [639, 1, 63, 64, 65, 300, 301]), (13, 97, 28, 4, [1036 + 7 * i for i in range(24)]),
     (13, 97, 28, 4, [1100 + 3 * i for i in range(96)])])
 def test_plan_attention_equals_decode_attention(L, chws, n_splits, max_pages, nq, nkv, ctx):
     """The attention op of a plan (csrc/chain.cu) = ocrb_decode_attention bit for bit: output, cache append and all."""
