@@ -26,6 +26,8 @@
 #include "skinny_common.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <mutex>
 #include <vector>
 
 namespace ocrb {
@@ -1143,6 +1145,11 @@ static int ch_fill_linear(ChainDesc &d, const ocrb_chain_linear &l, int g, int B
 struct PlanHeader { uint32_t magic; int32_t n, B, has_attn; int32_t pad[12]; };     // 64 bytes in front of the descriptors
 constexpr uint32_t CH_PLAN_MAGIC = 0x0c4a1b20u;
 
+// plans built in this process: device pointer -> (ops, rows), so that a run with the wrong count or batch is refused
+// instead of walking garbage descriptors
+static std::mutex g_plan_mu;
+static std::map<const void *, std::pair<int, int>> g_plans;
+
 }  // namespace ocrb
 
 using namespace ocrb;
@@ -1272,12 +1279,22 @@ extern "C" int ocrb_chain_plan_build(const ocrb_chain_op *ops, int32_t n, int32_
   cudaStream_t st = (cudaStream_t)stream;
   OCRB_CUDA(cudaMemcpyAsync(plan, host.data(), host.size(), cudaMemcpyHostToDevice, st));
   OCRB_CUDA(cudaStreamSynchronize(st));
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    g_plans[plan] = std::make_pair((int)n, (int)B);
+  }
   return OCRB_OK;
 }
 
 extern "C" int ocrb_chain_plan_run(const void *plan, int32_t n, int32_t B, void *workspace, void *stream) {
   OCRB_REQUIRE(plan && workspace, "chain_plan_run: null pointer");
   OCRB_REQUIRE(n >= 1 && n <= CH_MAX_OPS && B >= 1 && B <= SK_MAXBP, "chain_plan_run: bad n / B");
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    auto it = g_plans.find(plan);
+    OCRB_REQUIRE(it != g_plans.end() && it->second.first == n && it->second.second == B,
+                 "chain_plan_run: not a plan built by ocrb_chain_plan_build for %d ops and %d rows", n, B);
+  }
   const int grid = ch_sm_count();
   const ChainWs w = ch_carve(workspace);
   ChainCtl ctl;

@@ -34,6 +34,15 @@ plain = eng.read_batch(batch, max_new_tokens=12, use_graph=False)
 assert graph == plain, "CUDA-graph replay and step-by-step decode disagree"
 alone = eng.read_batch(outs[1], max_new_tokens=12)[0]
 assert alone == graph[1], "batch invariance"
+# the opt-in persistent step (csrc/chain.cu): whole step as one plan launch, then chains with attention kernels between them
+for fuse in (True, False):
+    vlm.CHAIN_MAX_B, vlm.CHAIN_FUSE_ATTN = 128, fuse
+    eng._states.clear()
+    fused = eng.read_batch(batch, max_new_tokens=12)
+    assert fused == eng.read_batch(batch, max_new_tokens=12, use_graph=False), "persistent step: graph vs step-by-step"
+    assert [t[:3] for t in fused] == [t[:3] for t in graph], "persistent step diverges from the launch sequence at once"
+vlm.CHAIN_MAX_B = 0
+eng._states.clear()
 # the long-sequence attention kernel on its own (the tiny config's sequences are short)
 for hd, nq, nkv, causal, lens in ((80, 4, 4, 0, [300, 130]), (128, 4, 2, 1, [257, 64])):
     T = sum(lens)
