@@ -659,20 +659,58 @@ warp_affine_cubic_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ 
   int sx = X >> 5, sy = Y >> 5;
   sx = min(max(sx, -32768), 32767);
   sy = min(max(sy, -32768), 32767);
-  const int16_t *wt = g_cubic_itab + (((Y & 31) * 32 + (X & 31)) << 4);
-  int xs[4], ys[4];
+  // the 16 fixed-point weights of this sub-pixel position: two 16-byte loads (the table row is 32-byte aligned)
+  const uint4 *wt4 = reinterpret_cast<const uint4 *>(g_cubic_itab + (((Y & 31) * 32 + (X & 31)) << 4));
+  const uint4 wa = wt4[0], wb = wt4[1];
+  const uint32_t wpk[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};      // wpk[i] = weights 2i (low), 2i + 1 (high)
+  auto wgt = [&](int i) -> int { return (int)(short)((i & 1) ? (wpk[i >> 1] >> 16) : (wpk[i >> 1] & 0xffffu)); };
+  int ys[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    xs[k] = min(max(sx - 1 + k, 0), W - 1);
-    ys[k] = min(max(sy - 1 + k, 0), H - 1);
+  for (int k = 0; k < 4; ++k) ys[k] = min(max(sy - 1 + k, 0), H - 1);
+  // Interior columns (no clamping in x, and room for the aligned over-read): the 4 taps x C channels of a source row
+  // are 4C contiguous bytes at an arbitrary alignment -- fetched as aligned 32-bit words and funnel-shifted into place
+  // (C = 3: 4 loads per row instead of 12 byte loads; the same integers enter the same sums).
+  const int margin = (C == 3) ? 1 : 3;
+  if (sx - 1 >= 0 && sx + 2 + margin <= W - 1 && (C == 1 || C == 3)) {
+    int acc[3] = {0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const size_t off = ((size_t)ys[ky] * W + (sx - 1)) * C + img_off;
+      const uint32_t *wp = reinterpret_cast<const uint32_t *>(src + (off & ~(size_t)3));
+      const uint32_t sh = (uint32_t)(off & 3) * 8;
+      if (C == 3) {
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+        const uint32_t b[3] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh)};
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int j = kx * 3 + c;
+            acc[c] += wgt(ky * 4 + kx) * (int)((b[j >> 2] >> ((j & 3) * 8)) & 0xffu);
+          }
+      } else {
+        const uint32_t w0 = wp[0], w1 = wp[1];
+        const uint32_t b0 = __funnelshift_r(w0, w1, sh);
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) acc[0] += wgt(ky * 4 + kx) * (int)((b0 >> (kx * 8)) & 0xffu);
+      }
+    }
+    for (int c = 0; c < C; ++c) {
+      const int v = (acc[c] + 16384) >> 15;
+      o[c] = (uint8_t)min(max(v, 0), 255);
+    }
+    return;
   }
+  int xs[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) xs[k] = min(max(sx - 1 + k, 0), W - 1);
   for (int c = 0; c < C; ++c) {
     int acc = 0;
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 4; ++kx)
-        acc += (int)wt[ky * 4 + kx] * (int)im[((size_t)ys[ky] * W + xs[kx]) * C + c];
+        acc += wgt(ky * 4 + kx) * (int)im[((size_t)ys[ky] * W + xs[kx]) * C + c];
     int v = (acc + 16384) >> 15;
     o[c] = (uint8_t)min(max(v, 0), 255);
   }
