@@ -16,6 +16,7 @@
 // M/N/K tails are handled by TMA zero fill on loads and predicated stores.
 #include "tc_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace ocrb {
@@ -368,6 +369,8 @@ extern "C" int ocrb_gemm_bf16(const void *A, int64_t lda, const void *W, int64_t
   p.epilogue = epilogue;
   // Tile width: 256 whenever it divides N and the grid still fills the machine.  (Choosing 128 to shave the last
   // partial wave was measured slower: 128-wide tiles re-read the activation panel twice as often.)
+  // (128-wide tiles for the N = 1280 shapes -- 940 half tiles = 6.4 half waves instead of 470 tiles = 3.2 waves -- re-measured
+  // with eight epilogue warps: proj 46.6 -> 54.1 us, down 95.8 -> 123.5 us; the activation panel is re-read twice as often.)
   const bool wide = (N % 256 == 0) && ((long long)cdiv(N, 256) * cdiv(M, GM_BM) >= 148);
   const int BN = wide ? 256 : 128;
   CUtensorMap ma, mw;
