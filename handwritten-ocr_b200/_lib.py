@@ -50,6 +50,8 @@ _SIGS = {
     "ocrb_rgb2gray_u8": [_P, _P, _I, _I, _I, _P],
     "ocrb_clahe_u8": [_P, _P, _I, _I, _I, _P, _P],
     "ocrb_adaptive_gauss_thresh_u8": [_P, _P, _I, _I, _I, _P],
+    "ocrb_high_contrast_u8": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "ocrb_binarize_u8": [_P, _P, _I, _I, _I, _I, _P],
     "ocrb_sharpen3x3_u8": [_P, _P, _I, _I, _I, _I, _P],
     "ocrb_remove_lines_mask_u8": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "ocrb_inpaint_telea_u8": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

@@ -36,21 +36,27 @@ def to_gray(x: torch.Tensor) -> torch.Tensor:
 
 
 def high_contrast(x: torch.Tensor) -> torch.Tensor:
-    """tools._apply_high_contrast (tools.py:503-516): gray + CLAHE(3.0, 8x8) -> "L"."""
-    g = to_gray(x)
-    n, H, W = g.shape
-    out = torch.empty_like(g)
-    lut = torch.empty((n, 64, 256), dtype=torch.uint8, device=g.device)
-    _lib.call("ocrb_clahe_u8", _lib.ptr(g), _lib.ptr(out), n, H, W, _lib.ptr(lut), _lib.stream_ptr())
+    """tools._apply_high_contrast (tools.py:503-516): gray + CLAHE(3.0, 8x8) -> "L".  One C-ABI call; for RGB pages the
+    gray conversion rides on the tile-histogram pass."""
+    _check(x)
+    n, H, W = x.shape[:3]
+    C = 3 if x.dim() == 4 else 1
+    out = torch.empty((n, H, W), dtype=torch.uint8, device=x.device)
+    gray = torch.empty_like(out) if C == 3 else None
+    lut = torch.empty((n, 64, 256), dtype=torch.uint8, device=x.device)
+    _lib.call("ocrb_high_contrast_u8", _lib.ptr(x), _lib.ptr(out), _lib.ptr(gray), _lib.ptr(lut), n, H, W, C,
+              _lib.stream_ptr())
     return out
 
 
 def binarize(x: torch.Tensor) -> torch.Tensor:
-    """tools._apply_binarize (tools.py:519-531): gray + adaptive Gaussian threshold 21/10 -> "L"."""
-    g = to_gray(x)
-    n, H, W = g.shape
-    out = torch.empty_like(g)
-    _lib.call("ocrb_adaptive_gauss_thresh_u8", _lib.ptr(g), _lib.ptr(out), n, H, W, _lib.stream_ptr())
+    """tools._apply_binarize (tools.py:519-531): gray + adaptive Gaussian threshold 21/10 -> "L".  One kernel; RGB pages
+    become gray while their tiles are staged."""
+    _check(x)
+    n, H, W = x.shape[:3]
+    C = 3 if x.dim() == 4 else 1
+    out = torch.empty((n, H, W), dtype=torch.uint8, device=x.device)
+    _lib.call("ocrb_binarize_u8", _lib.ptr(x), _lib.ptr(out), n, H, W, C, _lib.stream_ptr())
     return out
 
 

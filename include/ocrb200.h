@@ -59,6 +59,17 @@ int ocrb_rgb2gray_u8(const uint8_t *src_rgb, uint8_t *dst_gray, int32_t n_img, i
 int ocrb_clahe_u8(const uint8_t *src_gray, uint8_t *dst_gray, int32_t n_img, int32_t H, int32_t W,
                   uint8_t *lut_ws, void *stream);
 
+/* tools.py:503-516 (_apply_high_contrast) in one call: RGB (C == 3) or gray (C == 1) page -> CLAHE(3.0,(8,8)) of its gray
+ * version.  For C == 3 the RGB -> gray conversion is fused into the tile-histogram pass (no pass of its own) and the gray
+ * page is left in gray_ws: uint8[n_img*H*W] (ignored for C == 1).  lut_ws: uint8[n_img*64*256]. */
+int ocrb_high_contrast_u8(const uint8_t *src, uint8_t *dst_gray, uint8_t *gray_ws, uint8_t *lut_ws, int32_t n_img,
+                          int32_t H, int32_t W, int32_t C, void *stream);
+
+/* tools.py:519-531 (_apply_binarize) in one call: RGB or gray page -> adaptive Gaussian threshold 21/10 of its gray version;
+ * for C == 3 the gray tile is computed while it is staged into shared memory (no gray page in memory at all). */
+int ocrb_binarize_u8(const uint8_t *src, uint8_t *dst_gray, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                     void *stream);
+
 /* tools.py:527-529 cv2.adaptiveThreshold(gray,255,GAUSSIAN_C,BINARY,21,10) */
 int ocrb_adaptive_gauss_thresh_u8(const uint8_t *src_gray, uint8_t *dst_gray, int32_t n_img,
                                   int32_t H, int32_t W, void *stream);
@@ -99,7 +110,8 @@ int ocrb_denoise_tables_host(int32_t *cbrt_tab, int32_t *lab_yf, int32_t *coef, 
  * rotation matrix about (W//2, H//2).  src has C channels (gray computed on the fly for C=3).
  * out_angle: double[n_img] (NaN when <= 100 dark pixels: image must be left unchanged),
  * out_M: double[n_img*6] forward matrix of cv2.getRotationMatrix2D.
- * ext_ws: int32[n_img*H*3].  hull_ws: int32[n_img*(4*H+8)*2]. */
+ * ext_ws: int32[n_img*H*3].  hull_ws: int32[n_img*(4*H+8)*2] (only touched for H > ~2600, where the hull tree does not
+ * fit in shared memory). */
 int ocrb_deskew_angle(const uint8_t *src, int32_t n_img, int32_t H, int32_t W, int32_t C,
                       double *out_angle, double *out_M, int32_t *ext_ws, int32_t *hull_ws,
                       void *stream);

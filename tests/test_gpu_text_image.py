@@ -257,3 +257,33 @@ def test_vectorised_paths_small_widths(pp):
     for (h, w) in [(33, 72), (70, 130), (8, 8), (40, 64)]:
         a = rng.integers(0, 256, (h, w), dtype=np.uint8)
         assert np.array_equal(pp.binarize(pp.to_device(a))[0].cpu().numpy(), R.adaptive_threshold(a)), (h, w)
+
+
+def test_fused_transforms_full_pages_batched(pp, synth):
+    """Round-2 throughput kernels at page size (RGB -> gray fused into the CLAHE histogram / threshold staging, cell-wise
+    CLAHE apply, packed-lane sharpen, hull tree, dp2a warp): a batch of different pages equals the pages one by one
+    (whose results the golden hashes pin), and the one-call transforms equal the two-pass C-ABI route
+    (ocrb_rgb2gray_u8 -> ocrb_clahe_u8 / ocrb_adaptive_gauss_thresh_u8)."""
+    from handwritten_ocr_b200 import _lib
+    for (w, h) in [(1024, 768), (768, 1024)]:
+        pages = [synth.page(700 + i, w, h) for i in range(3)]
+        x = pp.to_device(pages)
+        g = pp.to_gray(x)
+        n = x.shape[0]
+        for name in ("high_contrast", "binarize", "sharpen", "deskew"):
+            fn = getattr(pp, name)
+            out = fn(x)
+            for i in range(n):
+                assert torch.equal(out[i], fn(x[i:i + 1].contiguous())[0]), (name, w, h, i)
+            if name in ("high_contrast", "binarize"):
+                assert torch.equal(out, fn(g)), (name, "gray input", w, h)
+        two = torch.empty_like(g)
+        lut = torch.empty((n, 64, 256), dtype=torch.uint8, device=x.device)
+        _lib.call("ocrb_clahe_u8", _lib.ptr(g), _lib.ptr(two), n, h, w, _lib.ptr(lut), _lib.stream_ptr())
+        assert torch.equal(two, pp.high_contrast(x))
+        _lib.call("ocrb_adaptive_gauss_thresh_u8", _lib.ptr(g), _lib.ptr(two), n, h, w, _lib.stream_ptr())
+        assert torch.equal(two, pp.binarize(x))
+        # oracle on one page of the batch (numpy, a few seconds)
+        assert np.array_equal(pp.high_contrast(x)[2].cpu().numpy(), R.clahe(R.rgb2gray(pages[2])))
+        assert np.array_equal(pp.sharpen(x)[1].cpu().numpy(), R.sharpen(pages[1]))
+        assert np.array_equal(pp.deskew(x)[1].cpu().numpy(), R.deskew(pages[1]))
