@@ -88,6 +88,107 @@ allreduce_residual_kernel(ArPeers peers, int world, int rank, int *__restrict__ 
   if (tid == 0) seq[cta] = k;
 }
 
+// ───────────── vocab-split lm_head: greedy token by a (max, lowest index) exchange instead of gathering the logits ─────────────
+// HF's plan leaves lm_head "colwise_rep" (every rank ends up with all logits).  A greedy step only needs the arg max: each
+// rank reduces its own [B, V / world] slice to one (value, global index) pair per sequence, publishes it in a peer-mapped
+// slot, and reads the other ranks' pairs -- 8 bytes per rank and sequence instead of an all-gather of B x V bf16 followed
+// by an arg max over the full vocabulary.  Equal values resolve to the LOWEST global index, which is what the first-index
+// arg max over the concatenated logits returns, so the tokens equal the gather route's bit for bit and are identical on
+// every rank.  Same flag protocol and two-slot argument as the all-reduce above (one CTA per sequence, counters in seq).
+struct AmPeers {
+  const unsigned long long *pairs[AR_MAX_WORLD];   // peer r's pair slots [2][max_rows]
+  int *flags[AR_MAX_WORLD];                        // peer r's flag array [max_rows][AR_MAX_WORLD]
+};
+
+__global__ void __launch_bounds__(512)
+tp_argmax_step_kernel(AmPeers peers, int world, int rank, int *__restrict__ seq, int max_rows,
+                      const bf16 *__restrict__ logits, long long ldl, int vl, int eos, int pad, int max_new,
+                      int32_t *__restrict__ out_tokens, int32_t *__restrict__ next_ids, int32_t *__restrict__ finished,
+                      int32_t *__restrict__ ctx_len, const int32_t *__restrict__ step, int advance_ctx) {
+  __shared__ float s_val[16];
+  __shared__ int s_idx[16];
+  __shared__ unsigned long long s_pair[AR_MAX_WORLD];
+  __shared__ int s_k;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const bf16 *row = logits + (size_t)b * ldl;
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  const int nvec = vl >> 3;
+  for (int v = tid; v < nvec; v += 512) {
+    const uint4 raw = *reinterpret_cast<const uint4 *>(row + v * 8);
+    const bf16 *e = reinterpret_cast<const bf16 *>(&raw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float f = __bfloat162float(e[k]);
+      if (f > best) { best = f; best_i = v * 8 + k; }  // ascending index within a thread: first max kept
+    }
+  }
+  for (int i = (nvec << 3) + tid; i < vl; i += 512) {
+    const float f = __bfloat162float(row[i]);
+    if (f > best || (f == best && i < best_i)) { best = f; best_i = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = best_i; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 1; k < 16; ++k)
+      if (s_val[k] > best || (s_val[k] == best && s_idx[k] < best_i)) { best = s_val[k]; best_i = s_idx[k]; }
+    const int k = seq[b] + 1;
+    s_k = k;
+    // a slice without any finite-comparable value keeps best_i = 0x7fffffff, which loses every tie
+    const unsigned gi = best_i == 0x7fffffff ? 0x7fffffffu : (unsigned)(rank * vl + best_i);
+    const unsigned long long pr = ((unsigned long long)__float_as_uint(best) << 32) | gi;
+    unsigned long long *mine = const_cast<unsigned long long *>(peers.pairs[rank]) + (size_t)(k & 1) * max_rows + b;
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(mine), "l"(pr) : "memory");
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int k = s_k;
+  if (tid < world) {
+    int *dst = peers.flags[tid] + b * AR_MAX_WORLD + rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(k) : "memory");
+    const int *src = peers.flags[rank] + b * AR_MAX_WORLD + tid;
+    int v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+      if (v < k && clock64() - t0 > 60000000000LL) {
+        printf("ocrb tp arg max: rank %d never saw rank %d announce step %d (flag %d)\n", rank, tid, k, v);
+        __trap();
+      }
+    } while (v < k);
+    const unsigned long long *pp = peers.pairs[tid] + (size_t)(k & 1) * max_rows + b;
+    unsigned long long pr;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(pr) : "l"(pp) : "memory");
+    s_pair[tid] = pr;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float bv = __uint_as_float((unsigned)(s_pair[0] >> 32));
+    unsigned bi = (unsigned)s_pair[0];
+    for (int p = 1; p < world; ++p) {
+      const float v = __uint_as_float((unsigned)(s_pair[p] >> 32));
+      const unsigned i = (unsigned)s_pair[p];
+      if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+    int tok = (int)bi;
+    const int st = step[0];
+    if (finished[b]) tok = pad;
+    if (st < max_new) out_tokens[(size_t)b * max_new + st] = tok;
+    if (tok == eos) finished[b] = 1;
+    next_ids[b] = tok;
+    if (advance_ctx) ctx_len[b] += 1;
+    seq[b] = k;
+  }
+}
+
+__global__ void tp_step_increment_kernel(int32_t *step) { step[0] += 1; }
+
 }  // namespace ocrb
 
 using namespace ocrb;
@@ -148,4 +249,33 @@ extern "C" int ocrb_allreduce_residual_bf16(void *x, int64_t ldx, const void *co
   allreduce_residual_kernel<<<AR_CTAS, AR_THREADS, 0, (cudaStream_t)stream>>>(peers, world, rank, seq, (bf16 *)x, ldx, rows,
                                                                               dim, ld_part);
   return check_launch("allreduce_residual_kernel");
+}
+
+/* Greedy step of a vocab-split lm_head without gathering the logits: every rank passes its [B, vl] slice (vl = V / world,
+ * rank r holds vocabulary rows [r*vl, (r+1)*vl)), the kernel exchanges one (max, global index) pair per sequence through
+ * peer memory and then does the bookkeeping of ocrb_argmax_step with the winning token (ties -> lowest index, identical
+ * on all ranks).  pair_ptrs / flag_ptrs: host arrays of `world` device pointers valid on THIS GPU: each rank's pair slots
+ * (uint64 [2][max_rows]) and flag array (int32 [max_rows][8]), zero-initialised once; seq: int32[max_rows] private to
+ * this rank, zero-initialised once.  B <= max_rows.  Every rank must issue the same sequence of calls. */
+extern "C" int ocrb_tp_argmax_step(const void *logits_local, int64_t ldl, int32_t B, int32_t vl, const void *const *pair_ptrs,
+                                   void *const *flag_ptrs, int32_t world, int32_t rank, int32_t *seq, int32_t max_rows,
+                                   int32_t eos, int32_t pad, int32_t max_new, int32_t *out_tokens, int32_t *next_ids,
+                                   int32_t *finished, int32_t *ctx_len, int32_t *step, int32_t advance_ctx, void *stream) {
+  OCRB_REQUIRE(logits_local && pair_ptrs && flag_ptrs && seq && out_tokens && next_ids && finished && ctx_len && step,
+               "tp_argmax_step: null pointer");
+  OCRB_REQUIRE(world >= 1 && world <= AR_MAX_WORLD && rank >= 0 && rank < world, "tp_argmax_step: bad world/rank");
+  OCRB_REQUIRE(B > 0 && B <= max_rows && vl > 0 && ldl % 8 == 0 && max_new > 0 && (long long)vl * world < 0x7fffffffLL,
+               "tp_argmax_step: bad sizes");
+  AmPeers peers;
+  for (int r = 0; r < AR_MAX_WORLD; ++r) {
+    peers.pairs[r] = (const unsigned long long *)(r < world ? pair_ptrs[r] : nullptr);
+    peers.flags[r] = (int *)(r < world ? flag_ptrs[r] : nullptr);
+  }
+  tp_argmax_step_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(peers, world, rank, seq, max_rows, (const bf16 *)logits_local, ldl,
+                                                             vl, eos, pad, max_new, out_tokens, next_ids, finished, ctx_len,
+                                                             step, advance_ctx);
+  int rc = check_launch("tp_argmax_step_kernel");
+  if (rc) return rc;
+  tp_step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+  return check_launch("tp_step_increment_kernel");
 }

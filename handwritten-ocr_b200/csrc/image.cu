@@ -464,6 +464,7 @@ extern "C" int ocrb_warp_affine_cubic_u8(const uint8_t *src, uint8_t *dst, int32
                                          int32_t C, const double *M, void *stream) {
   OCRB_REQUIRE(src && dst && M && n_img > 0 && H > 0 && W > 0 && (C == 1 || C == 3), "warp_affine_cubic_u8: bad arguments");
   OCRB_REQUIRE(src != dst, "warp_affine_cubic_u8: in-place not supported");
+  OCRB_REQUIRE((long long)H * W * C < (1ll << 31) - 8, "warp_affine_cubic_u8: image too large (H * W * C must be below 2^31)");
   int rc = ensure_itab();
   if (rc) return rc;
   const dim3 grid(cdiv(W, 256), H, n_img);

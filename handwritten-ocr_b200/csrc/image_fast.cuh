@@ -225,7 +225,7 @@ clahe_hist_lut_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ gra
 // arithmetic as the per-pixel formula (clahe_cells_host), one CTA per (cell, image) keeps the quadruple as a float4
 // table -- one 16-byte shared-memory load per pixel instead of four global byte loads and four conversions -- and the
 // column weights of the cell in shared memory as well.  Rounding by the 1.5 * 2^23 add (round-half-even, as cvRound).
-constexpr int CLAHE_MAX_CELL_W = 2048;
+constexpr int CLAHE_MAX_CELL = 1024;   // widest / tallest cell the shared-memory weight tables hold
 struct ClaheCells {
   int xb[10];
   int yb[10];
@@ -259,17 +259,37 @@ static inline int clahe_cells_host(int H, int W, float inv_tw, float inv_th, Cla
   }
   for (int k = 0; k < 9; ++k) {
     if (cells->xb[k] % 4) ok = 0;
-    if (cells->xb[k + 1] - cells->xb[k] > CLAHE_MAX_CELL_W) ok = 0;
+    if (cells->xb[k + 1] - cells->xb[k] > CLAHE_MAX_CELL) ok = 0;
+    if (cells->yb[k + 1] - cells->yb[k] > CLAHE_MAX_CELL) ok = 0;
   }
   return ok;
+}
+
+// one pixel: the reference's unfused blend, rounded half-to-even by the 1.5 * 2^23 add; the result's low byte IS the
+// output (a convex blend of values <= 255 cannot round above 255, nor below 0), so no clamp and no conversion
+__device__ __forceinline__ uint32_t clahe_blend_bits(const float4 l, float xa, float xa1, float ya, float ya1) {
+  const float top = __fadd_rn(__fmul_rn(l.x, xa1), __fmul_rn(l.y, xa));
+  const float bot = __fadd_rn(__fmul_rn(l.z, xa1), __fmul_rn(l.w, xa));
+  const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+  return (uint32_t)__float_as_int(__fadd_rn(res, 12582912.0f));
+}
+
+__device__ __forceinline__ uint32_t clahe_blend4(uint32_t v4, const float4 *s_lut, const float *xa, const float *xa1,
+                                                 float ya, float ya1) {
+  const uint32_t q0 = clahe_blend_bits(s_lut[v4 & 0xffu], xa[0], xa1[0], ya, ya1);
+  const uint32_t q1 = clahe_blend_bits(s_lut[(v4 >> 8) & 0xffu], xa[1], xa1[1], ya, ya1);
+  const uint32_t q2 = clahe_blend_bits(s_lut[(v4 >> 16) & 0xffu], xa[2], xa1[2], ya, ya1);
+  const uint32_t q3 = clahe_blend_bits(s_lut[v4 >> 24], xa[3], xa1[3], ya, ya1);
+  return __byte_perm(__byte_perm(q0, q1, 0x0040), __byte_perm(q2, q3, 0x0040), 0x5410);
 }
 
 __global__ void __launch_bounds__(256)
 clahe_apply_cells_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const uint8_t *__restrict__ lut,
                          int H, int W, float inv_tw, float inv_th, ClaheCells cells) {
   __shared__ float4 s_lut[256];
-  __shared__ __align__(16) float s_xa[CLAHE_MAX_CELL_W];
-  __shared__ __align__(16) float s_xa1[CLAHE_MAX_CELL_W];
+  __shared__ __align__(16) float s_xa[CLAHE_MAX_CELL];
+  __shared__ __align__(16) float s_xa1[CLAHE_MAX_CELL];
+  __shared__ float2 s_ya[CLAHE_MAX_CELL];
   const int t = threadIdx.x;
   const int cx = blockIdx.x % 9, cy = blockIdx.x / 9, img = blockIdx.y;
   const int x_lo = cells.xb[cx], x_hi = cells.xb[cx + 1];
@@ -286,32 +306,49 @@ clahe_apply_cells_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ 
     s_xa[c] = xa;
     s_xa1[c] = __fsub_rn(1.0f, xa);
   }
-  __syncthreads();
-  const int gpr = w >> 2, total = gpr * h;
-  const int dr = 256 / gpr, dg = 256 - dr * gpr;
-  int r = t / gpr, g = t - r * gpr;
-  for (int i = t; i < total; i += 256) {
-    const int y = y_lo + r;
-    const float yf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+  for (int r = t; r < h; r += 256) {
+    const float yf = __fsub_rn(__fmul_rn((float)(y_lo + r), inv_th), 0.5f);
     const float ya = __fsub_rn(yf, floorf(yf));
-    const float ya1 = __fsub_rn(1.0f, ya);
-    const size_t p = ((size_t)img * H + y) * W + x_lo + 4 * g;
-    const uint32_t v4 = *reinterpret_cast<const uint32_t *>(src + p);
+    s_ya[r] = make_float2(ya, __fsub_rn(1.0f, ya));
+  }
+  __syncthreads();
+  const int gpr = w >> 2;
+  const size_t cell0 = ((size_t)img * H + y_lo) * W + x_lo;
+  if (gpr <= 256 && (gpr & (gpr - 1)) == 0) {
+    // 256 / gpr rows per pass; a thread keeps its column group, so its four column weights live in registers
+    const int g = t & (gpr - 1), rpp = 256 / gpr;
     const float4 a4 = *reinterpret_cast<const float4 *>(&s_xa[4 * g]);
     const float4 b4 = *reinterpret_cast<const float4 *>(&s_xa1[4 * g]);
     const float xa[4] = {a4.x, a4.y, a4.z, a4.w}, xa1[4] = {b4.x, b4.y, b4.z, b4.w};
-    uint32_t o = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 l = s_lut[(v4 >> (8 * k)) & 0xffu];
-      const float top = __fadd_rn(__fmul_rn(l.x, xa1[k]), __fmul_rn(l.y, xa[k]));
-      const float bot = __fadd_rn(__fmul_rn(l.z, xa1[k]), __fmul_rn(l.w, xa[k]));
-      const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-      int q = __float_as_int(__fadd_rn(res, 12582912.0f)) - 0x4b400000;
-      q = imin(imax(q, 0), 255);
-      o |= (uint32_t)q << (8 * k);
+    int r = t / gpr;
+    const uint8_t *sp = src + cell0 + (size_t)r * W + 4 * g;
+    uint8_t *dp = dst + cell0 + (size_t)r * W + 4 * g;
+    const size_t step = (size_t)rpp * W;
+    for (; r + rpp < h; r += 2 * rpp) {           // two rows in flight
+      const uint32_t va = *reinterpret_cast<const uint32_t *>(sp);
+      const uint32_t vb = *reinterpret_cast<const uint32_t *>(sp + step);
+      const float2 ya = s_ya[r], yb = s_ya[r + rpp];
+      *reinterpret_cast<uint32_t *>(dp) = clahe_blend4(va, s_lut, xa, xa1, ya.x, ya.y);
+      *reinterpret_cast<uint32_t *>(dp + step) = clahe_blend4(vb, s_lut, xa, xa1, yb.x, yb.y);
+      sp += 2 * step;
+      dp += 2 * step;
     }
-    *reinterpret_cast<uint32_t *>(dst + p) = o;
+    if (r < h) {
+      const float2 ya = s_ya[r];
+      *reinterpret_cast<uint32_t *>(dp) = clahe_blend4(*reinterpret_cast<const uint32_t *>(sp), s_lut, xa, xa1, ya.x, ya.y);
+    }
+    return;
+  }
+  const int total = gpr * h;
+  const int dr = 256 / gpr, dg = 256 - dr * gpr;
+  int r = t / gpr, g = t - r * gpr;
+  for (int i = t; i < total; i += 256) {
+    const float2 ya = s_ya[r];
+    const size_t p = cell0 + (size_t)r * W + 4 * g;
+    const float4 a4 = *reinterpret_cast<const float4 *>(&s_xa[4 * g]);
+    const float4 b4 = *reinterpret_cast<const float4 *>(&s_xa1[4 * g]);
+    const float xa[4] = {a4.x, a4.y, a4.z, a4.w}, xa1[4] = {b4.x, b4.y, b4.z, b4.w};
+    *reinterpret_cast<uint32_t *>(dst + p) = clahe_blend4(*reinterpret_cast<const uint32_t *>(src + p), s_lut, xa, xa1, ya.x, ya.y);
     r += dr;
     g += dg;
     if (g >= gpr) {
@@ -495,22 +532,34 @@ __device__ __forceinline__ long long cross3(int ox, int oy, int ax, int ay, int 
 // vertices into st (room for 2n + 2 points): st[0 .. *lower) is the lower chain first -> last, st[*lower .. k) the upper
 // chain back towards the first point (not repeated).  Exactly the loops the one-thread kernel ran.
 __device__ __forceinline__ int chain_hull(const int32_t *pts, int n, int32_t *st, int *lower) {
-  int k = 0;
+  // the two topmost stack entries are mirrored in registers (a below b): a push never waits for a shared-memory load,
+  // a pop reloads one entry
+  int k = 0, ax = 0, ay = 0, bx = 0, by = 0;
   for (int i = 0; i < n; ++i) {
     const int qx = pts[2 * i], qy = pts[2 * i + 1];
-    while (k >= 2 && cross3(st[2 * (k - 2)], st[2 * (k - 2) + 1], st[2 * (k - 1)], st[2 * (k - 1) + 1], qx, qy) <= 0) --k;
+    while (k >= 2 && cross3(ax, ay, bx, by, qx, qy) <= 0) {
+      --k;
+      bx = ax; by = ay;
+      if (k >= 2) { ax = st[2 * (k - 2)]; ay = st[2 * (k - 2) + 1]; }
+    }
     st[2 * k] = qx;
     st[2 * k + 1] = qy;
     ++k;
+    ax = bx; ay = by; bx = qx; by = qy;
   }
   *lower = k;
   const int lo = k + 1;
   for (int i = n - 2; i >= 0; --i) {
     const int qx = pts[2 * i], qy = pts[2 * i + 1];
-    while (k >= lo && cross3(st[2 * (k - 2)], st[2 * (k - 2) + 1], st[2 * (k - 1)], st[2 * (k - 1) + 1], qx, qy) <= 0) --k;
+    while (k >= lo && cross3(ax, ay, bx, by, qx, qy) <= 0) {      // k >= lo >= 3: two entries stay below the top
+      --k;
+      bx = ax; by = ay;
+      ax = st[2 * (k - 2)]; ay = st[2 * (k - 2) + 1];
+    }
     st[2 * k] = qx;
     st[2 * k + 1] = qy;
     ++k;
+    ax = bx; ay = by; bx = qx; by = qy;
   }
   return k - 1;  // last point equals the first
 }
@@ -799,6 +848,10 @@ warp_affine_cubic_dp2a_kernel(const uint8_t *__restrict__ src, uint8_t *__restri
   const size_t img_off = (size_t)img * H * W * C;
   const uint8_t *im = src + img_off;
   uint8_t *o = dst + img_off + ((size_t)y * W + x) * C;
+  // 32-bit byte offsets inside the image (the host checks H * W * C < 2^31), from the image base rounded down to a word
+  const uint32_t basemis = (uint32_t)(reinterpret_cast<uintptr_t>(im) & 3);
+  const uint32_t *imw = reinterpret_cast<const uint32_t *>(im - basemis);
+  const uint32_t rowb = (uint32_t)W * C;
   if (s_o[2]) {
     for (int c = 0; c < C; ++c) o[c] = im[((size_t)y * W + x) * C + c];
     return;
@@ -822,12 +875,12 @@ warp_affine_cubic_dp2a_kernel(const uint8_t *__restrict__ src, uint8_t *__restri
   const int margin = (C == 3) ? 1 : 3;
   if (sx - 1 >= 0 && sx + 2 + margin <= W - 1) {
     int acc0 = 0, acc1 = 0, acc2 = 0;
+    const uint32_t colb = basemis + (uint32_t)(sx - 1) * C;
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
-      const uint8_t *pb = im + ((size_t)ys[ky] * W + (sx - 1)) * C;
-      const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(pb) & 3);
-      const uint32_t *wp = reinterpret_cast<const uint32_t *>(pb - mis);
-      const uint32_t sh = mis * 8;
+      const uint32_t off = (uint32_t)ys[ky] * rowb + colb;
+      const uint32_t *wp = imw + (off >> 2);
+      const uint32_t sh = (off & 3u) * 8;
       const uint32_t w01 = wpk[2 * ky], w23 = wpk[2 * ky + 1];
       if (C == 3) {
         const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];

@@ -7,8 +7,10 @@ HF:models/qwen2_5_vl/configuration_qwen2_5_vl.py:90-98):
     q_proj / k_proj / v_proj / gate_proj / up_proj : column-parallel (output rows split; heads stay whole,
                                                      q heads follow their KV head)
     o_proj / down_proj                             : row-parallel (input columns split) -> all-reduce(sum)
-    lm_head                                        : vocab-split -> all-gather of the logits, then the usual
-                                                     first-index argmax
+    lm_head                                        : vocab-split -> decode steps exchange one (max, lowest index) pair
+                                                     per rank and sequence through peer memory (csrc/comm.cu);
+                                                     the prefill step, whose logits the parity checks read, still
+                                                     all-gathers them
     embeddings, norms, vision tower                : replicated
 
 One process per GPU; NCCL over NVLink/NVSwitch carries the two all-reduces per layer (`[rows, hidden]` bf16) and
@@ -118,6 +120,10 @@ class PeerAllReduce:
         self.local = torch.zeros((2, self.MAX_ROWS, hidden), dtype=BF, device=device)
         self.flags = torch.zeros(16 * 8, dtype=torch.int32, device=device)
         self.seq = torch.zeros(16, dtype=torch.int32, device=device)
+        # (max, index) exchange of the vocab-split lm_head: two pair slots per sequence, one flag per (sequence, rank)
+        self.am_pairs = torch.zeros(2 * self.MAX_ROWS, dtype=torch.int64, device=device)
+        self.am_flags = torch.zeros(self.MAX_ROWS * 8, dtype=torch.int32, device=device)
+        self.am_seq = torch.zeros(self.MAX_ROWS, dtype=torch.int32, device=device)
         torch.cuda.synchronize()
 
         def handle(t):
@@ -126,27 +132,34 @@ class PeerAllReduce:
             _lib.call("ocrb_comm_ipc_handle", t.data_ptr(), h, ctypes.byref(off))
             return (h.raw, off.value)
 
-        mine = {"data": handle(self.local), "flags": handle(self.flags)}
+        mine = {"data": handle(self.local), "flags": handle(self.flags), "am_pairs": handle(self.am_pairs),
+                "am_flags": handle(self.am_flags)}
         everyone = [None] * self.world
         comm.dist.all_gather_object(everyone, mine, group=comm.group)
         slot_bytes = self.MAX_ROWS * hidden * 2
-        data_base, flag_ptr = [], []
+        data_base, flag_ptr, am_pair_ptr, am_flag_ptr = [], [], [], []
         for r, item in enumerate(everyone):
             if r == self.rank:
                 data_base.append(self.local.data_ptr())
                 flag_ptr.append(self.flags.data_ptr())
+                am_pair_ptr.append(self.am_pairs.data_ptr())
+                am_flag_ptr.append(self.am_flags.data_ptr())
                 continue
             out = []
-            for key in ("data", "flags"):
+            for key in ("data", "flags", "am_pairs", "am_flags"):
                 raw, off = item[key]
                 p = ctypes.c_void_p()
                 _lib.call("ocrb_comm_ipc_open", ctypes.create_string_buffer(raw, 64), off, ctypes.byref(p))
                 out.append(p.value)
             data_base.append(out[0])
             flag_ptr.append(out[1])
+            am_pair_ptr.append(out[2])
+            am_flag_ptr.append(out[3])
         arr = ctypes.c_void_p * self.world
         self._data_ptrs = [arr(*[b + s * slot_bytes for b in data_base]) for s in range(2)]
         self._flag_ptrs = arr(*flag_ptr)
+        self._am_pair_ptrs = arr(*am_pair_ptr)
+        self._am_flag_ptrs = arr(*am_flag_ptr)
         self.calls = 0
         comm.dist.barrier(group=comm.group)          # nobody launches before every mapping exists
 
@@ -161,6 +174,16 @@ class PeerAllReduce:
                        self.world, self.rank, self.seq.data_ptr(), rows, self.hidden, self.hidden,
                        torch.cuda.current_stream().cuda_stream)
         return x
+
+
+    def argmax_step(self, logits_local: torch.Tensor, B: int, eos: int, pad: int, max_new: int, out_tokens, next_ids,
+                    finished, ctx_len, step, advance_ctx: int):
+        """Greedy token of a vocab-split lm_head from every rank's [B, V / world] slice: one (max, lowest global index) pair
+        per rank and sequence through peer memory, then the step bookkeeping -- no all-gather of the logits."""
+        self._lib.call("ocrb_tp_argmax_step", logits_local.data_ptr(), logits_local.stride(0), B, logits_local.shape[1],
+                       self._am_pair_ptrs, self._am_flag_ptrs, self.world, self.rank, self.am_seq.data_ptr(), self.MAX_ROWS,
+                       eos, pad, max_new, out_tokens.data_ptr(), next_ids.data_ptr(), finished.data_ptr(),
+                       ctx_len.data_ptr(), step.data_ptr(), advance_ctx, torch.cuda.current_stream().cuda_stream)
 
 
 def random_weights_tp(cfg: VLMConfig, device, rank: int, world: int, seed: int = 0, **kw):

@@ -73,6 +73,7 @@ _CHAIN_WS = {}
 # cluster GEMMs + attention kernels under PDL) -- measured equal at B = 3 and faster above (profiles/r02_notes.md).
 CHAIN_MAX_B = int(os.environ.get("OCRB_CHAIN_MAX_B", "0"))
 CHAIN_FUSE_ATTN = os.environ.get("OCRB_CHAIN_ATTN", "1") == "1"   # the whole step (attention included) as one plan launch
+TP_ARGMAX_GATHER = os.environ.get("OCRB_TP_ARGMAX_GATHER", "0") == "1"   # tensor parallel: all-gather the logits (NCCL) instead of the pair exchange
 
 
 CHAIN_TRACE = None        # debugging: a list collects one timestamp buffer per chain launch
@@ -651,7 +652,12 @@ class Decoder:
                 self._row_parallel(st.act[sl], lay["down_w"], st.x[sl])
         self.logits_last(st.x, st.logits_local)
         if self.tp is not None:
-            self.tp.gather_vocab(st.logits_local, st.logits)     # vocab-split lm_head -> full [B, V] logits
+            peer = getattr(self.tp, "peer", None)
+            if peer is not None and B <= peer.MAX_ROWS and not TP_ARGMAX_GATHER:
+                # vocab-split lm_head: (max, lowest index) pairs through peer memory instead of gathering B x V logits
+                return peer.argmax_step(st.logits_local, B, EOS, EOS, st.max_new, st.out_tokens, st.next_ids, st.finished,
+                                        st.ctx_len, st.step, 1)
+            self.tp.gather_vocab(st.logits_local, st.logits)     # NCCL route: full [B, V] logits on every rank
         _lib.call("ocrb_argmax_step", st.logits.data_ptr(), st.logits.stride(0), B, t.vocab, EOS, EOS, st.max_new,
                   st.out_tokens.data_ptr(), st.next_ids.data_ptr(), st.finished.data_ptr(), st.ctx_len.data_ptr(),
                   st.step.data_ptr(), 1, _sp())

@@ -314,6 +314,17 @@ int ocrb_allreduce_residual_bf16(void *x, int64_t ldx, const void *const *data_p
                                  int32_t world, int32_t rank, int32_t *seq, int32_t rows, int32_t dim,
                                  int64_t ld_part, void *stream);
 
+/* Tensor-parallel greedy step for a vocab-split lm_head (HF `lm_head: colwise_rep`, configuration_qwen2_5_vl.py:90-98, reached
+ * from tools.py:764-765): instead of all-gathering B x V logits, each rank reduces its [B, vl] slice (rank r = vocabulary rows
+ * [r*vl, (r+1)*vl)) to one (max, global index) pair per sequence, the pairs are exchanged through peer memory, ties go to
+ * the lowest index (= first-index arg max over the full vocabulary), then the bookkeeping of ocrb_argmax_step runs with the
+ * winning token.  pair_ptrs / flag_ptrs: host arrays of `world` device pointers valid on this GPU (uint64 [2][max_rows] and
+ * int32 [max_rows][8] per rank, zero-initialised once); seq: int32[max_rows], private, zero-initialised once. */
+int ocrb_tp_argmax_step(const void *logits_local, int64_t ldl, int32_t B, int32_t vl, const void *const *pair_ptrs,
+                        void *const *flag_ptrs, int32_t world, int32_t rank, int32_t *seq, int32_t max_rows,
+                        int32_t eos, int32_t pad, int32_t max_new, int32_t *out_tokens, int32_t *next_ids,
+                        int32_t *finished, int32_t *ctx_len, int32_t *step, int32_t advance_ctx, void *stream);
+
 /* Per-step mRoPE tables for decode: pos[b] = ctx_len[b] + rope_delta[b]; writes bf16 cos/sin [B, hd]
  * (all three mrope sections share the position for text tokens). inv_freq: fp32[hd/2]. */
 int ocrb_decode_rope_table(const int32_t *ctx_len, const int32_t *rope_delta, const float *inv_freq,

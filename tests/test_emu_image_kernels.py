@@ -81,8 +81,8 @@ def test_high_contrast_fused(emu, C, shape):
     (tile width 12) + cell kernel refused (boundaries not multiples of 4) -> LUTs only; (50,70): reflect-101 extension."""
     rng = np.random.default_rng(5)
     H, W = shape
-    for kind in ("paper", "noise"):
-        imgs = [page(rng, H, W, C, kind) for _ in range(2)]
+    for kind in (("paper",) if shape in ((64, 128), (40, 96)) else ("noise",)):     # the emulated scan is slow: one kind each
+        imgs = [page(rng, H, W, C, kind), page(rng, H, W, C, "noise" if kind == "paper" else "paper")]
         src = aligned((2,) + imgs[0].shape)
         src[0], src[1] = imgs
         dst = aligned((2, H, W), fill=9)
@@ -139,7 +139,7 @@ def skewed_page(rng, H, W, C, angle_deg):
 @pytest.mark.parametrize("C", [1, 3])
 def test_deskew_angle_tree_and_warp(emu, C):
     rng = np.random.default_rng(17)
-    for (H, W), ang in [((96, 128), 2.0), ((130, 160), -3.5), ((64, 64), 0.0), ((200, 96), 7.0)]:
+    for (H, W), ang in [((96, 128), 2.0), ((130, 160), -3.5), ((72, 64), 7.0)]:
         imgs = [skewed_page(rng, H, W, C, ang), skewed_page(rng, H, W, C, -ang / 2)]
         blank = aligned(imgs[0].shape, fill=255)               # <= 100 dark pixels -> NaN, page unchanged
         src = aligned((3,) + imgs[0].shape)

@@ -55,6 +55,44 @@ def _worker(rank, world, port, q):
         torch.cuda.synchronize()
         assert torch.equal(x, want), "graph-replayed one-shot all-reduce differs"
         del gr
+        # direct check of the (max, lowest index) exchange of the vocab-split lm_head: eager and graph-replayed steps against
+        # the first-index arg max over the full logits, with ties planted across the rank boundary
+        Bq, V = 5, 1024
+        vl = V // world
+        full = torch.randn(6, Bq, V, generator=g, device=dev).to(torch.bfloat16)
+        full[1, 0, 3] = 9.0
+        full[1, 0, vl + 3] = 9.0            # tie between the ranks: the lower index (rank 0's) wins
+        full[2, 1, vl + 7] = 9.0
+        full[2, 1, V - 1] = 9.0             # tie inside the last rank's slice
+        full[3, 2, vl - 1] = 9.0
+        full[3, 2, vl] = 9.0                # tie across the slice boundary
+        want_tok = np.argmax(full.float().cpu().numpy(), axis=-1)          # numpy: first occurrence
+        outs = torch.full((Bq, 16), -7, dtype=torch.int32, device=dev)
+        nxt = torch.zeros(Bq, dtype=torch.int32, device=dev)
+        fin = torch.zeros(Bq, dtype=torch.int32, device=dev)
+        ctx = torch.zeros(Bq, dtype=torch.int32, device=dev)
+        stp = torch.zeros(1, dtype=torch.int32, device=dev)
+        loc = torch.empty((Bq, vl), dtype=torch.bfloat16, device=dev)
+
+        def am(i):
+            loc.copy_(full[i % 6][:, rank * vl:(rank + 1) * vl])
+            peer.argmax_step(loc, Bq, -1, -1, 16, outs, nxt, fin, ctx, stp, 1)
+
+        for i in range(3):
+            am(i)
+        gr2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr2):
+            for i in range(3, 6):
+                am(i)
+        gr2.replay()            # steps 3..5
+        gr2.replay()            # steps 6..8 = inputs 3..5 again
+        torch.cuda.synchronize()
+        got_tok = outs.cpu().numpy()
+        for i in range(9):
+            src = i if i < 6 else i - 3
+            assert (got_tok[:, i] == want_tok[src]).all(), ("pair-exchange arg max", i, got_tok[:, i], want_tok[src])
+        assert int(stp[0]) == 9 and (ctx.cpu().numpy() == 9).all() and (nxt.cpu().numpy() == want_tok[5]).all()
+        del gr2
     eng = engine.OcrEngine(w_local, max_batch=4, max_new_tokens=24, max_prompt=400, tp=comm)
     pages = preprocess.to_device([synth.page(100 + i, 504, 392) for i in range(2)])
     toks, dbg = eng.read_batch(pages, max_new_tokens=24, return_debug=True)
