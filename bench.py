@@ -44,6 +44,7 @@ PROMPT = "Extract and return all the text from this handwritten document."   # c
 METRIC, UNIT = "ocr_page_reads_per_s", "page-reads/s"
 FOLDER_PAGES = 256                                           # BASELINE.json configs[2]
 FOLDER_PAGES_PER_STEP = 32                                   # per GPU: B = 96 sequences per batched read
+TP_LEG_LIMIT_S = 600                                         # N > 1: wall-clock bound of the tensor-parallel leg
 
 
 def peaks():
@@ -421,12 +422,28 @@ def run_b200(args):
     if world > 1 and not args.no_extra and not args.tiny:
         # tensor-parallel leg (configs[4]) -- after everything the line reports has been measured; a failure here is recorded
         # in the line, it cannot take the data-parallel numbers with it
+        # watchdog: a peer-memory exchange that never completes (a rank died, a flag never arrives) must not cost the
+        # data-parallel line, which is already measured -- after TP_LEG_LIMIT_S rank 0 prints it without the leg and leaves
+        done = threading.Event()
+
+        def _bail():
+            if not done.is_set():
+                if rank == 0:
+                    line.setdefault("extra", {})["tp_leg"] = {"error": f"tensor-parallel leg exceeded {TP_LEG_LIMIT_S} s; skipped"}
+                    print(json.dumps(line), flush=True)
+                os._exit(0)
+
+        wd = threading.Timer(TP_LEG_LIMIT_S, _bail)
+        wd.daemon = True
+        wd.start()
         try:
             tools._ocr_engine = None
             eng.close()
             tpx = run_tp_leg(torch, dist, dev, rank, world, pk)
         except Exception as e:          # noqa: BLE001
             tpx = {"error": f"{type(e).__name__}: {e}"[:400]}
+        done.set()
+        wd.cancel()
         if rank == 0:
             line.setdefault("extra", {}).update(tpx)
     if rank == 0:
@@ -588,10 +605,12 @@ def preprocess_table(torch, preprocess, synth, page, peak_gbs):
     x = preprocess.to_device(page)
     ruled = preprocess.to_device(synth.rule_lines(page))
     H, W = page.shape[:2]
-    cases = {"high_contrast": (lambda: preprocess.high_contrast(x), 4 * H * W, "hbm"),
-             "binarize": (lambda: preprocess.binarize(x), 4 * H * W, "hbm (rgb2gray) + fp32 FMA (2 x 21-tap stencil)"),
+    cases = {"high_contrast": (lambda: preprocess.high_contrast(x), 4 * H * W,
+                               "fp32 issue (CLAHE blend: 9 unfused mul/add per pixel, as OpenCV rounds them) + shared-memory histogram atomics; "
+                               "DRAM traffic = algorithmic bytes (profiles/r02_image_kernels.md)"),
+             "binarize": (lambda: preprocess.binarize(x), 4 * H * W, "fp32 FMA (2 x 21-tap stencil in OpenCV's order: 42 FMA/add per pixel); rgb2gray fused into the tile staging"),
              "sharpen": (lambda: preprocess.sharpen(x), 6 * H * W, "hbm"),
-             "deskew": (lambda: preprocess.deskew(x), 6 * H * W, "hbm"),
+             "deskew": (lambda: preprocess.deskew(x), 6 * H * W, "L1 / LSU (cubic warp: 16 taps x 3 channels gathered per pixel, 24 dp2a) + one-CTA-per-page hull / calipers"),
              "denoise": (lambda: preprocess.denoise(x), 6 * H * W, "integer ALU / shared memory (441 x 49 comparisons per pixel)"),
              "remove_lines": (lambda: preprocess.remove_lines(ruled), 6 * H * W, "latency (ordered fast march, one warp per ruled line)")}
     out = {}
