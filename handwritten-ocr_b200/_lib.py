@@ -81,12 +81,14 @@ _SIGS = {
     "ocrb_comm_ipc_handle": [_P, _P, _P],
     "ocrb_comm_ipc_open": [_P, _L, _P],
     "ocrb_allreduce_residual_bf16": [_P, _L, _P, _P, _I, _I, _P, _I, _I, _L, _P],
+    "ocrb_skinny_rowparallel_tp_bf16": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _P, _I, _P],
     "ocrb_tp_argmax_step": [_P, _L, _I, _I, _P, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "ocrb_decode_rope_table": [_P, _P, _P, _I, _I, _P, _P, _P],
 }
 
 EXPORTS = ["ocrb_version", "ocrb_last_error", "ocrb_launch_count", "ocrb_launch_count_reset",
-           "ocrb_skinny_workspace_bytes", "ocrb_chain_workspace_bytes", "ocrb_chain_plan_bytes", "ocrb_inpaint_workspace_bytes"] + list(_SIGS)
+           "ocrb_skinny_workspace_bytes", "ocrb_chain_workspace_bytes", "ocrb_chain_plan_bytes", "ocrb_inpaint_workspace_bytes",
+           "ocrb_skinny_rowparallel_tp_was_fused"] + list(_SIGS)
 
 
 def load():
@@ -108,6 +110,8 @@ def load():
     L.ocrb_chain_plan_bytes.restype = c_int64
     L.ocrb_chain_plan_bytes.argtypes = [c_int32]
     L.ocrb_inpaint_workspace_bytes.restype = c_int64
+    L.ocrb_skinny_rowparallel_tp_was_fused.restype = c_int32
+    L.ocrb_skinny_rowparallel_tp_was_fused.argtypes = []
     L.ocrb_inpaint_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
     for name, args in _SIGS.items():
         fn = getattr(L, name)

@@ -26,6 +26,7 @@
 // warp % 4).
 #include "skinny_common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace ocrb {
 
@@ -38,7 +39,23 @@ namespace ocrb {
 #endif
 
 
+// Tensor-parallel row-parallel linear (o_proj / down_proj of the decode step, HF base_model_tp_plan "rowwise"): the
+// all-reduce of the bf16 partial products and the residual add run INSIDE the cluster kernel's epilogue, over NVLink peer
+// memory (see the TP section of skinny_cluster_kernel).  world == 0: not a tensor-parallel call.
+constexpr int SK_TP_UNITS = 512;   // (tile, cluster rank) exchange units: 128 tiles x cluster of 4
+constexpr int SK_EPI_TP = 4;       // internal epilogue code (not part of the public OCRB_EPI_* set)
+struct SkinnyTp {
+  const bf16 *data[8];             // every rank's partial slot of this call (device pointers valid on this GPU; own at [rank])
+  int *flags[8];                   // every rank's flag array [SK_TP_UNITS][8]
+  int *seq;                        // this rank's call counters [SK_TP_UNITS]
+  bf16 *x; long long ldx;          // residual stream [B, N], updated in place
+  long long ldp;                   // row stride of the partial slots
+  int world, rank;
+  int mode;                        // experiments (OCRB_TP_FUSED_MODE): bit 0 = every thread fences before the announcement
+};
+
 struct SkinnyParams {
+  SkinnyTp tp;
   const bf16 *X; long long ldx;
   bf16 *D; long long ldd;
   const bf16 *bias;
@@ -674,6 +691,62 @@ skinny_cluster_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
           if (c0 + i < p.B) dcol[(size_t)i * p.ldd] = __float2bfloat16_rn(o[i]);
       }
     }
+    // ───────────── tensor parallel: all-reduce + residual add of this CTA's columns, in place of a second kernel ─────────────
+    // p.D is this rank's peer-mapped partial slot: the bf16 partials above are what HF's rowwise plan sums.  Every CTA
+    // that owns live columns is one exchange unit (tile, cluster rank) -- the same units on every rank, since the tiling
+    // depends on (N, K, B) only: it announces "my partial of call k is written" to every peer (one remote flag store
+    // each), waits for the peers' announcements of the same unit, reads their partials of its 128 rows x <= 8 LG columns
+    // straight from peer memory, adds them in rank order in fp32 (identical bits on every rank), rounds to bf16 and adds
+    // the residual -- the arithmetic of allreduce_residual_kernel (csrc/comm.cu), so both routes give the same bits.
+    // Units exchange independently: a tile's reduction overlaps the weight streaming of the clusters still at work, and
+    // the 160 all-reduce launches of a 72B-class decode step disappear.  Slot reuse is safe for the reason given in
+    // comm.cu: a peer announces call k + 1 only after griddepcontrol.wait, i.e. after its call k has completely finished.
+    if (p.epilogue == SK_EPI_TP && rank * 8 < p.B) {
+      const int unit = tile * SKC_CS + rank;
+      const int k = p.tp.seq[unit] + 1;
+      // the partial stores of all 128 threads happen-before the barrier, the announcing threads' st.release.sys after it:
+      // release is cumulative, so one fence per announcing thread (inside the release) orders them all
+      if (p.tp.mode & 1) __threadfence_system();
+      named_bar_sync(1, 128);
+      if (et < p.tp.world) {
+        int *dst = p.tp.flags[et] + unit * 8 + p.tp.rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(k) : "memory");
+        const int *src = p.tp.flags[p.tp.rank] + unit * 8 + et;
+        int v;
+        const long long t0 = clock64();
+        do {
+          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+          if (v < k && clock64() - t0 > 60000000000LL) {
+            printf("ocrb fused all-reduce: rank %d unit %d never saw rank %d announce call %d (flag %d)\n", p.tp.rank, unit, et, k, v);
+            __trap();
+          }
+        } while (v < k);
+      }
+      named_bar_sync(1, 128);
+      if (n_ok) {
+#pragma unroll 1
+        for (int lg = 0; lg < LG; ++lg) {
+          const int c0 = (lg * SKC_CS + rank) * 8;
+          if (c0 >= p.B) break;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (c0 + i >= p.B) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q < p.tp.world) {
+                unsigned short raw;
+                asm volatile("ld.volatile.global.u16 %0, [%1];" : "=h"(raw) : "l"(p.tp.data[q] + (size_t)(c0 + i) * p.tp.ldp + n));
+                acc += __uint_as_float((uint32_t)raw << 16);
+              }
+            bf16 *xp = p.tp.x + (size_t)(c0 + i) * p.tp.ldx + n;
+            *xp = __float2bfloat16_rn(__bfloat162float(*xp) + bf16_round(acc));
+          }
+        }
+      }
+      named_bar_sync(1, 128);
+      if (et == 0) p.tp.seq[unit] = k;
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -795,6 +868,12 @@ extern "C" int64_t ocrb_skinny_workspace_bytes(void) {
          (int64_t)SK_MAXBP * SK_MAX_NORM_K * sizeof(bf16);
 }
 
+// Set by ocrb_skinny_rowparallel_tp_bf16 around its call of ocrb_skinny_gemm_bf16 (the library is driven by one host
+// thread per process): when the linear qualifies for the cluster kernel, the exchange is fused into its epilogue and
+// g_tp_fused says so; otherwise the GEMM only writes the partial and the caller launches the separate all-reduce kernel.
+static const SkinnyTp *g_tp_ctx = nullptr;
+static bool g_tp_fused = false;
+
 extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, int64_t ldw, void *D, int64_t ldd, int32_t B,
                                      int32_t N, int32_t K, const void *bias, const void *residual, int64_t ldr,
                                      int32_t epilogue, const void *norm_w, float eps, void *workspace, void *stream) {
@@ -808,6 +887,7 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
   OCRB_REQUIRE(epilogue != OCRB_EPI_RESIDUAL || residual, "skinny_gemm_bf16: residual epilogue without residual");
   OCRB_REQUIRE(epilogue != OCRB_EPI_SWIGLU || N % 128 == 0, "skinny_gemm_bf16: SwiGLU needs packed N % 128 == 0");
   SkinnyParams p;
+  memset(&p.tp, 0, sizeof(p.tp));
   p.X = (const bf16 *)X; p.ldx = ldx;
   p.D = (bf16 *)D; p.ldd = ldd;
   p.bias = (const bf16 *)bias;
@@ -870,6 +950,11 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
     const int cs = (use_cluster && epilogue != OCRB_EPI_SWIGLU && p.num_tiles * 2 <= sm_count() && p.num_kb >= 16)
                        ? pick_cluster_size(p.num_tiles) : 0;
     if (cs > 0) {
+      if (g_tp_ctx && epilogue == OCRB_EPI_NONE && !bias && p.num_tiles * cs <= SK_TP_UNITS) {
+        p.tp = *g_tp_ctx;
+        p.epilogue = SK_EPI_TP;
+        g_tp_fused = true;
+      }
       if (B <= 8) return launch_skinny_cluster_cs<16, 8>(cs, mw, mx, p, st);
       if (B <= 16) return launch_skinny_cluster_cs<16, 16>(cs, mw, mx, p, st);
       if (B <= 32) return launch_skinny_cluster_cs<32, 32>(cs, mw, mx, p, st);
@@ -887,3 +972,48 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
   if (B <= 96) return launch_skinny<96, 96>(mw, mx, p, grid, st);
   return launch_skinny<128, 128>(mw, mx, p, grid, st);
 }
+
+extern "C" int ocrb_allreduce_residual_bf16(void *x, int64_t ldx, const void *const *data_ptrs, void *const *flag_ptrs,
+                                            int32_t world, int32_t rank, int32_t *seq, int32_t rows, int32_t dim,
+                                            int64_t ld_part, void *stream);
+
+extern "C" int ocrb_skinny_rowparallel_tp_bf16(const void *X, int64_t ldx, const void *W, int64_t ldw, int32_t B, int32_t N,
+                                               int32_t K, void *x, int64_t ldx_res, const void *const *data_ptrs,
+                                               int64_t ld_part, void *const *fused_flag_ptrs, int32_t *fused_seq,
+                                               void *const *flag_ptrs, int32_t *seq, int32_t world, int32_t rank,
+                                               void *workspace, int32_t allow_fused, void *stream) {
+  OCRB_REQUIRE(x && data_ptrs && fused_flag_ptrs && fused_seq && flag_ptrs && seq, "skinny_rowparallel_tp_bf16: null pointer");
+  OCRB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "skinny_rowparallel_tp_bf16: bad world/rank");
+  OCRB_REQUIRE(N % 8 == 0 && ldx_res % 8 == 0 && ld_part % 8 == 0, "skinny_rowparallel_tp_bf16: N and strides must be multiples of 8");
+  SkinnyTp tp;
+  memset(&tp, 0, sizeof(tp));
+  for (int r = 0; r < world; ++r) {
+    tp.data[r] = (const bf16 *)data_ptrs[r];
+    tp.flags[r] = (int *)fused_flag_ptrs[r];
+  }
+  tp.seq = fused_seq;
+  tp.x = (bf16 *)x;
+  tp.ldx = ldx_res;
+  tp.ldp = ld_part;
+  tp.world = world;
+  tp.rank = rank;
+  {
+    static int mode = -1;
+    if (mode < 0) {
+      const char *e = getenv("OCRB_TP_FUSED_MODE");
+      mode = e ? atoi(e) : 0;
+    }
+    tp.mode = mode;
+  }
+  g_tp_ctx = allow_fused ? &tp : nullptr;
+  g_tp_fused = false;
+  const int rc = ocrb_skinny_gemm_bf16(X, ldx, W, ldw, (void *)data_ptrs[rank], ld_part, B, N, K, nullptr, nullptr, 0,
+                                       OCRB_EPI_NONE, nullptr, 0.f, workspace, stream);
+  g_tp_ctx = nullptr;
+  if (rc) return rc;
+  if (g_tp_fused) return OCRB_OK;
+  return ocrb_allreduce_residual_bf16(x, ldx_res, data_ptrs, flag_ptrs, world, rank, seq, B, N, ld_part, stream);
+}
+
+/* 1 when the last ocrb_skinny_rowparallel_tp_bf16 call ran the exchange inside the GEMM (debug / tests). */
+extern "C" int ocrb_skinny_rowparallel_tp_was_fused(void) { return g_tp_fused ? 1 : 0; }

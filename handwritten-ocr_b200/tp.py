@@ -20,6 +20,7 @@ paged KV of the rank's KV heads) is the single-GPU code on local shapes.
 from __future__ import annotations
 
 import copy
+import os
 
 import torch
 
@@ -124,6 +125,12 @@ class PeerAllReduce:
         self.am_pairs = torch.zeros(2 * self.MAX_ROWS, dtype=torch.int64, device=device)
         self.am_flags = torch.zeros(self.MAX_ROWS * 8, dtype=torch.int32, device=device)
         self.am_seq = torch.zeros(self.MAX_ROWS, dtype=torch.int32, device=device)
+        # all-reduce fused into the row-parallel GEMM's epilogue: one flag row per (tile, cluster CTA) exchange unit
+        self.fz_flags = torch.zeros(512 * 8, dtype=torch.int32, device=device)
+        self.fz_seq = torch.zeros(512, dtype=torch.int32, device=device)
+        # opt-in: bit-equal to the two-kernel route, measured 3 % slower per decode step at TP-2 on 72B-class shards
+        # (profiles/r02_notes.md, "Fused GEMM + all-reduce")
+        self.fused = os.environ.get("OCRB_TP_FUSED", "0") == "1"
         torch.cuda.synchronize()
 
         def handle(t):
@@ -133,20 +140,21 @@ class PeerAllReduce:
             return (h.raw, off.value)
 
         mine = {"data": handle(self.local), "flags": handle(self.flags), "am_pairs": handle(self.am_pairs),
-                "am_flags": handle(self.am_flags)}
+                "am_flags": handle(self.am_flags), "fz_flags": handle(self.fz_flags)}
         everyone = [None] * self.world
         comm.dist.all_gather_object(everyone, mine, group=comm.group)
         slot_bytes = self.MAX_ROWS * hidden * 2
-        data_base, flag_ptr, am_pair_ptr, am_flag_ptr = [], [], [], []
+        data_base, flag_ptr, am_pair_ptr, am_flag_ptr, fz_flag_ptr = [], [], [], [], []
         for r, item in enumerate(everyone):
             if r == self.rank:
                 data_base.append(self.local.data_ptr())
                 flag_ptr.append(self.flags.data_ptr())
                 am_pair_ptr.append(self.am_pairs.data_ptr())
                 am_flag_ptr.append(self.am_flags.data_ptr())
+                fz_flag_ptr.append(self.fz_flags.data_ptr())
                 continue
             out = []
-            for key in ("data", "flags", "am_pairs", "am_flags"):
+            for key in ("data", "flags", "am_pairs", "am_flags", "fz_flags"):
                 raw, off = item[key]
                 p = ctypes.c_void_p()
                 _lib.call("ocrb_comm_ipc_open", ctypes.create_string_buffer(raw, 64), off, ctypes.byref(p))
@@ -155,11 +163,13 @@ class PeerAllReduce:
             flag_ptr.append(out[1])
             am_pair_ptr.append(out[2])
             am_flag_ptr.append(out[3])
+            fz_flag_ptr.append(out[4])
         arr = ctypes.c_void_p * self.world
         self._data_ptrs = [arr(*[b + s * slot_bytes for b in data_base]) for s in range(2)]
         self._flag_ptrs = arr(*flag_ptr)
         self._am_pair_ptrs = arr(*am_pair_ptr)
         self._am_flag_ptrs = arr(*am_flag_ptr)
+        self._fz_flag_ptrs = arr(*fz_flag_ptr)
         self.calls = 0
         comm.dist.barrier(group=comm.group)          # nobody launches before every mapping exists
 
@@ -175,6 +185,17 @@ class PeerAllReduce:
                        torch.cuda.current_stream().cuda_stream)
         return x
 
+
+    def row_parallel(self, X: torch.Tensor, W: torch.Tensor, x: torch.Tensor, workspace: torch.Tensor) -> torch.Tensor:
+        """x[rows, hidden] += sum over ranks of bf16(X @ W^T) for a row-parallel linear, ONE kernel when the shape runs on the
+        cluster GEMM (the exchange is its epilogue), GEMM + `all_reduce_residual` kernel otherwise -- same bits."""
+        slot = self.next_slot()
+        rows = X.shape[0]
+        self._lib.call("ocrb_skinny_rowparallel_tp_bf16", X.data_ptr(), X.stride(0), W.data_ptr(), W.stride(0), rows,
+                       W.shape[0], X.shape[1], x.data_ptr(), x.stride(0), self._data_ptrs[slot], self.hidden,
+                       self._fz_flag_ptrs, self.fz_seq.data_ptr(), self._flag_ptrs, self.seq.data_ptr(), self.world, self.rank,
+                       workspace.data_ptr(), 1 if self.fused else 0, torch.cuda.current_stream().cuda_stream)
+        return x
 
     def argmax_step(self, logits_local: torch.Tensor, B: int, eos: int, pad: int, max_new: int, out_tokens, next_ids,
                     finished, ctx_len, step, advance_ctx: int):

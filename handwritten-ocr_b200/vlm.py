@@ -484,11 +484,10 @@ class Decoder:
             return linear_small_or_big(X, W, h, residual=h, epilogue=EPI_RESIDUAL)
         peer = getattr(self.tp, "peer", None)
         if peer is not None and X.shape[0] <= peer.MAX_ROWS:
-            # decode: the GEMM writes its partial into the peer-mapped slot, one kernel does all-reduce + residual
-            slot = peer.next_slot()
-            linear_small_or_big(X, W, peer.local[slot][: X.shape[0]])
+            # decode: the GEMM writes its partial into the peer-mapped slot and, on the cluster kernel, exchanges it with
+            # the peers and finishes the residual stream in its own epilogue (csrc/skinny.cu); tiny shapes: one more kernel
             self.tp.n_all_reduce += 1
-            return peer.all_reduce_residual(h, X.shape[0], slot)
+            return peer.row_parallel(X, W, h, skinny_workspace(X.device))
         key = (X.shape[0], h.shape[1])
         tmp = self._tp_tmp.get(key)
         if tmp is None:

@@ -314,6 +314,24 @@ int ocrb_allreduce_residual_bf16(void *x, int64_t ldx, const void *const *data_p
                                  int32_t world, int32_t rank, int32_t *seq, int32_t rows, int32_t dim,
                                  int64_t ld_part, void *stream);
 
+/* Row-parallel linear of the tensor-parallel decode step (o_proj / down_proj, HF "rowwise") WITH its all-reduce and residual
+ * add: x[B, N] += bf16(sum over ranks of bf16(X_r[B, K] @ W_r[N, K]^T)), every rank calling with its K-slice.  When the
+ * linear runs on the cluster kernel (few 128-row tiles, K >= 1024) the exchange is part of the GEMM's epilogue: each
+ * (tile, cluster CTA) announces its partial to the peers with one remote flag store, waits for theirs, reads their
+ * partials of its tile over NVLink peer memory and finishes the residual stream in place -- no second kernel, and a
+ * tile's reduction overlaps the weight streaming of the others.  Otherwise (tiny shapes) the partial is written and
+ * ocrb_allreduce_residual_bf16 follows; both routes produce identical bits.  data_ptrs: every rank's partial slot for
+ * this call (this rank's own at [rank]), row stride ld_part; fused_flag_ptrs: every rank's int32 [512][8] flag array and
+ * fused_seq: int32[512] (zero-initialised once; used by the fused route); flag_ptrs / seq: the arrays of
+ * ocrb_allreduce_residual_bf16 (fallback route).  allow_fused = 0 forces the two-kernel route.  B <= 128. */
+int ocrb_skinny_rowparallel_tp_bf16(const void *X, int64_t ldx, const void *W, int64_t ldw, int32_t B, int32_t N,
+                                    int32_t K, void *x, int64_t ldx_res, const void *const *data_ptrs,
+                                    int64_t ld_part, void *const *fused_flag_ptrs, int32_t *fused_seq,
+                                    void *const *flag_ptrs, int32_t *seq, int32_t world, int32_t rank,
+                                    void *workspace, int32_t allow_fused, void *stream);
+/* 1 when the last ocrb_skinny_rowparallel_tp_bf16 call ran the exchange inside the GEMM kernel. */
+int ocrb_skinny_rowparallel_tp_was_fused(void);
+
 /* Tensor-parallel greedy step for a vocab-split lm_head (HF `lm_head: colwise_rep`, configuration_qwen2_5_vl.py:90-98, reached
  * from tools.py:764-765): instead of all-gathering B x V logits, each rank reduces its [B, vl] slice (rank r = vocabulary rows
  * [r*vl, (r+1)*vl)) to one (max, global index) pair per sequence, the pairs are exchanged through peer memory, ties go to

@@ -93,6 +93,47 @@ def _worker(rank, world, port, q):
             assert (got_tok[:, i] == want_tok[src]).all(), ("pair-exchange arg max", i, got_tok[:, i], want_tok[src])
         assert int(stp[0]) == 9 and (ctx.cpu().numpy() == 9).all() and (nxt.cpu().numpy() == want_tok[5]).all()
         del gr2
+        # all-reduce fused into the row-parallel GEMM's epilogue, at the shard shapes of the 72B-class config under TP-8
+        # (o_proj: K = 1024, down_proj: K = 3696 -> padded k-blocks; N = 8192 = 64 tiles on the cluster kernel): the fused
+        # route must give the bits of the two-kernel route (GEMM into the slot + allreduce_residual_kernel), eagerly and
+        # under CUDA-graph replay, for batch sizes on both sides of the 8-column group boundary
+        from handwritten_ocr_b200 import _lib
+        N = 8192
+        peer2 = tp.PeerAllReduce(comm, dev, N)
+        ws = vlm.skinny_workspace(dev)
+        for K, Bq2 in [(1024, 3), (3696, 5), (1024, 24)]:
+            gw = torch.Generator(device=dev).manual_seed(1000 + 17 * rank + K + Bq2)      # this rank's shard
+            Wr = (torch.randn(N, K, generator=gw, device=dev) * 0.02).to(torch.bfloat16)
+            Xr = torch.randn(Bq2, K, generator=gw, device=dev).to(torch.bfloat16)
+            x0 = torch.randn(Bq2, N, generator=g, device=dev).to(torch.bfloat16)          # same on both ranks
+            xa, xb = x0.clone(), x0.clone()
+            for _ in range(3):
+                peer2.fused = True
+                peer2.row_parallel(Xr, Wr, xa, ws)
+                was = _lib.load().ocrb_skinny_rowparallel_tp_was_fused()
+                peer2.fused = False
+                peer2.row_parallel(Xr, Wr, xb, ws)
+            torch.cuda.synchronize()
+            assert was == 1, "expected the cluster kernel (fused exchange) for this shape"
+            assert torch.equal(xa, xb), ("fused all-reduce differs from the two-kernel route", K, Bq2)
+            part = (Xr.float() @ Wr.float().t())
+            dist.all_reduce(part)
+            approx = x0.float() + 3 * part
+            assert ((xa.float() - approx).abs().max() / approx.abs().max()).item() < 0.03
+            peer2.fused = True
+            gr3 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr3):
+                for _ in range(4):
+                    peer2.row_parallel(Xr, Wr, xa, ws)
+            for _ in range(3):
+                gr3.replay()
+            peer2.fused = False
+            for _ in range(12):
+                peer2.row_parallel(Xr, Wr, xb, ws)
+            torch.cuda.synchronize()
+            assert torch.equal(xa, xb), ("graph-replayed fused all-reduce differs", K, Bq2)
+            del gr3
+        res_fused = True
     eng = engine.OcrEngine(w_local, max_batch=4, max_new_tokens=24, max_prompt=400, tp=comm)
     pages = preprocess.to_device([synth.page(100 + i, 504, 392) for i in range(2)])
     toks, dbg = eng.read_batch(pages, max_new_tokens=24, return_debug=True)
