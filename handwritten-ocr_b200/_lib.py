@@ -81,7 +81,7 @@ _SIGS = {
     "ocrb_comm_ipc_handle": [_P, _P, _P],
     "ocrb_comm_ipc_open": [_P, _L, _P],
     "ocrb_allreduce_residual_bf16": [_P, _L, _P, _P, _I, _I, _P, _I, _I, _L, _P],
-    "ocrb_skinny_rowparallel_tp_bf16": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _P, _I, _P],
+    "ocrb_skinny_rowparallel_tp_bf16": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P],
     "ocrb_tp_argmax_step": [_P, _L, _I, _I, _P, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "ocrb_decode_rope_table": [_P, _P, _P, _I, _I, _P, _P, _P],
 }

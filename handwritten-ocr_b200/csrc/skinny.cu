@@ -51,8 +51,11 @@ struct SkinnyTp {
   bf16 *x; long long ldx;          // residual stream [B, N], updated in place
   long long ldp;                   // row stride of the partial slots
   int world, rank;
-  int mode;                        // experiments (OCRB_TP_FUSED_MODE): bit 0 = every thread fences before the announcement
+  int mode;                        // bit 0 (experiment): every thread fences before the announcement; bit 1: LL protocol
+  unsigned long long *ll[8];       // LL protocol: every rank's receive buffer, cells [2 slots][8 sources][64 rows][ldp / 2]
+  int *ll_seq;                     // LL protocol: [0] global call index, [1] ticket of the call in flight
 };
+constexpr int SK_LL_ROWS = 64;
 
 struct SkinnyParams {
   SkinnyTp tp;
@@ -684,11 +687,103 @@ skinny_cluster_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = sk_gelu(o[i]);
       }
-      if (n_ok) {
+      if (p.epilogue == SK_EPI_TP && (p.tp.mode & 2)) {
+        // LL protocol (as NCCL's low-latency one): the partial travels WITH its flag -- two bf16 values of adjacent rows
+        // and the call index in one 8-byte cell, pushed by one 8-byte store (atomic over NVLink) into every peer's
+        // receive buffer.  No fence, no flag round trip: the receiver polls its own memory for cells of this call.
+        const uint32_t kk = (uint32_t)(p.tp.ll_seq[0] + 1);
+        const size_t half = (size_t)(p.tp.ldp >> 1);
+        const size_t base = ((size_t)(kk & 1u) * 8 + p.tp.rank) * SK_LL_ROWS;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t mine = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(o[i]));
+          const uint32_t up = __shfl_down_sync(0xffffffffu, mine, 1);
+          if ((lane & 1) == 0 && n_ok && c0 + i < p.B) {
+            const unsigned long long cell = ((unsigned long long)kk << 32) | (up << 16) | mine;
+            const size_t idx = (base + (size_t)(c0 + i)) * half + (size_t)(n >> 1);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q < p.tp.world && q != p.tp.rank)
+                asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p.tp.ll[q] + idx), "l"(cell) : "memory");
+          }
+        }
+      } else if (n_ok) {
         bf16 *dcol = p.D + (size_t)c0 * p.ldd + n;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           if (c0 + i < p.B) dcol[(size_t)i * p.ldd] = __float2bfloat16_rn(o[i]);
+      }
+    }
+    if (p.epilogue == SK_EPI_TP && (p.tp.mode & 2) && rank * 8 < p.B) {
+      // LL receive: the peers' cells of my rows arrive in MY memory; sum in rank order with my own partial in its place
+      const uint32_t kk = (uint32_t)(p.tp.ll_seq[0] + 1);
+      const size_t half = (size_t)(p.tp.ldp >> 1);
+      const unsigned long long *mybuf = p.tp.ll[p.tp.rank];
+#pragma unroll 1
+      for (int lg = 0; lg < LG; ++lg) {
+        const int c0 = (lg * SKC_CS + rank) * 8;
+        if (c0 >= p.B) break;
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          if (c0 + i >= p.B) break;
+          float sum = 0.f;
+#pragma unroll
+          for (int src = 0; src < SKC_CS; ++src) sum += recv[((src * LG + lg) * 8 + i) * 128 + et];     // k order, as above
+          const float own = bf16_round(sum + bv);
+          // the cells of ALL sources are requested together and re-read until each carries this call's index: one L2
+          // round trip when the peers were not later than this rank, whatever the world size
+          uint32_t pb[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pb[q] = 0u;
+          if ((lane & 1) == 0 && n_ok) {
+            const unsigned long long *cp = mybuf + (((size_t)(kk & 1u) * 8) * SK_LL_ROWS + (size_t)(c0 + i)) * half + (size_t)(n >> 1);
+            const size_t qstride = (size_t)SK_LL_ROWS * half;
+            unsigned long long cell[8];
+            bool all;
+            const long long t0 = clock64();
+            do {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (q < p.tp.world && q != p.tp.rank)
+                  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(cell[q]) : "l"(cp + (size_t)q * qstride) : "memory");
+              all = true;
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (q < p.tp.world && q != p.tp.rank) all = all && ((uint32_t)(cell[q] >> 32) == kk);
+              if (!all && clock64() - t0 > 60000000000LL) {
+                printf("ocrb fused all-reduce (LL): rank %d never received call %u from every peer (tile %d row %d)\n", p.tp.rank, kk, tile, c0 + i);
+                __trap();
+              }
+            } while (!all);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q < p.tp.world && q != p.tp.rank) pb[q] = (uint32_t)cell[q];
+          }
+          __syncwarp();
+          float acc = 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < p.tp.world) {
+              const uint32_t got = __shfl_sync(0xffffffffu, pb[q], lane & ~1);
+              const float v = (q == p.tp.rank) ? own : __uint_as_float(((lane & 1) ? (got >> 16) : (got & 0xffffu)) << 16);
+              acc += v;
+            }
+          if (n_ok) {
+            bf16 *xp = p.tp.x + (size_t)(c0 + i) * p.tp.ldx + n;
+            *xp = __float2bfloat16_rn(__bfloat162float(*xp) + bf16_round(acc));
+          }
+        }
+      }
+      named_bar_sync(1, 128);
+      if (et == 0) {
+        const int units_per_tile = (p.B + 7) / 8 < SKC_CS ? (p.B + 7) / 8 : SKC_CS;
+        const int n_units = (int)(gridDim.x / SKC_CS) * units_per_tile;
+        const int t = atomicAdd(&p.tp.ll_seq[1], 1);
+        if (t == n_units - 1) {                          // last unit of this call on this rank: publish the call index
+          p.tp.ll_seq[1] = 0;
+          __threadfence();
+          p.tp.ll_seq[0] = (int)kk;
+        }
       }
     }
     // ───────────── tensor parallel: all-reduce + residual add of this CTA's columns, in place of a second kernel ─────────────
@@ -701,7 +796,7 @@ skinny_cluster_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     // Units exchange independently: a tile's reduction overlaps the weight streaming of the clusters still at work, and
     // the 160 all-reduce launches of a 72B-class decode step disappear.  Slot reuse is safe for the reason given in
     // comm.cu: a peer announces call k + 1 only after griddepcontrol.wait, i.e. after its call k has completely finished.
-    if (p.epilogue == SK_EPI_TP && rank * 8 < p.B) {
+    if (p.epilogue == SK_EPI_TP && !(p.tp.mode & 2) && rank * 8 < p.B) {
       const int unit = tile * SKC_CS + rank;
       const int k = p.tp.seq[unit] + 1;
       // the partial stores of all 128 threads happen-before the barrier, the announcing threads' st.release.sys after it:
@@ -980,8 +1075,9 @@ extern "C" int ocrb_allreduce_residual_bf16(void *x, int64_t ldx, const void *co
 extern "C" int ocrb_skinny_rowparallel_tp_bf16(const void *X, int64_t ldx, const void *W, int64_t ldw, int32_t B, int32_t N,
                                                int32_t K, void *x, int64_t ldx_res, const void *const *data_ptrs,
                                                int64_t ld_part, void *const *fused_flag_ptrs, int32_t *fused_seq,
-                                               void *const *flag_ptrs, int32_t *seq, int32_t world, int32_t rank,
-                                               void *workspace, int32_t allow_fused, void *stream) {
+                                               void *const *flag_ptrs, int32_t *seq, void *const *ll_ptrs, int32_t *ll_seq,
+                                               int32_t world, int32_t rank, void *workspace, int32_t allow_fused,
+                                               void *stream) {
   OCRB_REQUIRE(x && data_ptrs && fused_flag_ptrs && fused_seq && flag_ptrs && seq, "skinny_rowparallel_tp_bf16: null pointer");
   OCRB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "skinny_rowparallel_tp_bf16: bad world/rank");
   OCRB_REQUIRE(N % 8 == 0 && ldx_res % 8 == 0 && ld_part % 8 == 0, "skinny_rowparallel_tp_bf16: N and strides must be multiples of 8");
@@ -1003,7 +1099,13 @@ extern "C" int ocrb_skinny_rowparallel_tp_bf16(const void *X, int64_t ldx, const
       const char *e = getenv("OCRB_TP_FUSED_MODE");
       mode = e ? atoi(e) : 0;
     }
-    tp.mode = mode;
+    tp.mode = mode & 1;
+  }
+  if (allow_fused == 2) {
+    OCRB_REQUIRE(ll_ptrs && ll_seq && B <= SK_LL_ROWS && ld_part % 2 == 0, "skinny_rowparallel_tp_bf16: LL route needs its buffers and B <= 64");
+    for (int r = 0; r < world; ++r) tp.ll[r] = (unsigned long long *)ll_ptrs[r];
+    tp.ll_seq = ll_seq;
+    tp.mode |= 2;
   }
   g_tp_ctx = allow_fused ? &tp : nullptr;
   g_tp_fused = false;

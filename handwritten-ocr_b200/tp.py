@@ -128,9 +128,12 @@ class PeerAllReduce:
         # all-reduce fused into the row-parallel GEMM's epilogue: one flag row per (tile, cluster CTA) exchange unit
         self.fz_flags = torch.zeros(512 * 8, dtype=torch.int32, device=device)
         self.fz_seq = torch.zeros(512, dtype=torch.int32, device=device)
-        # opt-in: bit-equal to the two-kernel route, measured 3 % slower per decode step at TP-2 on 72B-class shards
-        # (profiles/r02_notes.md, "Fused GEMM + all-reduce")
-        self.fused = os.environ.get("OCRB_TP_FUSED", "0") == "1"
+        # LL route of the fused exchange: cells of (2 x bf16, call index) pushed into every peer's receive buffer
+        self.ll_buf = torch.zeros(2 * 8 * 64 * (hidden // 2), dtype=torch.int64, device=device)
+        self.ll_seq = torch.zeros(2, dtype=torch.int32, device=device)
+        # 0: GEMM + all-reduce kernel; 1: exchange in the GEMM epilogue, flag + pull; 2: exchange in the epilogue, LL push
+        # default 2: measured 17.2-17.5 ms per decode step against 17.8-18.0 (route 0) and 18.3 (route 1) at TP-2 on 72B-class shards
+        self.fused = int(os.environ.get("OCRB_TP_FUSED", "2"))
         torch.cuda.synchronize()
 
         def handle(t):
@@ -140,11 +143,11 @@ class PeerAllReduce:
             return (h.raw, off.value)
 
         mine = {"data": handle(self.local), "flags": handle(self.flags), "am_pairs": handle(self.am_pairs),
-                "am_flags": handle(self.am_flags), "fz_flags": handle(self.fz_flags)}
+                "am_flags": handle(self.am_flags), "fz_flags": handle(self.fz_flags), "ll_buf": handle(self.ll_buf)}
         everyone = [None] * self.world
         comm.dist.all_gather_object(everyone, mine, group=comm.group)
         slot_bytes = self.MAX_ROWS * hidden * 2
-        data_base, flag_ptr, am_pair_ptr, am_flag_ptr, fz_flag_ptr = [], [], [], [], []
+        data_base, flag_ptr, am_pair_ptr, am_flag_ptr, fz_flag_ptr, ll_ptr = [], [], [], [], [], []
         for r, item in enumerate(everyone):
             if r == self.rank:
                 data_base.append(self.local.data_ptr())
@@ -152,9 +155,10 @@ class PeerAllReduce:
                 am_pair_ptr.append(self.am_pairs.data_ptr())
                 am_flag_ptr.append(self.am_flags.data_ptr())
                 fz_flag_ptr.append(self.fz_flags.data_ptr())
+                ll_ptr.append(self.ll_buf.data_ptr())
                 continue
             out = []
-            for key in ("data", "flags", "am_pairs", "am_flags", "fz_flags"):
+            for key in ("data", "flags", "am_pairs", "am_flags", "fz_flags", "ll_buf"):
                 raw, off = item[key]
                 p = ctypes.c_void_p()
                 _lib.call("ocrb_comm_ipc_open", ctypes.create_string_buffer(raw, 64), off, ctypes.byref(p))
@@ -164,12 +168,14 @@ class PeerAllReduce:
             am_pair_ptr.append(out[2])
             am_flag_ptr.append(out[3])
             fz_flag_ptr.append(out[4])
+            ll_ptr.append(out[5])
         arr = ctypes.c_void_p * self.world
         self._data_ptrs = [arr(*[b + s * slot_bytes for b in data_base]) for s in range(2)]
         self._flag_ptrs = arr(*flag_ptr)
         self._am_pair_ptrs = arr(*am_pair_ptr)
         self._am_flag_ptrs = arr(*am_flag_ptr)
         self._fz_flag_ptrs = arr(*fz_flag_ptr)
+        self._ll_ptrs = arr(*ll_ptr)
         self.calls = 0
         comm.dist.barrier(group=comm.group)          # nobody launches before every mapping exists
 
@@ -193,8 +199,9 @@ class PeerAllReduce:
         rows = X.shape[0]
         self._lib.call("ocrb_skinny_rowparallel_tp_bf16", X.data_ptr(), X.stride(0), W.data_ptr(), W.stride(0), rows,
                        W.shape[0], X.shape[1], x.data_ptr(), x.stride(0), self._data_ptrs[slot], self.hidden,
-                       self._fz_flag_ptrs, self.fz_seq.data_ptr(), self._flag_ptrs, self.seq.data_ptr(), self.world, self.rank,
-                       workspace.data_ptr(), 1 if self.fused else 0, torch.cuda.current_stream().cuda_stream)
+                       self._fz_flag_ptrs, self.fz_seq.data_ptr(), self._flag_ptrs, self.seq.data_ptr(), self._ll_ptrs,
+                       self.ll_seq.data_ptr(), self.world, self.rank, workspace.data_ptr(), int(self.fused),
+                       torch.cuda.current_stream().cuda_stream)
         return x
 
     def argmax_step(self, logits_local: torch.Tensor, B: int, eos: int, pad: int, max_new: int, out_tokens, next_ids,

@@ -323,12 +323,16 @@ int ocrb_allreduce_residual_bf16(void *x, int64_t ldx, const void *const *data_p
  * ocrb_allreduce_residual_bf16 follows; both routes produce identical bits.  data_ptrs: every rank's partial slot for
  * this call (this rank's own at [rank]), row stride ld_part; fused_flag_ptrs: every rank's int32 [512][8] flag array and
  * fused_seq: int32[512] (zero-initialised once; used by the fused route); flag_ptrs / seq: the arrays of
- * ocrb_allreduce_residual_bf16 (fallback route).  allow_fused = 0 forces the two-kernel route.  B <= 128. */
+ * ocrb_allreduce_residual_bf16 (fallback route).  allow_fused: 0 = two-kernel route; 1 = fused, flag + pull (above); 2 = fused,
+ * LL protocol: every partial travels with its flag -- two bf16 values of adjacent rows and the call index in one 8-byte cell,
+ * pushed by one 8-byte store into every peer's receive buffer ll_ptrs[r] (uint64 [2][8][64][ld_part / 2], zero-initialised
+ * once; ll_seq: int32[2], zero-initialised once), so the exchange is ONE one-way NVLink latency and the receiver polls its
+ * own memory (B <= 64).  B <= 128. */
 int ocrb_skinny_rowparallel_tp_bf16(const void *X, int64_t ldx, const void *W, int64_t ldw, int32_t B, int32_t N,
                                     int32_t K, void *x, int64_t ldx_res, const void *const *data_ptrs,
                                     int64_t ld_part, void *const *fused_flag_ptrs, int32_t *fused_seq,
-                                    void *const *flag_ptrs, int32_t *seq, int32_t world, int32_t rank,
-                                    void *workspace, int32_t allow_fused, void *stream);
+                                    void *const *flag_ptrs, int32_t *seq, void *const *ll_ptrs, int32_t *ll_seq,
+                                    int32_t world, int32_t rank, void *workspace, int32_t allow_fused, void *stream);
 /* 1 when the last ocrb_skinny_rowparallel_tp_bf16 call ran the exchange inside the GEMM kernel. */
 int ocrb_skinny_rowparallel_tp_was_fused(void);
 

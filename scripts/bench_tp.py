@@ -51,7 +51,7 @@ if rank == 0:
                       "read_wall_s": round(float(t[1]), 3), "vision_ms": round(tm["vision_ms"], 1), "prefill_ms": round(tm["prefill_ms"], 1),
                       "weight_bytes_per_rank_per_step": wbytes, "hbm_gbs_per_rank": round(alg / (float(t[0]) * 1e-3) / 1e9, 1),
                       "hbm_frac_of_measured_peak": round(alg / (float(t[0]) * 1e-3) / 1e9 / peak, 4),
-                      "all_reduces_per_step": 2 * lcfg.text.layers, "all_reduce": "nccl" if comm.peer is None else ("fused into the row-parallel GEMM epilogue (peer memory)" if comm.peer.fused and _lib.load().ocrb_skinny_rowparallel_tp_was_fused() else "one-shot peer-memory kernel after the GEMM"),
+                      "all_reduces_per_step": 2 * lcfg.text.layers, "all_reduce": "nccl" if comm.peer is None else ({1: "fused into the row-parallel GEMM epilogue (flag + pull over peer memory)", 2: "fused into the row-parallel GEMM epilogue (LL push over peer memory)"}[comm.peer.fused] if comm.peer.fused and _lib.load().ocrb_skinny_rowparallel_tp_was_fused() else "one-shot peer-memory kernel after the GEMM"),
                       "lm_head": "logits all-gather" if os.environ.get("OCRB_TP_ARGMAX_GATHER") == "1" else "(max, lowest index) pair exchange", "init_s": round(t_init, 1), "tokens_generated": [len(x) for x in toks]}))
 sys.stdout.flush()
 eng.close()

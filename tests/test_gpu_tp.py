@@ -106,32 +106,39 @@ def _worker(rank, world, port, q):
             Wr = (torch.randn(N, K, generator=gw, device=dev) * 0.02).to(torch.bfloat16)
             Xr = torch.randn(Bq2, K, generator=gw, device=dev).to(torch.bfloat16)
             x0 = torch.randn(Bq2, N, generator=g, device=dev).to(torch.bfloat16)          # same on both ranks
-            xa, xb = x0.clone(), x0.clone()
+            xa, xb, xc = x0.clone(), x0.clone(), x0.clone()
             for _ in range(3):
-                peer2.fused = True
+                peer2.fused = 1                                   # exchange in the GEMM epilogue: flag + pull
                 peer2.row_parallel(Xr, Wr, xa, ws)
                 was = _lib.load().ocrb_skinny_rowparallel_tp_was_fused()
-                peer2.fused = False
+                peer2.fused = 0                                   # GEMM + all-reduce kernel
                 peer2.row_parallel(Xr, Wr, xb, ws)
+                peer2.fused = 2                                   # exchange in the GEMM epilogue: LL push
+                peer2.row_parallel(Xr, Wr, xc, ws)
+                was = was and _lib.load().ocrb_skinny_rowparallel_tp_was_fused()
             torch.cuda.synchronize()
             assert was == 1, "expected the cluster kernel (fused exchange) for this shape"
             assert torch.equal(xa, xb), ("fused all-reduce differs from the two-kernel route", K, Bq2)
+            assert torch.equal(xc, xb), ("LL fused all-reduce differs from the two-kernel route", K, Bq2)
             part = (Xr.float() @ Wr.float().t())
             dist.all_reduce(part)
             approx = x0.float() + 3 * part
             assert ((xa.float() - approx).abs().max() / approx.abs().max()).item() < 0.03
-            peer2.fused = True
             gr3 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr3):
                 for _ in range(4):
+                    peer2.fused = 1
                     peer2.row_parallel(Xr, Wr, xa, ws)
+                    peer2.fused = 2
+                    peer2.row_parallel(Xr, Wr, xc, ws)
             for _ in range(3):
                 gr3.replay()
-            peer2.fused = False
+            peer2.fused = 0
             for _ in range(12):
                 peer2.row_parallel(Xr, Wr, xb, ws)
             torch.cuda.synchronize()
             assert torch.equal(xa, xb), ("graph-replayed fused all-reduce differs", K, Bq2)
+            assert torch.equal(xc, xb), ("graph-replayed LL fused all-reduce differs", K, Bq2)
             del gr3
         res_fused = True
     eng = engine.OcrEngine(w_local, max_batch=4, max_new_tokens=24, max_prompt=400, tp=comm)
