@@ -549,7 +549,8 @@ def run_tp_leg(torch, dist, dev, rank, world, pk, new_tokens: int = 384) -> dict
             same = [next((i for i, (x, y) in enumerate(zip(t0, t1)) if x != y), len(t0)) for t0, t1 in zip(toks, toks1)]
             out["tp2_parity_tiny"] = {"prefill_logits_rel_err": round(rel, 5), "tolerance": 0.02,
                                       "tokens_identical_for": same, "of": [len(t) for t in toks1],
-                                      "all_reduce": "nccl" if comm.peer is None else "one-shot peer-memory kernel",
+                                      "all_reduce": "nccl" if comm.peer is None else "one-shot peer-memory kernel (tiny shapes run on the stream-K GEMM; "
+                                                    "the fused epilogue exchange needs the cluster GEMM), pair-exchange arg max",
                                       "note": "partial sums are rounded to bf16 before the all-reduce (HF rowwise TP), so a near-tie may "
                                               "flip a greedy token; parity is judged on the logits",
                                       "ok": bool(rel < 0.02)}
@@ -588,7 +589,11 @@ def run_tp_leg(torch, dist, dev, rank, world, pk, new_tokens: int = 384) -> dict
                           "hbm_gbs_per_rank": round(alg / (step_ms * 1e-3) / 1e9, 1),
                           "hbm_frac_per_rank": round(alg / (step_ms * 1e-3) / 1e9 / pk["hbm"], 4),
                           "all_reduces_per_step": 2 * lcfg.text.layers,
-                          "all_reduce": "nccl" if comm.peer is None else "one-shot peer-memory kernel (csrc/comm.cu)",
+                          "all_reduce": "nccl" if comm.peer is None else
+                          {0: "one-shot peer-memory kernel after the GEMM (csrc/comm.cu)",
+                           1: "fused into the row-parallel GEMM epilogue, flag + pull over peer memory (csrc/skinny.cu)",
+                           2: "fused into the row-parallel GEMM epilogue, LL push over NVLink peer memory (csrc/skinny.cu)"}[int(comm.peer.fused)],
+                          "lm_head": "(max, lowest index) pair exchange over peer memory" if comm.peer is not None else "logits all-gather",
                           "tokens_generated": [len(x) for x in toks]}
         eng.close()
         del eng, comm, w

@@ -523,7 +523,8 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t local_saddr, uint32_t ra
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
 
-template <int BP, int BC, int SKC_CS>
+// TP: the tensor-parallel instantiation (exchange in the epilogue, below); the single-GPU instantiation carries none of it.
+template <int BP, int BC, int SKC_CS, bool TP = false>
 __global__ void __launch_bounds__(SK_THREADS, (BP > 64) ? SK_OCC_BIG : 2)
 skinny_cluster_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, SkinnyParams p) {
   constexpr int ST = (BP > 64) ? SK_ST_BIG : ((BP >= 64) ? 4 : SK_STAGES);
@@ -687,7 +688,7 @@ skinny_cluster_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = sk_gelu(o[i]);
       }
-      if (p.epilogue == SK_EPI_TP && (p.tp.mode & 2)) {
+      if (TP && (p.tp.mode & 2)) {
         // LL protocol (as NCCL's low-latency one): the partial travels WITH its flag -- two bf16 values of adjacent rows
         // and the call index in one 8-byte cell, pushed by one 8-byte store (atomic over NVLink) into every peer's
         // receive buffer.  No fence, no flag round trip: the receiver polls its own memory for cells of this call.
@@ -714,7 +715,7 @@ skinny_cluster_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
           if (c0 + i < p.B) dcol[(size_t)i * p.ldd] = __float2bfloat16_rn(o[i]);
       }
     }
-    if (p.epilogue == SK_EPI_TP && (p.tp.mode & 2) && rank * 8 < p.B) {
+    if (TP && (p.tp.mode & 2) && rank * 8 < p.B) {
       // LL receive: the peers' cells of my rows arrive in MY memory; sum in rank order with my own partial in its place
       const uint32_t kk = (uint32_t)(p.tp.ll_seq[0] + 1);
       const size_t half = (size_t)(p.tp.ldp >> 1);
@@ -796,7 +797,7 @@ skinny_cluster_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
     // Units exchange independently: a tile's reduction overlaps the weight streaming of the clusters still at work, and
     // the 160 all-reduce launches of a 72B-class decode step disappear.  Slot reuse is safe for the reason given in
     // comm.cu: a peer announces call k + 1 only after griddepcontrol.wait, i.e. after its call k has completely finished.
-    if (p.epilogue == SK_EPI_TP && !(p.tp.mode & 2) && rank * 8 < p.B) {
+    if (TP && !(p.tp.mode & 2) && rank * 8 < p.B) {
       const int unit = tile * SKC_CS + rank;
       const int k = p.tp.seq[unit] + 1;
       // the partial stores of all 128 threads happen-before the barrier, the announcing threads' st.release.sys after it:
@@ -850,13 +851,13 @@ skinny_cluster_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
   }
 }
 
-template <int BP, int BC, int CS>
+template <int BP, int BC, int CS, bool TP = false>
 static int launch_skinny_cluster(const CUtensorMap &mw, const CUtensorMap &mx, const SkinnyParams &p, cudaStream_t st) {
   constexpr int ST = (BP > 64) ? SK_ST_BIG : ((BP >= 64) ? 4 : SK_STAGES);
   constexpr size_t smem = (size_t)ST * (SK_W_BYTES + BP * SK_BK * 2) + 1024 /*align*/ + 320 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
-    OCRB_CUDA(cudaFuncSetAttribute(skinny_cluster_kernel<BP, BC, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OCRB_CUDA(cudaFuncSetAttribute(skinny_cluster_kernel<BP, BC, CS, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -873,7 +874,7 @@ static int launch_skinny_cluster(const CUtensorMap &mw, const CUtensorMap &mx, c
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled(1) ? 2 : 1;
-  OCRB_CUDA(cudaLaunchKernelEx(&cfg, skinny_cluster_kernel<BP, BC, CS>, mw, mx, p));
+  OCRB_CUDA(cudaLaunchKernelEx(&cfg, skinny_cluster_kernel<BP, BC, CS, TP>, mw, mx, p));
   return check_launch("skinny_cluster_kernel");
 }
 
@@ -917,11 +918,11 @@ static int pick_cluster_size(int tiles) {
   return 0;
 }
 
-template <int BP, int BC>
+template <int BP, int BC, bool TP = false>
 static int launch_skinny_cluster_cs(int cs, const CUtensorMap &mw, const CUtensorMap &mx, const SkinnyParams &p, cudaStream_t st) {
-  if (cs == 4) return launch_skinny_cluster<BP, BC, 4>(mw, mx, p, st);
-  if (cs == 3) return launch_skinny_cluster<BP, BC, 3>(mw, mx, p, st);
-  return launch_skinny_cluster<BP, BC, 2>(mw, mx, p, st);
+  if (cs == 4) return launch_skinny_cluster<BP, BC, 4, TP>(mw, mx, p, st);
+  if (cs == 3) return launch_skinny_cluster<BP, BC, 3, TP>(mw, mx, p, st);
+  return launch_skinny_cluster<BP, BC, 2, TP>(mw, mx, p, st);
 }
 
 template <int BP, int BC>
@@ -1045,10 +1046,15 @@ extern "C" int ocrb_skinny_gemm_bf16(const void *X, int64_t ldx, const void *W, 
     const int cs = (use_cluster && epilogue != OCRB_EPI_SWIGLU && p.num_tiles * 2 <= sm_count() && p.num_kb >= 16)
                        ? pick_cluster_size(p.num_tiles) : 0;
     if (cs > 0) {
-      if (g_tp_ctx && epilogue == OCRB_EPI_NONE && !bias && p.num_tiles * cs <= SK_TP_UNITS) {
+      if (g_tp_ctx && epilogue == OCRB_EPI_NONE && !bias && p.num_tiles * cs <= SK_TP_UNITS && B <= 64) {
+        // tensor-parallel instantiation: the exchange is the epilogue (decode batches only)
         p.tp = *g_tp_ctx;
         p.epilogue = SK_EPI_TP;
         g_tp_fused = true;
+        if (B <= 8) return launch_skinny_cluster_cs<16, 8, true>(cs, mw, mx, p, st);
+        if (B <= 16) return launch_skinny_cluster_cs<16, 16, true>(cs, mw, mx, p, st);
+        if (B <= 32) return launch_skinny_cluster_cs<32, 32, true>(cs, mw, mx, p, st);
+        return launch_skinny_cluster_cs<64, 64, true>(cs, mw, mx, p, st);
       }
       if (B <= 8) return launch_skinny_cluster_cs<16, 8>(cs, mw, mx, p, st);
       if (B <= 16) return launch_skinny_cluster_cs<16, 16>(cs, mw, mx, p, st);
