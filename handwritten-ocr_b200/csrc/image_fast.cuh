@@ -17,7 +17,9 @@
 #include <stdint.h>
 
 #ifndef OCRB_EMU
+#ifndef OCRB_DYN_SMEM
 #define OCRB_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
 #endif
 
 namespace ocrb {

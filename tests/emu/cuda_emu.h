@@ -73,6 +73,9 @@ static inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATO
 
 template <class T>
 static inline T __ldg(const T *p) { return *p; }
+template <class T>
+static inline T __ldcg(const T *p) { return *p; }
+static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
   const uint64_t v = ((uint64_t)y << 32) | x;
