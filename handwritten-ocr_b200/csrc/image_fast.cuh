@@ -38,12 +38,19 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
 __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
 
-// gray values of the 4 RGB pixels held in three consecutive 32-bit words, packed into one word
+// gray values of the 4 RGB pixels held in three consecutive 32-bit words, packed into one word.  The 15-bit coefficients
+// split into byte pairs (9798 = 38 * 256 + 70, 19235 = 75 * 256 + 35, 3735 = 14 * 256 + 151), so a pixel's weighted sum is two
+// dp4a over its three bytes (the fourth byte of the register meets a zero coefficient) instead of three IMAD on extracted bytes.
+__device__ __forceinline__ uint32_t gray_px_dp4a(uint32_t rgbx) {
+  const uint32_t hi = __dp4a(rgbx, 0x000e4b26u, 0u);      // 38 R + 75 G + 14 B
+  const uint32_t lo = __dp4a(rgbx, 0x00972346u, 16384u);  // 70 R + 35 G + 151 B + rounding
+  return (hi * 256u + lo) >> 15;
+}
 __device__ __forceinline__ uint32_t gray4_from_rgb12(uint32_t a, uint32_t b, uint32_t c) {
-  const uint32_t g0 = gray_px(a & 0xffu, (a >> 8) & 0xffu, (a >> 16) & 0xffu);
-  const uint32_t g1 = gray_px(a >> 24, b & 0xffu, (b >> 8) & 0xffu);
-  const uint32_t g2 = gray_px((b >> 16) & 0xffu, b >> 24, c & 0xffu);
-  const uint32_t g3 = gray_px((c >> 8) & 0xffu, (c >> 16) & 0xffu, c >> 24);
+  const uint32_t g0 = gray_px_dp4a(a);
+  const uint32_t g1 = gray_px_dp4a(__funnelshift_r(a, b, 24));
+  const uint32_t g2 = gray_px_dp4a(__funnelshift_r(b, c, 16));
+  const uint32_t g3 = gray_px_dp4a(c >> 8);
   return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
 }
 
@@ -761,7 +768,10 @@ deskew_angle_par_kernel(const int32_t *__restrict__ ext, int H, int W, double *_
 }
 
 // ───────────────────────── cv2.warpAffine(INTER_CUBIC, BORDER_REPLICATE) ─────────────────────────
-// OpenCV fixed-point bicubic table: int16 [1024][16], index (fy*32 + fx), built on the host.
+// OpenCV fixed-point bicubic table: int16 [1024][16], built on the host.  Index (fx*32 + fy), the transpose of OpenCV's: along an
+// output row of a slightly rotated page fx stays put while fy sweeps its 32 values, so the 32 lanes of a warp read 32
+// CONSECUTIVE 32-byte rows (8 cache lines) instead of rows 1 KB apart (32 lines) -- the weight loads were two thirds of the
+// kernel's L1 wavefronts.
 __device__ int16_t g_cubic_itab[1024 * 16];
 
 // Host: OpenCV's interpolateCubic + initInterTab2D (fp32, unfused), incl. the ksize/2 quirk.
@@ -808,7 +818,7 @@ static inline void build_cubic_itab(int16_t *out) {
         else iw[mk1][mk2] = (int16_t)(iw[mk1][mk2] - diff);
       }
       for (int ky = 0; ky < 4; ++ky)
-        for (int kx = 0; kx < 4; ++kx) out[(fy * 32 + fx) * 16 + ky * 4 + kx] = (int16_t)iw[ky][kx];
+        for (int kx = 0; kx < 4; ++kx) out[(fx * 32 + fy) * 16 + ky * 4 + kx] = (int16_t)iw[ky][kx];
     }
 }
 
@@ -866,7 +876,7 @@ warp_affine_cubic_dp2a_kernel(const uint8_t *__restrict__ src, uint8_t *__restri
   sy = imin(imax(sy, -32768), 32767);
   // the 16 fixed-point weights of this sub-pixel position: two 16-byte loads (the table row is 32-byte aligned);
   // wpk[i] = weights 2i (low half), 2i + 1 (high half)
-  const uint4 *wt4 = reinterpret_cast<const uint4 *>(g_cubic_itab + (((Y & 31) * 32 + (X & 31)) << 4));
+  const uint4 *wt4 = reinterpret_cast<const uint4 *>(g_cubic_itab + (((X & 31) * 32 + (Y & 31)) << 4));
   const uint4 wa = wt4[0], wb = wt4[1];
   const uint32_t wpk[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
   int ys[4];

@@ -105,6 +105,12 @@ static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 
+// unsigned dp4a: four byte products added to c
+static inline uint32_t __dp4a(uint32_t a, uint32_t b, uint32_t c) {
+  for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+  return c;
+}
+
 // per 16-bit lane, signed: max(min(a + b, c), 0)   (VIADDMNMX.S16x2.RELU)
 static inline uint32_t __viaddmin_s16x2_relu(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r = 0;
