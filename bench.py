@@ -449,6 +449,10 @@ def run_b200(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        # the line is out; a rank whose context died in the tensor-parallel leg must not hold the others in the last barrier
+        bye = threading.Timer(60.0, lambda: os._exit(0))
+        bye.daemon = True
+        bye.start()
         try:
             dist.barrier()
             torch.cuda.synchronize()

@@ -98,16 +98,19 @@ sharpen_vec16_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
   const int v = blockIdx.x * 64 + (threadIdx.x & 63);
   const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
   if (v >= nv || y >= H) return;
-  const int yu = y == 0 ? 1 : y - 1, yd = y == H - 1 ? H - 2 : y + 1;
+  // 32-bit vector offsets inside the image (H * nv < 2^27 for any page), one 64-bit base per image
   const uint4 *im = reinterpret_cast<const uint4 *>(src) + (size_t)blockIdx.z * H * nv;
-  const uint4 *rowp = im + (size_t)y * nv;
-  const uint4 cu = rowp[v];
-  const uint4 up = im[(size_t)yu * nv + v];
-  const uint4 dn = im[(size_t)yd * nv + v];
+  const unsigned rv = (unsigned)y * (unsigned)nv + (unsigned)v;
+  const unsigned ru = (y == 0) ? rv + (unsigned)nv : rv - (unsigned)nv;          // reflect-101: row -1 -> row 1
+  const unsigned rd = (y == H - 1) ? rv - (unsigned)nv : rv + (unsigned)nv;      //              row H -> row H - 2
+  const uint4 cu = im[rv];
+  const uint4 up = im[ru];
+  const uint4 dn = im[rd];
+  const uint32_t *imw = reinterpret_cast<const uint32_t *>(im);
   uint32_t wl, wr;
-  if (v > 0) wl = reinterpret_cast<const uint32_t *>(rowp)[4 * v - 1];
+  if (v > 0) wl = imw[4u * rv - 1u];
   else wl = (C == 3) ? __byte_perm(cu.x, cu.y, 0x5430) : __byte_perm(cu.x, 0u, 0x1000);
-  if (v + 1 < nv) wr = reinterpret_cast<const uint32_t *>(rowp)[4 * v + 4];
+  if (v + 1 < nv) wr = imw[4u * rv + 4u];
   else wr = (C == 3) ? __byte_perm(cu.z, cu.w, 0x0432) : __byte_perm(cu.w, 0u, 0x0002);
   const uint32_t w[6] = {wl, cu.x, cu.y, cu.z, cu.w, wr};
   const uint32_t u[4] = {up.x, up.y, up.z, up.w}, d[4] = {dn.x, dn.y, dn.z, dn.w};
@@ -119,7 +122,7 @@ sharpen_vec16_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
     const uint32_t right = (C == 3) ? __byte_perm(cur, next, 0x6543) : __byte_perm(cur, next, 0x4321);
     o[j] = sharpen_word(cur, u[j], d[j], left, right);
   }
-  (reinterpret_cast<uint4 *>(dst) + ((size_t)blockIdx.z * H + y) * nv)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  (reinterpret_cast<uint4 *>(dst) + (size_t)blockIdx.z * H * nv)[rv] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // ───────────────────────── A.2 CLAHE ─────────────────────────
