@@ -4,6 +4,7 @@
 // _rn intrinsic so that nothing is contracted or reassociated.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include "image_fast.cuh"
 
 namespace ocrb {
@@ -387,7 +388,16 @@ extern "C" int ocrb_high_contrast_u8(const uint8_t *src, uint8_t *dst, uint8_t *
 static int thresh_run(const uint8_t *src, int C, uint8_t *dst, int n_img, int H, int W, cudaStream_t st) {
   const int aligned = (W % 4 == 0) && ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 3) == 0;
   const dim3 grid(cdiv(W, AT2_TW), cdiv(H, AT2_TH), n_img);
-  if (C == 3) adaptive_thresh_tile_kernel<3><<<grid, 256, 0, st>>>(src, dst, H, W, aligned);
+  // 4 CTAs per SM at 63 registers (default; 64 pages: 0.223 ms) or 5 at 48 with a few spilled words (0.232 ms): OCRB_AT_OCC=5
+  static int occ = -1;
+  if (occ < 0) {
+    const char *e = getenv("OCRB_AT_OCC");
+    occ = (e && atoi(e) == 5) ? 5 : 4;
+  }
+  if (occ == 5) {
+    if (C == 3) adaptive_thresh_tile_kernel<3, 5><<<grid, 256, 0, st>>>(src, dst, H, W, aligned);
+    else adaptive_thresh_tile_kernel<1, 5><<<grid, 256, 0, st>>>(src, dst, H, W, aligned);
+  } else if (C == 3) adaptive_thresh_tile_kernel<3><<<grid, 256, 0, st>>>(src, dst, H, W, aligned);
   else adaptive_thresh_tile_kernel<1><<<grid, 256, 0, st>>>(src, dst, H, W, aligned);
   return check_launch("adaptive_thresh_tile_kernel");
 }
@@ -468,7 +478,14 @@ extern "C" int ocrb_warp_affine_cubic_u8(const uint8_t *src, uint8_t *dst, int32
   int rc = ensure_itab();
   if (rc) return rc;
   const dim3 grid(cdiv(W, 256), H, n_img);
-  if (C == 3) warp_affine_cubic_dp2a_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, M);
+  // 5 CTAs per SM at 48 registers (default; 64 pages: 0.66 ms for the whole deskew against 0.72 ms) or 4 at 64: OCRB_WARP_OCC=4
+  static int occ = -1;
+  if (occ < 0) {
+    const char *e = getenv("OCRB_WARP_OCC");
+    occ = (e && atoi(e) == 4) ? 4 : 5;
+  }
+  if (occ == 5 && C == 3) warp_affine_cubic_dp2a_kernel<3, 5><<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, M);
+  else if (C == 3) warp_affine_cubic_dp2a_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, M);
   else warp_affine_cubic_dp2a_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, M);
   return check_launch("warp_affine_cubic_kernel");
 }

@@ -387,8 +387,8 @@ constexpr int AT2_WPR = AT2_SW / 4;          // 22 words per staged row
 // pass (sequential FMA, OpenCV's order) converts bytes with a PRMT + FSUB instead of I2F; the column pass keeps a
 // column's 44 row-pass values in registers for 24 outputs; results replace the tile's own centre bytes in shared memory
 // and leave as 32-bit stores.  aligned: W % 4 == 0 and 4-byte aligned images.
-template <int C>
-__global__ void __launch_bounds__(256)
+template <int C, int OCC = 4>
+__global__ void __launch_bounds__(256, OCC)
 adaptive_thresh_tile_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H, int W, int aligned) {
   __shared__ __align__(16) uint8_t s_src[AT2_SH][AT2_SW];
   __shared__ float s_row[AT2_SH][AT2_TW + 1];
@@ -830,8 +830,8 @@ static inline void build_cubic_itab(int16_t *out) {
 // holds the 16 weights as int16 pairs (taps kx, kx + 1 of one source row), a PRMT puts the two source bytes of a channel
 // next to each other, and one IDP.2A adds both products -- 4 PRMT + 6 IDP.2A per source row instead of 12 byte extractions,
 // 4 weight extractions and 12 IMAD.  Integer sums, so the order of the taps does not matter.
-template <int C>
-__global__ void __launch_bounds__(256)
+template <int C, int OCC = 4>
+__global__ void __launch_bounds__(256, OCC)
 warp_affine_cubic_dp2a_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int H, int W,
                               const double *__restrict__ Mall) {
   __shared__ double s_m[2];
