@@ -77,3 +77,23 @@ extern "C" int emu_warp(const uint8_t *src, uint8_t *dst, int n, int H, int W, i
   else emu::launch(grid, dim3(256), 0, [&] { warp_affine_cubic_dp2a_kernel<1>(src, dst, H, W, M); });
   return 0;
 }
+
+// the host-side CLAHE cell boundaries alone (image.cu: clahe_run), for property tests over many page sizes
+extern "C" int emu_clahe_cells(int H, int W, int *xb, int *yb, float *inv_tw_out, float *inv_th_out) {
+  int We = W, He = H;
+  if (!(W % 8 == 0 && H % 8 == 0)) {
+    We = W + (8 - W % 8);
+    He = H + (8 - H % 8);
+  }
+  const int tw = We / 8, th = He / 8;
+  volatile float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+  ClaheCells cells;
+  const int ok = clahe_cells_host(H, W, inv_tw, inv_th, &cells);
+  for (int k = 0; k < 10; ++k) {
+    xb[k] = cells.xb[k];
+    yb[k] = cells.yb[k];
+  }
+  *inv_tw_out = inv_tw;
+  *inv_th_out = inv_th;
+  return ok;
+}

@@ -196,3 +196,65 @@ def test_hull_tree_equals_single_scan_on_random_extents(emu):
             assert np.isnan(angle[0]), (trial, angle[0])
         else:
             assert angle[0] == ref, (trial, H, W, angle[0], ref)
+
+
+def test_clahe_cell_boundaries_match_the_per_pixel_formula(emu):
+    """clahe_apply_cells_kernel trusts the host to say where the LUT quadruple changes.  For many page sizes the boundaries
+    must reproduce, coordinate by coordinate, the tile index the per-pixel kernel (and OpenCV) derive in fp32:
+    floor(x * inv_tw - 0.5)."""
+    rng = np.random.default_rng(31)
+    sizes = [(768, 1024), (1024, 768), (389, 517), (8, 8), (4000, 3000), (2481, 3508)] + \
+            [(int(rng.integers(8, 4200)), int(rng.integers(8, 4200))) for _ in range(300)]
+    f32 = np.float32
+    for H, W in sizes:
+        xb = np.zeros(10, np.int32)
+        yb = np.zeros(10, np.int32)
+        itw, ith = ctypes.c_float(), ctypes.c_float()
+        ok = emu.emu_clahe_cells(H, W, P(xb), P(yb), ctypes.byref(itw), ctypes.byref(ith))
+        for n, b, inv in ((W, xb, f32(itw.value)), (H, yb, f32(ith.value))):
+            assert b[0] == 0 and b[9] == n and (np.diff(b) >= 0).all(), (H, W, b)
+            idx = np.arange(n, dtype=f32)
+            t1 = np.floor((idx * inv).astype(f32) - f32(0.5)).astype(np.int64)      # raw tile index, -1 .. 7
+            cell = np.clip(t1 + 1, 0, 8)
+            want = np.searchsorted(cell, np.arange(10), side="left")             # first coordinate of each cell
+            want[9] = n
+            assert np.array_equal(b, want), (H, W, n, b, want)
+        if W % 4 == 0 and all(int(v) % 4 == 0 for v in xb[:9]) and np.diff(xb).max() <= 1024 and np.diff(yb).max() <= 1024:
+            assert ok == 1, (H, W)
+        else:
+            assert ok == 0, (H, W)
+
+
+def test_sharpen_packed_lanes_saturate_both_ways(emu):
+    """Pixels drawn from the extremes: 5c - (u + d + l + r) reaches -1020 and +1275, so both clamps of the 16-bit-lane
+    arithmetic and the bias of 1020 are exercised in every lane position."""
+    rng = np.random.default_rng(41)
+    vals = np.array([0, 1, 2, 127, 128, 253, 254, 255], np.uint8)
+    for C, (H, W) in [(1, (12, 64)), (3, (12, 32))]:
+        shape = (H, W, 3) if C == 3 else (H, W)
+        img = aligned(shape)
+        img[...] = vals[rng.integers(0, len(vals), shape)]
+        src = aligned((1,) + shape)
+        src[0] = img
+        dst = aligned(src.shape, fill=9)
+        assert emu.emu_sharpen(P(src), P(dst), 1, H, W, C) == 0
+        ref = R.sharpen(img)
+        assert np.array_equal(dst[0], ref)
+        assert (ref == 0).any() and (ref == 255).any()
+
+
+def test_round_half_even_by_magic_add():
+    """The kernels round fp32 results in [0, 256) with `x + 1.5 * 2^23` and read the low mantissa bits (no F2I).  numpy's
+    float32 add rounds to nearest-even exactly like FADD.RN: the trick must equal rint on ties and on random values."""
+    f32 = np.float32
+    rng = np.random.default_rng(7)
+    x = np.concatenate([np.arange(0, 256, dtype=f32), np.arange(0, 256, dtype=f32) + f32(0.5),
+                        np.nextafter(np.arange(0, 256, dtype=f32) + f32(0.5), f32(0)),
+                        np.nextafter(np.arange(0, 256, dtype=f32) + f32(0.5), f32(300)),
+                        rng.uniform(0, 255.49, 200000).astype(f32)])
+    magic = f32(12582912.0)
+    got = (x + magic).view(np.int32) - np.int32(0x4B400000)
+    assert np.array_equal(got, np.rint(x).astype(np.int32))
+    # bytes as floats without a conversion: 2^23 + b has b in its low mantissa bits
+    b = np.arange(256, dtype=np.uint32)
+    assert np.array_equal(((b | np.uint32(0x4B000000)).view(f32) - f32(8388608.0)), b.astype(f32))
