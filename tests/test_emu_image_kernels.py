@@ -258,3 +258,35 @@ def test_round_half_even_by_magic_add():
     # bytes as floats without a conversion: 2^23 + b has b in its low mantissa bits
     b = np.arange(256, dtype=np.uint32)
     assert np.array_equal(((b | np.uint32(0x4B000000)).view(f32) - f32(8388608.0)), b.astype(f32))
+
+
+def test_fuzz_odd_sizes_binarize_and_clahe_luts(emu):
+    """Random small page sizes (odd widths, pages smaller than one tile, tiles cut by every edge) through the new kernels'
+    scalar / clamped paths."""
+    rng = np.random.default_rng(53)
+    for _ in range(12):
+        H, W, C = int(rng.integers(1, 150)), int(rng.integers(1, 150)), int(rng.choice([1, 3]))
+        img = page(rng, H, W, C, "noise" if rng.random() < 0.5 else "paper")
+        src = aligned((1,) + img.shape)
+        src[0] = img
+        dst = aligned((1, H, W), fill=5)
+        assert emu.emu_binarize(P(src), P(dst), 1, H, W, C) == 0
+        g = R.rgb2gray(img) if C == 3 else img
+        assert np.array_equal(dst[0], R.adaptive_threshold(g)), (H, W, C)
+    for _ in range(4):
+        H, W, C = int(rng.integers(8, 90)), int(rng.integers(8, 90)), int(rng.choice([1, 3]))
+        img = page(rng, H, W, C, "paper")
+        src = aligned((1,) + img.shape)
+        src[0] = img
+        dst = aligned((1, H, W), fill=9)
+        gray = aligned((1, H, W), fill=3)
+        lut = aligned((1, 64, 256))
+        vec = ctypes.c_int(0)
+        rc = emu.emu_high_contrast(P(src), P(dst), P(gray), P(lut), 1, H, W, C, ctypes.byref(vec))
+        assert rc in (0, 1), (H, W, C)
+        g = R.rgb2gray(img) if C == 3 else img
+        if C == 3:
+            assert np.array_equal(gray[0], g)
+        assert np.array_equal(lut[0].reshape(-1), np.asarray(R.clahe_luts(g)[0], np.uint8).reshape(-1)), (H, W, C)
+        if rc == 0:
+            assert np.array_equal(dst[0], R.clahe(g)), (H, W, C)
