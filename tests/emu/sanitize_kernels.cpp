@@ -1,0 +1,141 @@
+// TEST INFRASTRUCTURE: the emulated kernels (tests/emu/cuda_emu.h) as a standalone program to be built with
+//   g++ -fsanitize=address,undefined   -> out-of-bounds accesses to global buffers (exact-size heap blocks) and to
+//                                         __shared__ arrays (statics carry red zones), misaligned vector accesses
+//   g++ -fsanitize=thread              -> data races between the emulated CUDA threads (a missing __syncthreads, two
+//                                         threads writing one shared-memory word)
+// compute-sanitizer is closed on the GPU pool this repository is measured on (profiles/r02_sanitize.md); this is the
+// host-side stand-in for memcheck / racecheck of the kernels that can be emulated (image_fast.cuh, textops_kernels.cuh).
+// Results are not compared here (tests/test_emu_*_kernels.py do that); the sanitizers are the check.
+#include "cuda_emu.h"
+#include "../../handwritten-ocr_b200/csrc/image_fast.cuh"
+#include "../../handwritten-ocr_b200/csrc/textops_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+
+using namespace ocrb;
+
+static std::mt19937 rng(12345);
+static inline unsigned cdivu(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// exact-size, 64-byte aligned heap block (ASan puts red zones around it)
+template <class T>
+struct Buf {
+  T *p;
+  size_t n;
+  explicit Buf(size_t n_, int fill = -1) : n(n_) {
+    void *q = nullptr;
+    if (posix_memalign(&q, 64, n * sizeof(T) ? n * sizeof(T) : 1) != 0) std::abort();
+    p = static_cast<T *>(q);
+    for (size_t i = 0; i < n; ++i) p[i] = fill >= 0 ? (T)fill : (T)(rng() & 0xff);
+  }
+  ~Buf() { free(p); }
+};
+
+static void paper(uint8_t *img, size_t n) {
+  for (size_t i = 0; i < n; ++i) img[i] = (rng() % 23 == 0) ? (uint8_t)(rng() % 90) : (uint8_t)(230 + rng() % 20);
+}
+
+static void run_image(int n, int H, int W, int C) {
+  const size_t px = (size_t)n * H * W;
+  Buf<uint8_t> src(px * C), dst(px * C, 0), gray(px, 0), out1(px, 0), lut((size_t)n * 64 * 256, 0);
+  paper(src.p, px * C);
+  // sharpen
+  if ((W * C) % 16 == 0 && H >= 2) {
+    const int nv = W * C / 16;
+    const dim3 grid(cdivu(nv, 64), cdivu(H, 4), n);
+    if (C == 3) emu::launch(grid, dim3(256), 0, [&] { sharpen_vec16_kernel<3>(src.p, dst.p, H, nv); });
+    else emu::launch(grid, dim3(256), 0, [&] { sharpen_vec16_kernel<1>(src.p, dst.p, H, nv); });
+  }
+  // high_contrast
+  {
+    int We = W, He = H;
+    if (!(W % 8 == 0 && H % 8 == 0)) { We = W + (8 - W % 8); He = H + (8 - H % 8); }
+    const int tw = We / 8, th = He / 8;
+    if (tw >= 1 && th >= 1 && tw <= W && th <= H) {
+      const int area = tw * th;
+      int clip = (int)(3.0 * area / 256.0);
+      if (clip < 1) clip = 1;
+      const float ls = 255.0f / (float)area;
+      const uint8_t *g = (C == 3) ? gray.p : src.p;
+      const int vec_ok = (W % 16 == 0) && (tw % 16 == 0);
+      if (C == 3) emu::launch(dim3(64, n), dim3(256), 0, [&] { clahe_hist_lut_kernel<3>(src.p, gray.p, lut.p, H, W, tw, th, clip, ls, vec_ok); });
+      else emu::launch(dim3(64, n), dim3(256), 0, [&] { clahe_hist_lut_kernel<1>(src.p, nullptr, lut.p, H, W, tw, th, clip, ls, vec_ok); });
+      const float itw = 1.0f / (float)tw, ith = 1.0f / (float)th;
+      ClaheCells cells;
+      if (clahe_cells_host(H, W, itw, ith, &cells))
+        emu::launch(dim3(81, n), dim3(256), 0, [&] { clahe_apply_cells_kernel(g, out1.p, lut.p, H, W, itw, ith, cells); });
+    }
+  }
+  // binarize
+  {
+    const int aligned = (W % 4 == 0);
+    const dim3 grid(cdivu(W, AT2_TW), cdivu(H, AT2_TH), n);
+    if (C == 3) emu::launch(grid, dim3(256), 0, [&] { adaptive_thresh_tile_kernel<3>(src.p, out1.p, H, W, aligned); });
+    else emu::launch(grid, dim3(256), 0, [&] { adaptive_thresh_tile_kernel<1>(src.p, out1.p, H, W, aligned); });
+  }
+  // deskew: extents, hull tree + calipers, warp
+  if (W % 16 == 0) {
+    Buf<int32_t> ext((size_t)n * H * 3, 0);
+    Buf<double> angle(n, 0), M((size_t)n * 6, 0);
+    const int rows = n * H;
+    emu::launch(dim3(cdivu(rows, 8)), dim3(256), 0, [&] { dark_extents16_kernel(src.p, ext.p, W, C, rows); });
+    emu::launch(dim3(n), dim3(256), deskew_par_smem_bytes(H), [&] { deskew_angle_par_kernel(ext.p, H, W, angle.p, M.p); });
+    static bool built = false;
+    if (!built) { build_cubic_itab(g_cubic_itab); built = true; }
+    const dim3 grid(cdivu(W, 256), H, n);
+    if (C == 3) emu::launch(grid, dim3(256), 0, [&] { warp_affine_cubic_dp2a_kernel<3>(src.p, dst.p, H, W, M.p); });
+    else emu::launch(grid, dim3(256), 0, [&] { warp_affine_cubic_dp2a_kernel<1>(src.p, dst.p, H, W, M.p); });
+  }
+  std::printf("image n=%d %dx%d C=%d ok\n", n, H, W, C);
+}
+
+static void run_text() {
+  const int lens[][2] = {{1, 1}, {33, 31}, {64, 1}, {0, 5}, {70, 100}, {200, 255}};
+  const int np = 6;
+  std::vector<int32_t> a, b, oa{0}, ob{0};
+  int maxb = 0;
+  for (int k = 0; k < np; ++k) {
+    for (int i = 0; i < lens[k][0]; ++i) a.push_back((int32_t)(rng() % 5));
+    for (int i = 0; i < lens[k][1]; ++i) b.push_back((int32_t)(rng() % 5));
+    oa.push_back((int32_t)a.size());
+    ob.push_back((int32_t)b.size());
+    if (lens[k][1] > maxb) maxb = lens[k][1];
+  }
+  Buf<int32_t> A(a.size() + 1, 0), B(b.size() + 1, 0), OA(oa.size(), 0), OB(ob.size(), 0), out(np, 0);
+  std::copy(a.begin(), a.end(), A.p);
+  std::copy(b.begin(), b.end(), B.p);
+  std::copy(oa.begin(), oa.end(), OA.p);
+  std::copy(ob.begin(), ob.end(), OB.p);
+  emu::launch(dim3(np), dim3(64), 0, [&] { levenshtein_kernel<4, 64>(A.p, OA.p, B.p, OB.p, out.p); });
+  emu::launch(dim3(np), dim3(128), 0, [&] { levenshtein_kernel<8, 128>(A.p, OA.p, B.p, OB.p, out.p); });
+  // LCS: backbone = a sequences, versions = b sequences
+  std::vector<int64_t> wo(np);
+  size_t tot = 0;
+  int maxbb = 0;
+  for (int k = 0; k < np; ++k) {
+    wo[k] = (int64_t)tot;
+    tot += (size_t)lens[k][0] * lens[k][1];
+    if (lens[k][0] > maxbb) maxbb = lens[k][0];
+  }
+  Buf<uint8_t> work(tot + 1, 0);
+  Buf<int64_t> WO(np, 0);
+  std::copy(wo.begin(), wo.end(), WO.p);
+  Buf<int32_t> aligned(a.size() + 1, 0);
+  const int diag_stride = (maxbb + 2 + 7) & ~7;
+  emu::launch(dim3(np), dim3(LCS_THREADS), (size_t)3 * diag_stride * sizeof(uint16_t),
+              [&] { lcs_align_kernel(A.p, OA.p, B.p, OB.p, aligned.p, work.p, WO.p, diag_stride); });
+  std::printf("text ok\n");
+}
+
+int main() {
+  run_image(2, 64, 128, 3);    // vector histogram path, cell kernel, interior + border tiles
+  run_image(1, 96, 256, 1);
+  run_image(1, 50, 70, 3);     // reflect-101 tile extension, unaligned widths, scalar paths
+  run_image(1, 37, 64, 1);
+  run_image(2, 130, 160, 3);   // two tile rows of the threshold, ragged hull groups
+  run_text();
+  std::printf("emulated kernels: sanitizer run complete\n");
+  return 0;
+}
