@@ -33,6 +33,8 @@ struct alignas(16) uint4 { uint32_t x, y, z, w; };
 struct alignas(8) uint2 { uint32_t x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(8) float2 { float x, y; };
+struct alignas(8) int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
@@ -69,6 +71,52 @@ static inline T __shfl_xor_sync(unsigned, T v, int o) {
 }
 
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+// CUDA's overloaded integer min / max
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+// lane + d / lane - d of the warp; lanes without a source keep their own value
+template <class T>
+static inline T __shfl_down_sync(unsigned m, T v, unsigned d) {
+  const unsigned lane = threadIdx.x & 31;
+  (void)m;
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  const unsigned warp = threadIdx.x >> 5;
+  uint64_t bits = 0;
+  std::memcpy(&bits, &v, sizeof(T));
+  emu::cta->slots[warp][lane] = bits;
+  (*emu::cta->warp_bar)[warp]->arrive_and_wait();
+  const uint64_t o = emu::cta->slots[warp][lane + d < 32 ? lane + d : lane];
+  (*emu::cta->warp_bar)[warp]->arrive_and_wait();
+  T r;
+  std::memcpy(&r, &o, sizeof(T));
+  return r;
+}
+template <class T>
+static inline T __shfl_up_sync(unsigned, T v, unsigned d) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t bits = 0;
+  std::memcpy(&bits, &v, sizeof(T));
+  emu::cta->slots[warp][lane] = bits;
+  (*emu::cta->warp_bar)[warp]->arrive_and_wait();
+  const uint64_t o = emu::cta->slots[warp][lane >= d ? lane - d : lane];
+  (*emu::cta->warp_bar)[warp]->arrive_and_wait();
+  T r;
+  std::memcpy(&r, &o, sizeof(T));
+  return r;
+}
+// per-byte |a - b|
+static inline uint32_t __vabsdiffu4(uint32_t a, uint32_t b) {
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int x = (int)((a >> (8 * i)) & 0xffu), y = (int)((b >> (8 * i)) & 0xffu);
+    r |= (uint32_t)(x > y ? x - y : y - x) << (8 * i);
+  }
+  return r;
+}
+
 static inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 
 template <class T>

@@ -9,10 +9,12 @@
 #include "cuda_emu.h"
 #include "../../handwritten-ocr_b200/csrc/image_fast.cuh"
 #include "../../handwritten-ocr_b200/csrc/textops_kernels.cuh"
+#include "../../handwritten-ocr_b200/csrc/denoise_kernels.cuh"
 
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <string>
 
 using namespace ocrb;
 
@@ -129,7 +131,37 @@ static void run_text() {
   std::printf("text ok\n");
 }
 
-int main() {
+static void run_denoise(int H, int W, int C) {
+  const DenoiseHostTables &t = host_tables();
+  const size_t npix = (size_t)H * W;
+  Buf<uint8_t> src(npix * C), dst(npix * C, 0), ws(npix * 6, 0);
+  Buf<uint16_t> w0(NLM_LUT, 0), w1(NLM_LUT, 0), cb(3072, 0);
+  Buf<int2> yf(256, 0);
+  std::copy(t.w[0], t.w[0] + NLM_LUT, w0.p);
+  std::copy(t.w[1], t.w[1] + NLM_LUT, w1.p);
+  std::copy(t.cbrt_tab, t.cbrt_tab + 3072, cb.p);
+  std::memcpy(yf.p, t.yf, sizeof(t.yf));
+  paper(src.p, npix * C);
+  const dim3 grid(cdivu(W, NLM_COLS), cdivu(H, NLM_ROWS), 1);
+  if (C == 1) {
+    emu::launch(grid, dim3(32 * NLM_NW), 0, [&] { nlm_kernel<1>(src.p, dst.p, H, W, w0.p); });
+  } else {
+    uint8_t *ab0 = ws.p, *ab1 = ws.p + 2 * npix, *L0 = ws.p + 4 * npix, *L1 = ws.p + 5 * npix;
+    emu::launch(dim3(cdivu((long long)npix, 256)), dim3(256), 0, [&] { lbgr2lab_kernel(src.p, L0, ab0, npix, cb.p, t.cf); });
+    emu::launch(grid, dim3(32 * NLM_NW), 0, [&] { nlm_kernel<1>(L0, L1, H, W, w0.p); });
+    emu::launch(grid, dim3(32 * NLM_NW), 0, [&] { nlm_kernel<2>(ab0, ab1, H, W, w1.p); });
+    emu::launch(dim3(cdivu((long long)npix, 256)), dim3(256), 0, [&] { lab2lbgr_kernel(L1, ab1, dst.p, npix, yf.p, t.cf); });
+  }
+  std::printf("denoise %dx%d C=%d ok\n", H, W, C);
+}
+
+int main(int argc, char **argv) {
+  if (argc > 1 && std::string(argv[1]) == "denoise") {
+    run_denoise(30, 28, 1);    // two tile columns (26 + 2), reflect-101 on every side
+    run_denoise(20, 40, 3);    // colored route: Lab, NLM on L and on (a, b), back
+    std::printf("emulated kernels: sanitizer run complete\n");
+    return 0;
+  }
   run_image(2, 64, 128, 3);    // vector histogram path, cell kernel, interior + border tiles
   run_image(1, 96, 256, 1);
   run_image(1, 50, 70, 3);     // reflect-101 tile extension, unaligned widths, scalar paths
