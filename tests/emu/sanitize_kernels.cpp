@@ -8,6 +8,7 @@
 // Results are not compared here (tests/test_emu_*_kernels.py do that); the sanitizers are the check.
 #include "cuda_emu.h"
 #include "../../handwritten-ocr_b200/csrc/image_fast.cuh"
+#include "../../handwritten-ocr_b200/csrc/image_general.cuh"
 #include "../../handwritten-ocr_b200/csrc/textops_kernels.cuh"
 #include "../../handwritten-ocr_b200/csrc/denoise_kernels.cuh"
 
@@ -93,6 +94,46 @@ static void run_image(int n, int H, int W, int C) {
   std::printf("image n=%d %dx%d C=%d ok\n", n, H, W, C);
 }
 
+// the general-shape kernels on sizes the fast paths refuse
+static void run_general(int H, int W, int C) {
+  const size_t px = (size_t)H * W;
+  Buf<uint8_t> src(px * C), dst(px * C, 0), gray(px, 0), out1(px, 0), tmp(px, 0), lut(64 * 256, 0);
+  paper(src.p, px * C);
+  if (C == 3) {
+    emu::launch(dim3(cdivu((long long)((px + 15) / 16), 256)), dim3(256), 0, [&] { rgb2gray_kernel(src.p, gray.p, px); });
+  } else {
+    std::copy(src.p, src.p + px, gray.p);
+  }
+  emu::launch(dim3(cdivu((long long)W * C, 256), H, 1), dim3(256), 0, [&] { sharpen_kernel(src.p, dst.p, H, W, C); });
+  if ((W * C) % 4 == 0 && W >= 4)
+    emu::launch(dim3(cdivu((long long)W * C / 4, 256), H, 1), dim3(256), 0, [&] { sharpen4_kernel(src.p, dst.p, H, W, C); });
+  int We = W, He = H;
+  if (!(W % 8 == 0 && H % 8 == 0)) { We = W + (8 - W % 8); He = H + (8 - H % 8); }
+  const int tw = We / 8, th = He / 8;
+  if (tw >= 1 && th >= 1 && tw <= W && th <= H) {
+    const int area = tw * th;
+    int clip = (int)(3.0 * area / 256.0);
+    if (clip < 1) clip = 1;
+    const float ls = 255.0f / (float)area, itw = 1.0f / (float)tw, ith = 1.0f / (float)th;
+    emu::launch(dim3(64, 1), dim3(256), 0, [&] { clahe_hist_lut_kernel<1>(gray.p, nullptr, lut.p, H, W, tw, th, clip, ls, 0); });
+    emu::launch(dim3(cdivu(W, 256), H, 1), dim3(256), 0, [&] { clahe_apply_kernel(gray.p, out1.p, lut.p, H, W, itw, ith); });
+    if (W % 4 == 0)
+      emu::launch(dim3(cdivu(W / 4, 256), H, 1), dim3(256), 0, [&] { clahe_apply4_kernel(gray.p, out1.p, lut.p, H, W, itw, ith); });
+  }
+  {
+    Buf<int32_t> ext((size_t)H * 3, 0), hull((size_t)(4 * H + 8) * 2, 0), nz(1, 0);
+    Buf<double> angle(1, 0), M(6, 0);
+    emu::launch(dim3(cdivu(H, 8)), dim3(256), 0, [&] { dark_extents_kernel(src.p, ext.p, H, W, C, H); });
+    emu::launch(dim3(1), dim3(32), 0, [&] { deskew_angle_seq_kernel(ext.p, H, W, angle.p, M.p, hull.p); });
+    if (W >= 4) {
+      emu::launch(dim3(cdivu(W, 256), H, 1), dim3(256), 0, [&] { rl_thresh_kernel(src.p, out1.p, H, W, C); });
+      emu::launch(dim3(H), dim3(256), (2 * (size_t)W + 1) * sizeof(int), [&] { rl_open_row_kernel(out1.p, tmp.p, W, W / 4); });
+      emu::launch(dim3(cdivu(W, 256), H, 1), dim3(256), 0, [&] { rl_dilate_v_kernel(tmp.p, out1.p, nz.p, H, W); });
+    }
+  }
+  std::printf("general %dx%d C=%d ok\n", H, W, C);
+}
+
 static void run_text() {
   const int lens[][2] = {{1, 1}, {33, 31}, {64, 1}, {0, 5}, {70, 100}, {200, 255}};
   const int np = 6;
@@ -159,6 +200,13 @@ int main(int argc, char **argv) {
   if (argc > 1 && std::string(argv[1]) == "denoise") {
     run_denoise(30, 28, 1);    // two tile columns (26 + 2), reflect-101 on every side
     run_denoise(20, 40, 3);    // colored route: Lab, NLM on L and on (a, b), back
+    std::printf("emulated kernels: sanitizer run complete\n");
+    return 0;
+  }
+  if (argc > 1 && std::string(argv[1]) == "general") {
+    run_general(23, 27, 3);
+    run_general(24, 36, 1);
+    run_general(9, 13, 1);
     std::printf("emulated kernels: sanitizer run complete\n");
     return 0;
   }

@@ -290,3 +290,66 @@ def test_fuzz_odd_sizes_binarize_and_clahe_luts(emu):
         assert np.array_equal(lut[0].reshape(-1), np.asarray(R.clahe_luts(g)[0], np.uint8).reshape(-1)), (H, W, C)
         if rc == 0:
             assert np.array_equal(dst[0], R.clahe(g)), (H, W, C)
+
+
+# ───────────── the general-shape kernels (csrc/image_general.cuh: any width, any alignment) ─────────────
+def test_general_kernels_odd_widths(emu):
+    """rgb2gray (16-pixel path + scalar tail), both general sharpen kernels, both general CLAHE apply kernels, the
+    general extent kernel + one-thread hull scan, and the ruled-line mask, on sizes the fast paths refuse."""
+    rng = np.random.default_rng(61)
+    # rgb2gray: pixel counts around the 16-pixel vector
+    for H, W in [(3, 5), (4, 16), (7, 37)]:
+        img = page(rng, H, W, 3, "noise")
+        src = aligned((2, H, W, 3))
+        src[0], src[1] = img, img[::-1]
+        dst = aligned((2, H, W), fill=1)
+        assert emu.emu_rgb2gray(P(src), P(dst), 2, H, W) == 0
+        assert np.array_equal(dst[0], R.rgb2gray(img)) and np.array_equal(dst[1], R.rgb2gray(img[::-1]))
+    # sharpen: byte kernel on any width, word kernel where the row bytes are a multiple of 4
+    for (H, W), C in [((5, 7), 3), ((4, 9), 1), ((6, 12), 3), ((3, 8), 1), ((2, 2), 1)]:
+        img = page(rng, H, W, C, "noise")
+        src = aligned((1,) + img.shape)
+        src[0] = img
+        for variant in (0, 1):
+            dst = aligned(src.shape, fill=3)
+            rc = emu.emu_sharpen_general(P(src), P(dst), 1, H, W, C, variant)
+            if variant == 1 and ((W * C) % 4 or W < 4):
+                assert rc == -1
+                continue
+            assert rc == 0 and np.array_equal(dst[0], R.sharpen(img)), (H, W, C, variant)
+    # CLAHE apply: per pixel (odd width, reflect-101 extension) and four pixels per thread
+    for (H, W), variant in [((23, 27), 0), ((24, 36), 1), ((16, 16), 1), ((31, 36), 0)]:
+        img = page(rng, H, W, 1, "paper")
+        src = aligned((1, H, W))
+        src[0] = img
+        dst = aligned((1, H, W), fill=4)
+        lut = aligned((1, 64, 256))
+        assert emu.emu_clahe_general(P(src), P(dst), P(lut), 1, H, W, variant) == 0
+        assert np.array_equal(dst[0], R.clahe(img)), (H, W, variant)
+    # deskew angle by the general extent kernel + the sequential scan (global-memory hull): odd width, RGB and gray
+    for (H, W), C in [((90, 75), 3), ((70, 101), 1)]:
+        img = skewed_page(rng, H, W, C, 3.0)
+        src = aligned((1,) + img.shape)
+        src[0] = img
+        angle = np.zeros(1, np.float64)
+        M = np.zeros((1, 6), np.float64)
+        ext = np.zeros((1, H, 3), np.int32)
+        hull = np.zeros((1, (4 * H + 8) * 2), np.int32)
+        assert emu.emu_deskew_angle_general(P(src), 1, H, W, C, P(angle), P(M), P(ext), P(hull)) == 0
+        g = R.rgb2gray(img) if C == 3 else img
+        assert angle[0] == R.deskew_angle(g), (H, W, C)
+    # ruled-line mask of remove_lines
+    for (H, W), C in [((40, 64), 3), ((33, 50), 1)]:
+        img = page(rng, H, W, C, "paper")
+        img[10, 3:W - 3] = 60
+        img[25, 5:W - 8] = 70                                       # two ruled lines
+        src = aligned((1,) + img.shape)
+        src[0] = img
+        mask = aligned((1, H, W), fill=9)
+        tmp = aligned((1, H, W), fill=9)
+        nz = np.zeros(1, np.int32)
+        assert emu.emu_remove_lines_mask(P(src), P(mask), P(nz), P(tmp), 1, H, W, C) == 0
+        g = R.rgb2gray(img) if C == 3 else img
+        want = R.lines_mask(g)
+        assert np.array_equal(mask[0], want), (H, W, C)
+        assert bool(nz[0]) == bool(want.any()) and want.any()
