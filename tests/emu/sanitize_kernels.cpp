@@ -11,6 +11,7 @@
 #include "../../handwritten-ocr_b200/csrc/image_general.cuh"
 #include "../../handwritten-ocr_b200/csrc/textops_kernels.cuh"
 #include "../../handwritten-ocr_b200/csrc/denoise_kernels.cuh"
+#include "../../handwritten-ocr_b200/csrc/resize_kernels.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -134,6 +135,35 @@ static void run_general(int H, int W, int C) {
   std::printf("general %dx%d C=%d ok\n", H, W, C);
 }
 
+static void run_resize(int H, int W, int C, int oh, int ow) {
+  const size_t n = (size_t)H * W * C;
+  Buf<uint8_t> src(n), tmp((size_t)H * ow * C, 0), dst((size_t)oh * ow * C, 0);
+  AxisWeights tx, ty;
+  compute_axis_weights(W, ow, &tx);
+  compute_axis_weights(H, oh, &ty);
+  Buf<int32_t> xmin(tx.xmin.size(), 0), xsize(tx.xsize.size(), 0), ymin(ty.xmin.size(), 0), ysize(ty.xsize.size(), 0);
+  Buf<int16_t> wx(tx.w.size(), 0), wy(ty.w.size(), 0);
+  std::copy(tx.xmin.begin(), tx.xmin.end(), xmin.p);
+  std::copy(tx.xsize.begin(), tx.xsize.end(), xsize.p);
+  std::copy(tx.w.begin(), tx.w.end(), wx.p);
+  std::copy(ty.xmin.begin(), ty.xmin.end(), ymin.p);
+  std::copy(ty.xsize.begin(), ty.xsize.end(), ysize.p);
+  std::copy(ty.w.begin(), ty.w.end(), wy.p);
+  emu::launch(dim3(cdivu((long long)ow * C, 256), H), dim3(256), 0,
+              [&] { resize_h_kernel(src.p, tmp.p, H, W, C, ow, xmin.p, xsize.p, wx.p, tx.kmax, tx.prec); });
+  emu::launch(dim3(cdivu((long long)ow * C, 256), oh, 1), dim3(256), 0,
+              [&] { resize_v_kernel(tmp.p, dst.p, H, ow * C, oh, ymin.p, ysize.p, wy.p, ty.kmax, ty.prec); });
+  if (oh % 28 == 0 && ow % 28 == 0) {
+    const int gh = oh / 14, gw = ow / 14;
+    const long long total = (long long)gh * gw * 3 * 14 * 14;
+    Buf<float> pv((size_t)gh * gw * 1176, 0);
+    emu::launch(dim3(cdivu(total, 256)), dim3(256), 0, [&] {
+      normalize_patchify_kernel<float>(dst.p, pv.p, oh, ow, C, gh, gw, nullptr, total, 122.77f, 116.75f, 104.09f, 68.5f, 66.63f, 70.32f);
+    });
+  }
+  std::printf("resize %dx%d C=%d -> %dx%d ok\n", H, W, C, oh, ow);
+}
+
 static void run_text() {
   const int lens[][2] = {{1, 1}, {33, 31}, {64, 1}, {0, 5}, {70, 100}, {200, 255}};
   const int np = 6;
@@ -200,6 +230,12 @@ int main(int argc, char **argv) {
   if (argc > 1 && std::string(argv[1]) == "denoise") {
     run_denoise(30, 28, 1);    // two tile columns (26 + 2), reflect-101 on every side
     run_denoise(20, 40, 3);    // colored route: Lab, NLM on L and on (a, b), back
+    std::printf("emulated kernels: sanitizer run complete\n");
+    return 0;
+  }
+  if (argc > 1 && std::string(argv[1]) == "resize") {
+    run_resize(37, 53, 3, 28, 56);
+    run_resize(30, 20, 1, 56, 28);
     std::printf("emulated kernels: sanitizer run complete\n");
     return 0;
   }
