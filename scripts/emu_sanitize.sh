@@ -15,10 +15,12 @@ ASAN_OPTIONS=detect_leaks=0 ./_build/sanitize_asan > "$out/emu_asan.log" 2>&1; a
 ASAN_OPTIONS=detect_leaks=0 ./_build/sanitize_asan denoise >> "$out/emu_asan.log" 2>&1; a=$((a + $?))
 ASAN_OPTIONS=detect_leaks=0 ./_build/sanitize_asan general >> "$out/emu_asan.log" 2>&1; a=$((a + $?))
 ASAN_OPTIONS=detect_leaks=0 ./_build/sanitize_asan resize >> "$out/emu_asan.log" 2>&1; a=$((a + $?))
+ASAN_OPTIONS=detect_leaks=0 ./_build/sanitize_asan dense >> "$out/emu_asan.log" 2>&1; a=$((a + $?))
 TSAN_OPTIONS="halt_on_error=0" ./_build/sanitize_tsan > "$out/emu_tsan.log" 2>&1; t=$?
 TSAN_OPTIONS="halt_on_error=0" ./_build/sanitize_tsan denoise >> "$out/emu_tsan.log" 2>&1; t=$((t + $?))
 TSAN_OPTIONS="halt_on_error=0" ./_build/sanitize_tsan general >> "$out/emu_tsan.log" 2>&1; t=$((t + $?))
 TSAN_OPTIONS="halt_on_error=0" ./_build/sanitize_tsan resize >> "$out/emu_tsan.log" 2>&1; t=$((t + $?))
+TSAN_OPTIONS="halt_on_error=0" ./_build/sanitize_tsan dense >> "$out/emu_tsan.log" 2>&1; t=$((t + $?))
 ./_build/race_bad > "$out/emu_tsan_control_bad.log" 2>&1
 ./_build/race_ok > "$out/emu_tsan_control_ok.log" 2>&1
 echo "asan+ubsan: exit $a, $(grep -cE 'ERROR: AddressSanitizer|runtime error' "$out/emu_asan.log") reports"

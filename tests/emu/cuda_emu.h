@@ -150,6 +150,13 @@ static inline __nv_bfloat16 __float2bfloat16_rn(float f) {          // round to 
   u += 0x7fffu + ((u >> 16) & 1u);
   return __nv_bfloat16{(uint16_t)(u >> 16)};
 }
+static inline float __bfloat162float(__nv_bfloat16 h) {
+  const uint32_t u = (uint32_t)h.x << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }     // CUDA's rsqrtf is within 2 ulp of this; not bit-pinned
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }

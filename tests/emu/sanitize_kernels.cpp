@@ -12,6 +12,7 @@
 #include "../../handwritten-ocr_b200/csrc/textops_kernels.cuh"
 #include "../../handwritten-ocr_b200/csrc/denoise_kernels.cuh"
 #include "../../handwritten-ocr_b200/csrc/resize_kernels.cuh"
+#include "../../handwritten-ocr_b200/csrc/dense_kernels.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -164,6 +165,56 @@ static void run_resize(int H, int W, int C, int oh, int ow) {
   std::printf("resize %dx%d C=%d -> %dx%d ok\n", H, W, C, oh, ow);
 }
 
+static void run_dense() {
+  const int rows = 11, dim = 256;
+  Buf<uint16_t> x((size_t)rows * dim), w(dim), y((size_t)rows * dim, 0);
+  for (size_t i = 0; i < x.n; ++i) x.p[i] = (uint16_t)(0x3f00 + (rng() & 0xff));     // bf16 values around 0.5 .. 1
+  for (size_t i = 0; i < w.n; ++i) w.p[i] = (uint16_t)(0x3f80 + (rng() & 0x3f));
+  emu::launch(dim3(rows), dim3(256), 0, [&] { rmsnorm_kernel((const bf16 *)x.p, dim, (const bf16 *)w.p, (bf16 *)y.p, dim, dim, 1e-6f); });
+  emu::launch(dim3(cdivu(rows, 8)), dim3(256), 0, [&] { rmsnorm_warp_kernel((const bf16 *)x.p, dim, (const bf16 *)w.p, (bf16 *)y.p, dim, rows, dim, 1e-6f); });
+  {
+    const int S = 7, heads = 2, hd = 32;
+    Buf<uint16_t> qkv((size_t)S * 3 * heads * hd);
+    Buf<float> c((size_t)S * hd, 0), sn((size_t)S * hd, 0);            // tables are [S, hd]: both halves of a head
+    emu::launch(dim3(cdivu(S * 2 * heads * (hd / 16), 256)), dim3(256), 0, [&] { rope_vision_vec_kernel((bf16 *)qkv.p, S, heads, hd, c.p, sn.p); });
+    emu::launch(dim3(cdivu((long long)S * 2 * heads * (hd / 2), 256)), dim3(256), 0, [&] { rope_vision_kernel((bf16 *)qkv.p, S, heads, hd, c.p, sn.p); });
+  }
+  {
+    const int T = 5, nq = 4, nkv = 2, hd = 32;
+    Buf<uint16_t> q((size_t)T * nq * hd), k((size_t)T * nkv * hd), c((size_t)T * hd, 0x3f80), sn((size_t)T * hd, 0);
+    emu::launch(dim3(cdivu(T * (nq + nkv) * (hd / 16), 256)), dim3(256), 0,
+                [&] { rope_text_vec_kernel((bf16 *)q.p, nq * hd, (bf16 *)k.p, nkv * hd, T, nq, nkv, hd, (const bf16 *)c.p, (const bf16 *)sn.p); });
+    emu::launch(dim3(cdivu((long long)T * (nq + nkv) * (hd / 2), 256)), dim3(256), 0,
+                [&] { rope_text_kernel((bf16 *)q.p, nq * hd, (bf16 *)k.p, nkv * hd, T, nq, nkv, hd, (const bf16 *)c.p, (const bf16 *)sn.p); });
+    Buf<int32_t> ctx(3, 40), delta(3, 2);
+    Buf<float> invf(hd / 2, 0);
+    Buf<uint16_t> ct((size_t)3 * hd, 0), st((size_t)3 * hd, 0);
+    emu::launch(dim3(cdivu(3 * (hd / 2), 128)), dim3(128), 0,
+                [&] { decode_rope_table_kernel(ctx.p, delta.p, invf.p, 3, hd, (bf16 *)ct.p, (bf16 *)st.p); });
+    // paged KV write: sequences of 5 and 3 tokens... T = 5 here: one sequence of 5 tokens over two pages of 4
+    Buf<int32_t> bt(2, 0), cu(2, 0);
+    bt.p[0] = 1; bt.p[1] = 0; cu.p[0] = 0; cu.p[1] = T;
+    Buf<uint16_t> kc((size_t)2 * nkv * 4 * hd, 0), vc((size_t)2 * nkv * 4 * hd, 0);
+    emu::launch(dim3(cdivu((long long)T * (nkv * hd / 8), 256)), dim3(256), 0, [&] {
+      kv_write_prefill_kernel((const bf16 *)k.p, nkv * hd, (const bf16 *)k.p, nkv * hd, (bf16 *)kc.p, (bf16 *)vc.p, bt.p, 2, cu.p, 1, T, 4,
+                              nkv * hd / 8, hd / 8);
+    });
+  }
+  {
+    const int B = 3, V = 1003, ld = 1008, max_new = 4;
+    Buf<uint16_t> lg((size_t)B * ld);
+    for (size_t i = 0; i < lg.n; ++i) lg.p[i] = (uint16_t)(0x3c00 + (rng() & 0x3ff));
+    Buf<int32_t> out((size_t)B * max_new, 0), nxt(B, 0), fin(B, 0), ctx(B, 5), step(1, 1);
+    emu::launch(dim3(B), dim3(512), 0, [&] { argmax_step_kernel((const bf16 *)lg.p, ld, V, 7, 7, max_new, out.p, nxt.p, fin.p, ctx.p, step.p, 1); });
+    Buf<int32_t> si(2, 0), di(2, 0);
+    si.p[0] = 2; si.p[1] = 0; di.p[0] = 0; di.p[1] = 1;
+    Buf<uint16_t> dst((size_t)2 * 64, 0);
+    emu::launch(dim3(1), dim3(256), 0, [&] { rows_copy_kernel((const bf16 *)lg.p, ld, si.p, (bf16 *)dst.p, 64, di.p, 2, 8); });
+    emu::launch(dim3(1), dim3(256), 0, [&] { residual_add_kernel((bf16 *)dst.p, 64, (const bf16 *)lg.p, ld, 2, 8); });
+  }
+  std::printf("dense ok\n");
+}
+
 static void run_text() {
   const int lens[][2] = {{1, 1}, {33, 31}, {64, 1}, {0, 5}, {70, 100}, {200, 255}};
   const int np = 6;
@@ -230,6 +281,11 @@ int main(int argc, char **argv) {
   if (argc > 1 && std::string(argv[1]) == "denoise") {
     run_denoise(30, 28, 1);    // two tile columns (26 + 2), reflect-101 on every side
     run_denoise(20, 40, 3);    // colored route: Lab, NLM on L and on (a, b), back
+    std::printf("emulated kernels: sanitizer run complete\n");
+    return 0;
+  }
+  if (argc > 1 && std::string(argv[1]) == "dense") {
+    run_dense();
     std::printf("emulated kernels: sanitizer run complete\n");
     return 0;
   }
