@@ -91,3 +91,72 @@ def test_the_model_can_fail_one_slot_loses_cells():
     """Control: with a single slot a fast rank's call k + 1 overwrites the cell a slow peer has not read yet."""
     bad = [run_model(4, units=2, calls=12, slots=1, seed=s) for s in range(40)]
     assert any(r != "ok" for r in bad), "the one-slot mutation was never caught: the model checks nothing"
+
+
+# ───────────── the flag + pull protocol (allreduce_residual_kernel, fused route 1, tp_argmax_step_kernel) ─────────────
+def run_pull_model(world: int, units: int, calls: int, slots: int, seed: int, max_steps: int = 400000):
+    """Each unit writes its partial into ITS OWN slot k % slots (visible before the flag: st.release), announces k to every
+    peer (a flag store that arrives after an arbitrary delay, in order per channel), waits until its own flags from all
+    peers are >= k, then reads the peers' slots REMOTELY at some later moment -- it sees whatever the slot holds then."""
+    rng = random.Random(seed)
+    slot_data = [[[None] * units for _ in range(slots)] for _ in range(world)]     # slot_data[rank][slot][unit]
+    flag = [[[0] * units for _ in range(world)] for _ in range(world)]             # flag[dst][src][unit]
+    chan = {(s, d): [] for s in range(world) for d in range(world) if s != d}
+    call = [1] * world
+    stage = [[0] * units for _ in range(world)]        # 0 = not announced, 1 = announced / polling, 2 = flags seen, 3 = done
+    finished = [False] * world
+    for _ in range(max_steps):
+        actions = []
+        for r in range(world):
+            if finished[r]:
+                continue
+            for u in range(units):
+                if stage[r][u] < 3:
+                    actions.append(("unit", r, u))
+            if all(s == 3 for s in stage[r]):
+                actions.append(("next", r, 0))
+        for key, q in chan.items():
+            if q:
+                actions.append(("deliver", key, 0))
+        if not actions:
+            return "ok" if all(finished) else "deadlock: nothing enabled"
+        kind, a, b = rng.choice(actions)
+        if kind == "deliver":
+            s, d = a
+            u, k = chan[a].pop(0)
+            flag[d][s][u] = k
+        elif kind == "unit":
+            r, u, k = a, b, call[a]
+            if stage[r][u] == 0:
+                slot_data[r][k % slots][u] = (r, k, u)
+                for d in range(world):
+                    if d != r:
+                        chan[(r, d)].append((u, k))
+                stage[r][u] = 1
+            elif stage[r][u] == 1:
+                if all(flag[r][s][u] >= k for s in range(world) if s != r):
+                    stage[r][u] = 2
+            else:                                       # the remote reads happen now
+                for s in range(world):
+                    if s != r and slot_data[s][k % slots][u] != (s, k, u):
+                        return f"rank {r} call {k} unit {u}: read {slot_data[s][k % slots][u]} from rank {s}'s slot"
+                stage[r][u] = 3
+        else:
+            r = a
+            if call[r] == calls:
+                finished[r] = True
+            else:
+                call[r] += 1
+                stage[r] = [0] * units
+    return "step budget exhausted"
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_two_slot_flag_and_pull_exchange_is_safe(world):
+    for seed in range(40 if world == 8 else 100):
+        assert run_pull_model(world, units=3, calls=16, slots=2, seed=seed) == "ok", (world, seed)
+
+
+def test_pull_model_can_fail_with_one_slot():
+    bad = [run_pull_model(4, units=2, calls=12, slots=1, seed=s) for s in range(40)]
+    assert any(r != "ok" for r in bad)
